@@ -1,0 +1,391 @@
+// tcgen05 implicit-GEMM convolution for sm_100a.
+//
+//   D[128 pixels x BN channels] (TMEM, fp32) += A[128 x 64] (smem, fp16) * B[BN x 64]^T (smem, fp16)
+//
+// A tiles are fetched by TMA straight from the NHWC activation view as a 4-D box
+// {64 channels, TW, TH, TN}; a filter tap (ky,kx) is just a shifted box origin and the conv's zero
+// padding is TMA out-of-bounds fill, so no im2col buffer ever exists.  B tiles are rows of the
+// folded fp16 filter [cout_pad][taps][cin_pad].  Both land in 128B-swizzled K-major smem; one
+// elected thread issues tcgen05.mma (M=128, N=BN, K=16); accumulators live in TMEM and four
+// epilogue warps read them back with tcgen05.ld, apply bias/activation/affine/residual and store
+// NHWC fp16.  Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issue, 2..5 = epilogue.
+#include "kernels.h"
+
+#include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+
+namespace b200ocr {
+
+namespace {
+
+constexpr int kStagesMax = 4;
+constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 fp16
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major, 128B swizzle: 8-row atoms of 1024 B (SBO = 1024), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return uint64_t((saddr >> 4) & 0x3FFF) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ float act_fn(float v, int act, float a, float b) {
+  switch (act) {
+    case 1: return fmaxf(v, 0.f);
+    case 2: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    case 3: return v / (1.f + __expf(-v));
+    case 4: return fminf(fmaxf(v * a + b, 0.f), 1.f);
+    case 5: return 1.f / (1.f + __expf(-v));
+    default: return v;
+  }
+}
+
+struct ConvTcArgs {
+  // tile geometry over the output view (for 1x1 convs the view is flattened to n=1,h=1,w=P)
+  int on, oh, ow;          // output dims as tiled
+  int tw, th, tn;          // box: tw*th*tn <= 128 rows
+  int tiles_x, tiles_y;    // tiles_n = gridDim.x / (tiles_x*tiles_y)
+  int kh, kw, ph, pw;
+  int cin, cin_pad;        // logical input channels; weight row stride per tap
+  int bn;                  // N tile (multiple of 16, <= 256)
+  int tmem_cols;           // power of two >= max(32, bn)
+  int stages;
+  int cout;                // logical output channels
+  __half* out;
+  int out_pitch;
+  const float* bias;
+  Epi epi;
+};
+
+__global__ void __launch_bounds__(192)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const ConvTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  // [barriers | tmem ptr] then 1024-aligned tiles
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty_bar = full_bar + kStagesMax;
+  uint64_t* tmem_full = empty_bar + kStagesMax;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  const uint32_t tiles_base = (smem_u32(smem_raw) + 128 + 1023) & ~1023u;
+  uint8_t* tiles = smem_raw + (tiles_base - smem_u32(smem_raw));
+  const int stage_bytes = kATileBytes + a.bn * 128;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tx = t % a.tiles_x; t /= a.tiles_x;
+  const int ty = t % a.tiles_y; t /= a.tiles_y;
+  const int x0 = tx * a.tw, y0 = ty * a.th, n0 = t * a.tn;
+  const int nblk = blockIdx.y;  // N tile index
+
+  const int kchunks = (a.cin + 63) >> 6;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(uint32_t(a.tmem_cols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = uint32_t(a.tw * a.th * a.tn * 128 + a.bn * 128);
+      int it = 0;
+      for (int ky = 0; ky < a.kh; ++ky)
+        for (int kx = 0; kx < a.kw; ++kx)
+          for (int kc = 0; kc < kchunks; ++kc, ++it) {
+            const int s = it % a.stages;
+            const uint32_t ph = uint32_t(it / a.stages) & 1u;
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            uint8_t* sa = tiles + size_t(s) * stage_bytes;
+            uint8_t* sb = sa + kATileBytes;
+            mbar_expect_tx(&full_bar[s], tx_bytes);
+            tma_load_4d(&tmA, &full_bar[s], sa, kc * 64, x0 + kx - a.pw, y0 + ky - a.ph, n0);
+            tma_load_2d(&tmB, &full_bar[s], sb, (ky * a.kw + kx) * a.cin_pad + kc * 64, nblk * a.bn);
+          }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (uint32_t(a.bn >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+      int it = 0;
+      for (int tap = 0; tap < a.kh * a.kw; ++tap)
+        for (int kc = 0; kc < kchunks; ++kc, ++it) {
+          const int s = it % a.stages;
+          const uint32_t ph = uint32_t(it / a.stages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = tiles_base + uint32_t(s) * stage_bytes;
+          const uint32_t sb = sa + kATileBytes;
+          const int rem = a.cin - kc * 64;
+          const int k16 = rem >= 64 ? 4 : (rem + 15) >> 4;
+          for (int k = 0; k < k16; ++k)
+            umma_f16(tmem_base, umma_desc(sa + k * 32), umma_desc(sb + k * 32), idesc, (it | k) != 0);
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+        }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; row == lane of D
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int rows = a.tw * a.th * a.tn;
+    const int tw_ = r % a.tw, th_ = (r / a.tw) % a.th, tn_ = r / (a.tw * a.th);
+    const int x = x0 + tw_, y = y0 + th_, n = n0 + tn_;
+    const bool valid = r < rows && x < a.ow && y < a.oh && n < a.on;
+    const long pix = (long(n) * a.oh + y) * a.ow + x;
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int c8lim = (a.cout + 7) & ~7;
+    const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
+    for (int col = 0; col < a.bn; col += 16) {
+      uint32_t v[16];
+      tmem_ld16(trow + col, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int c0 = nblk * a.bn + col;
+      if (!valid || c0 >= c8lim) continue;
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + a.bias[c0 + i];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = a.epi.s2 * act_fn(f[i], a.epi.act, a.epi.a, a.epi.b) + a.epi.t2;
+      const bool second = c0 + 8 < c8lim;
+      if (a.epi.res) {
+        const __half* rp = a.epi.res + pix * a.epi.res_pitch + c0;
+        uint4 r0 = *reinterpret_cast<const uint4*>(rp);
+        const __half2* h = reinterpret_cast<const __half2*>(&r0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 p = __half22float2(h[i]); f[2 * i] += p.x; f[2 * i + 1] += p.y; }
+        if (second) {
+          uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
+          const __half2* g = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { float2 p = __half22float2(g[i]); f[8 + 2 * i] += p.x; f[8 + 2 * i + 1] += p.y; }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (c0 + i >= a.cout) f[i] = 0.f;
+      __half* op = a.out + pix * a.out_pitch + c0;
+      uint4 o0, o1;
+      __half2* h0 = reinterpret_cast<__half2*>(&o0);
+      __half2* h1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        h0[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+        h1[i] = __floats2half2_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
+      }
+      *reinterpret_cast<uint4*>(op) = o0;
+      if (second) *reinterpret_cast<uint4*>(op + 8) = o1;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(uint32_t(a.tmem_cols))
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !p) {
+      fprintf(stderr, "b200ocr: cuTensorMapEncodeTiled is unavailable (driver too old?)\n");
+      abort();
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+void encode(CUtensorMap* tm, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+            const cuuint32_t* box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, cuuint32_t(rank), base, dims, strides_bytes,
+                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "b200ocr: cuTensorMapEncodeTiled failed with %d (rank %d dims %llu %llu box %u %u)\n", int(r),
+            rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    abort();
+  }
+}
+
+}  // namespace
+
+struct ConvTcPlanImpl {
+  CUtensorMap tmA, tmB;
+  ConvTcArgs args;
+  dim3 grid;
+  size_t smem;
+};
+
+bool conv_tc_eligible(const TV& in, const TV& out, const ConvGeom& g) {
+  if (g.sh != 1 || g.sw != 1) return false;
+  if (in.c < 8) return false;  // stems (C_in = 3) stay on the CUDA-core kernel
+  if (in.pitch % 8 || out.pitch % 8) return false;
+  if ((reinterpret_cast<uintptr_t>(in.p) & 15) || (reinterpret_cast<uintptr_t>(out.p) & 15)) return false;
+  if (out.h != in.h + 2 * g.ph - g.kh + 1 || out.w != in.w + 2 * g.pw - g.kw + 1) return false;
+  return true;
+}
+
+ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, const ConvGeom& g) {
+  TV in = in_, out = out_;
+  const bool pointwise = g.kh == 1 && g.kw == 1 && g.ph == 0 && g.pw == 0;
+  if (pointwise) {  // plain GEMM over all pixels
+    const long P = long(in.n) * in.h * in.w;
+    in.n = out.n = 1;
+    in.h = out.h = 1;
+    in.w = out.w = int(P);
+  }
+  ConvTcArgs a{};
+  a.on = out.n; a.oh = out.h; a.ow = out.w;
+  // pick the box that wastes the fewest of the 128 MMA rows
+  double best = -1;
+  for (int tw = 1; tw <= 128 && tw <= out.w; ++tw) {
+    int th = 128 / tw;
+    if (th > out.h) th = out.h;
+    int tn = 1;
+    if (tw == out.w && th == out.h) { tn = 128 / (tw * th); if (tn > out.n) tn = out.n; }
+    const long tiles = long((out.w + tw - 1) / tw) * ((out.h + th - 1) / th) * ((out.n + tn - 1) / tn);
+    const double eff = double(long(out.n) * out.h * out.w) / double(tiles * 128);
+    if (eff > best + 1e-9) { best = eff; a.tw = tw; a.th = th; a.tn = tn; }
+  }
+  a.tiles_x = (out.w + a.tw - 1) / a.tw;
+  a.tiles_y = (out.h + a.th - 1) / a.th;
+  const int tiles_n = (out.n + a.tn - 1) / a.tn;
+  a.kh = g.kh; a.kw = g.kw; a.ph = g.ph; a.pw = g.pw;
+  a.cin = in.c; a.cin_pad = g.cin_pad;
+  const int n_tiles = (g.cout_pad + 255) / 256;
+  a.bn = ((g.cout_pad + n_tiles - 1) / n_tiles + 15) & ~15;
+  a.tmem_cols = 32;
+  while (a.tmem_cols < a.bn) a.tmem_cols <<= 1;
+  const int k_iters = g.kh * g.kw * ((in.c + 63) / 64);
+  a.stages = k_iters < kStagesMax ? k_iters : kStagesMax;
+  a.cout = out.c;
+  a.out = out.p;
+  a.out_pitch = out.pitch;
+
+  auto* impl = new ConvTcPlanImpl();
+  const int c8 = (in.c + 7) & ~7;
+  cuuint64_t dA[4] = {cuuint64_t(c8), cuuint64_t(in.w), cuuint64_t(in.h), cuuint64_t(in.n)};
+  cuuint64_t sA[3] = {cuuint64_t(in.pitch) * 2, cuuint64_t(in.pitch) * 2 * in.w,
+                      cuuint64_t(in.pitch) * 2 * in.w * in.h};
+  cuuint32_t bA[4] = {64, cuuint32_t(a.tw), cuuint32_t(a.th), cuuint32_t(a.tn)};
+  encode(&impl->tmA, in.p, 4, dA, sA, bA);
+  const int taps = g.kh * g.kw;
+  cuuint64_t dB[2] = {cuuint64_t(taps) * g.cin_pad, cuuint64_t(g.cout_pad)};
+  cuuint64_t sB[1] = {cuuint64_t(taps) * g.cin_pad * 2};
+  cuuint32_t bB[2] = {64, cuuint32_t(a.bn)};
+  encode(&impl->tmB, const_cast<__half*>(w), 2, dB, sB, bB);
+  impl->args = a;
+  impl->grid = dim3(unsigned(a.tiles_x * a.tiles_y * tiles_n), unsigned(n_tiles));
+  impl->smem = size_t(a.stages) * (kATileBytes + a.bn * 128) + 1024 + 128;
+  static size_t configured = 0;
+  if (impl->smem > configured) {
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = 200 * 1024;
+  }
+  ConvTcPlan p;
+  p.impl = impl;
+  return p;
+}
+
+void free_conv_tc_plan(ConvTcPlan* p) {
+  delete p->impl;
+  p->impl = nullptr;
+}
+
+void launch_conv_tc(const ConvTcPlan& p, const float* bias, const Epi& e, cudaStream_t s) {
+  ConvTcArgs a = p.impl->args;
+  a.bias = bias;
+  a.epi = e;
+  conv_tc_kernel<<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a);
+}
+
+}  // namespace b200ocr

@@ -1,0 +1,395 @@
+#include "engine.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+
+namespace b200ocr {
+
+void cuda_check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+struct Net::Inst {
+  int n = 0, h = 0, w = 0;
+  std::vector<Shape3> ts;            // per tensor
+  std::vector<int> splits, hw;       // per tensor (Gap outputs): partial-sum layout
+  std::vector<size_t> boff, bbytes;  // per buffer
+  std::vector<ConvTcPlan> tc;        // per layer (impl == nullptr -> CUDA-core kernel)
+  size_t need = 0;
+  cudaGraphExec_t graph = nullptr;
+  int graph_thresh = -2;
+  int runs = 0;
+  int launches = 0;
+  ~Inst() {
+    for (auto& p : tc)
+      if (p.impl) free_conv_tc_plan(&p);
+    if (graph) cudaGraphExecDestroy(graph);
+  }
+};
+
+Net::Net(const std::string& model_dir, int device, const NetOptions& opt) : opt_(opt), device_(device) {
+  std::string mfile, pfile;
+  if (!find_model_files(model_dir, &mfile, &pfile))
+    throw std::runtime_error("No valid model file found in " + model_dir);
+  PdProgram prog;
+  load_program(mfile, &prog);
+  load_params(pfile, &prog);
+  build_plan(prog, &plan_);
+  cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+  cuda_check(cudaMalloc(&d_wh_, std::max<size_t>(plan_.wh.size(), 8) * sizeof(uint16_t)), "cudaMalloc weights");
+  cuda_check(cudaMalloc(&d_wf_, std::max<size_t>(plan_.wf.size(), 4) * sizeof(float)), "cudaMalloc weights");
+  cuda_check(cudaMemcpy(d_wh_, plan_.wh.data(), plan_.wh.size() * sizeof(uint16_t), cudaMemcpyHostToDevice),
+             "upload weights");
+  cuda_check(cudaMemcpy(d_wf_, plan_.wf.data(), plan_.wf.size() * sizeof(float), cudaMemcpyHostToDevice),
+             "upload weights");
+}
+
+Net::~Net() {
+  cache_.clear();
+  cudaFree(d_wh_);
+  cudaFree(d_wf_);
+  cudaFree(arena_);
+}
+
+namespace {
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+}  // namespace
+
+Net::Inst* Net::instantiate(int n, int h, int w) {
+  auto I = std::make_unique<Inst>();
+  I->n = n; I->h = h; I->w = w;
+  const int nt = int(plan_.tensors.size()), nb = int(plan_.buffers.size()), nl = int(plan_.layers.size());
+  I->ts.assign(nt, Shape3());
+  I->splits.assign(nt, 0);
+  I->hw.assign(nt, 0);
+  I->ts[plan_.input] = Shape3{n, h, w};
+  auto fail = [&](const Layer& L, const char* why) {
+    throw std::runtime_error("shape error at layer " + L.name + ": " + why);
+  };
+  // ---- shape inference
+  for (const Layer& L : plan_.layers) {
+    const Shape3 in = I->ts[L.in];
+    Shape3 o = in;
+    switch (L.kind) {
+      case LKind::Conv:
+      case LKind::DwConv:
+        o.h = (in.h + 2 * L.ph - L.kh) / L.sh + 1;
+        o.w = (in.w + 2 * L.pw - L.kw) / L.sw + 1;
+        if (o.h < 1 || o.w < 1) fail(L, "input smaller than the filter");
+        break;
+      case LKind::Pool:
+        // Paddle PoolOutputSize with C++ truncating division (28-px-high rec input: (2-3)/3+1 = 1)
+        o.h = (in.h - L.kh) / L.sh + 1;
+        o.w = (in.w - L.kw) / L.sw + 1;
+        if (o.h < 1 || o.w < 1) fail(L, "pool output is empty");
+        break;
+      case LKind::Gap:
+        o = Shape3{in.n, 1, 1};
+        I->splits[L.out] = gap_splits(in.h * in.w);
+        I->hw[L.out] = in.h * in.w;
+        break;
+      case LKind::SeFc:
+      case LKind::FcSoftmax:
+        o = Shape3{in.n, 1, 1};
+        break;
+      case LKind::UpAdd: {
+        const Shape3 b = I->ts[L.in2];
+        if (b.h * 2 != in.h || b.w * 2 != in.w) fail(L, "FPN levels are not 2x apart (input not a multiple of 32?)");
+        break;
+      }
+      case LKind::UpCat: {
+        const int sh[4] = {L.kh, L.kw, L.sh, L.sw};
+        for (int k = 0; k < 4 && L.ins[k] >= 0; ++k) {
+          const Shape3 s = I->ts[L.ins[k]];
+          if ((s.h << sh[k]) != in.h || (s.w << sh[k]) != in.w) fail(L, "concat inputs do not upsample to one size");
+        }
+        break;
+      }
+      case LKind::Attn:
+        if (in.h != 1) fail(L, "sequence neck needs feature height 1 (rec_img_h must be 28..48-class)");
+        break;
+      case LKind::CtcHead:
+        if (in.h != 1) fail(L, "CTC head needs feature height 1");
+        break;
+      case LKind::DbHead:
+        o = Shape3{in.n, in.h * 4, in.w * 4};
+        break;
+      default: break;
+    }
+    I->ts[L.out] = o;
+  }
+  // concat views created by re-homing have no producing layer: take the shape of a member
+  for (int t = 0; t < nt; ++t)
+    if (I->ts[t].n == 0) {
+      for (int u = 0; u < nt; ++u)
+        if (u != t && plan_.tensors[u].buf == plan_.tensors[t].buf && I->ts[u].n) { I->ts[t] = I->ts[u]; break; }
+    }
+  // ---- buffer sizes
+  I->boff.assign(nb, 0);
+  I->bbytes.assign(nb, 0);
+  std::vector<int> first(nb, std::numeric_limits<int>::max()), last(nb, -1);
+  for (int t = 0; t < nt; ++t) {
+    const TensorDesc& td = plan_.tensors[t];
+    if (plan_.buffers[td.buf].c_total == 0) continue;
+    const Shape3 s = I->ts[t];
+    size_t bytes;
+    if (!td.vec) bytes = size_t(s.n) * s.h * s.w * round_up(plan_.buffers[td.buf].c_total, 8) * sizeof(__half);
+    else bytes = 0;  // vector buffers are sized by their producing layer below
+    I->bbytes[td.buf] = std::max(I->bbytes[td.buf], bytes);
+  }
+  for (int li = 0; li < nl; ++li) {
+    const Layer& L = plan_.layers[li];
+    const int ob = plan_.tensors[L.out].buf;
+    const Shape3 in = I->ts[L.in];
+    switch (L.kind) {
+      case LKind::Gap: I->bbytes[ob] = size_t(in.n) * I->splits[L.out] * round_up(L.cin, 8) * 4; break;
+      case LKind::SeFc: I->bbytes[ob] = size_t(in.n) * round_up(L.cin, 8) * 4; break;
+      case LKind::FcSoftmax: I->bbytes[ob] = size_t(in.n) * L.cout * 4; break;
+      case LKind::DbHead: I->bbytes[ob] = align_up(size_t(in.n) * in.h * in.w * 16 * 4, 256) + size_t(in.n) * in.h * in.w * 16; break;
+      case LKind::CtcHead: I->bbytes[ob] = align_up(size_t(in.n) * in.w * 4, 256) * 2; break;
+      default: break;
+    }
+    auto touch_r = [&](int t) { if (t >= 0) { int b = plan_.tensors[t].buf; last[b] = std::max(last[b], li); } };
+    touch_r(L.in); touch_r(L.in2); touch_r(L.residual);
+    for (int k = 0; k < 4; ++k) touch_r(L.ins[k]);
+    first[ob] = std::min(first[ob], li);
+    last[ob] = std::max(last[ob], li);
+  }
+  first[plan_.tensors[plan_.input].buf] = -1;
+  last[plan_.tensors[plan_.output].buf] = nl;
+  // ---- arena layout: first-fit over live intervals
+  struct Live { size_t off, bytes; int last; };
+  std::vector<Live> live;
+  std::vector<int> order;
+  for (int b = 0; b < nb; ++b)
+    if (I->bbytes[b]) order.push_back(b);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return first[a] < first[b]; });
+  size_t top = 0;
+  for (int b : order) {
+    const size_t bytes = align_up(I->bbytes[b], 1024);
+    if (!opt_.keep_all)
+      live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& l) { return l.last < first[b]; }),
+                 live.end());
+    std::sort(live.begin(), live.end(), [](const Live& a, const Live& c) { return a.off < c.off; });
+    size_t off = 0;
+    for (const Live& l : live) {
+      if (off + bytes <= l.off) break;
+      off = std::max(off, l.off + l.bytes);
+    }
+    I->boff[b] = off;
+    live.push_back(Live{off, bytes, last[b]});
+    top = std::max(top, off + bytes);
+  }
+  I->need = top;
+  I->tc.assign(nl, ConvTcPlan());
+  auto key = std::make_tuple(n, h, w);
+  Inst* raw = I.get();
+  cache_[key] = std::move(I);
+  return raw;
+}
+
+static TV make_tv(uint8_t* arena, const Plan& plan, const std::vector<size_t>& boff,
+                  const std::vector<Shape3>& ts, int t) {
+  TV v;
+  const TensorDesc& td = plan.tensors[t];
+  v.pitch = round_up(plan.buffers[td.buf].c_total, 8);
+  v.p = reinterpret_cast<__half*>(arena + boff[td.buf]) + td.c_off;
+  v.n = ts[t].n; v.h = ts[t].h; v.w = ts[t].w; v.c = td.c;
+  return v;
+}
+
+__half* Net::prepare(int n, int h, int w) {
+  if (n < 1 || h < 1 || w < 1) throw std::runtime_error("Net::prepare: empty input");
+  cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+  auto key = std::make_tuple(n, h, w);
+  auto it = cache_.find(key);
+  Inst* I = it != cache_.end() ? it->second.get() : instantiate(n, h, w);
+  if (I->need > arena_bytes_) {
+    // grow the shared arena; every cached instance holds pointers into the old one
+    const size_t need = I->need;
+    cuda_check(cudaDeviceSynchronize(), "sync before arena growth");
+    cache_.clear();
+    cudaFree(arena_);
+    arena_ = nullptr;
+    arena_bytes_ = align_up(need + need / 4, size_t(1) << 20);
+    cuda_check(cudaMalloc(&arena_, arena_bytes_), "cudaMalloc activation arena");
+    I = instantiate(n, h, w);
+  }
+  if (cache_.size() > 64) {  // bound the number of cached shapes (variable-width rec batches)
+    for (auto c = cache_.begin(); c != cache_.end();) {
+      if (c->second.get() != I) c = cache_.erase(c); else ++c;
+    }
+  }
+  cur_ = I;
+  return reinterpret_cast<__half*>(arena_ + I->boff[plan_.tensors[plan_.input].buf]);
+}
+
+void Net::record(Inst& I, cudaStream_t s, int thresh_u8) {
+  auto tv = [&](int t) { return make_tv(arena_, plan_, I.boff, I.ts, t); };
+  auto vecp = [&](int t) { return reinterpret_cast<float*>(arena_ + I.boff[plan_.tensors[t].buf]); };
+  int launches = 0;
+  for (size_t li = 0; li < plan_.layers.size(); ++li) {
+    const Layer& L = plan_.layers[li];
+    Epi e;
+    e.act = int(L.act); e.a = L.act_a; e.b = L.act_b; e.s2 = L.post_scale; e.t2 = L.post_shift;
+    if (L.residual >= 0) {
+      TV r = tv(L.residual);
+      e.res = r.p;
+      e.res_pitch = r.pitch;
+    }
+    ConvGeom g;
+    g.kh = L.kh; g.kw = L.kw; g.sh = L.sh; g.sw = L.sw; g.ph = L.ph; g.pw = L.pw;
+    g.cin_pad = L.cin_pad; g.cout_pad = L.cout_pad;
+    switch (L.kind) {
+      case LKind::Conv: {
+        TV in = tv(L.in), out = tv(L.out);
+        const __half* w = d_wh_ + L.wh_off;
+        const float* bias = d_wf_ + L.bias_off;
+        if (!opt_.force_simt && conv_tc_eligible(in, out, g)) {
+          if (!I.tc[li].impl) I.tc[li] = make_conv_tc_plan(in, out, w, g);
+          launch_conv_tc(I.tc[li], bias, e, s);
+        } else {
+          launch_conv_simt(in, out, w, bias, g, e, s);
+        }
+        break;
+      }
+      case LKind::DwConv: launch_dwconv(tv(L.in), tv(L.out), d_wf_ + L.wf_off, g, e, s); break;
+      case LKind::Gap: launch_gap_partial(tv(L.in), vecp(L.out), I.splits[L.out], s); break;
+      case LKind::SeFc:
+        launch_se_fc(vecp(L.in), I.splits[L.in], I.hw[L.in], I.ts[L.in].n, L.cin, L.cmid, d_wf_ + L.wf_off,
+                     L.act_a, L.act_b, vecp(L.out), s);
+        break;
+      case LKind::Scale: launch_scale(tv(L.in), vecp(L.in2), L.scale_residual, tv(L.out), s); break;
+      case LKind::UpAdd: launch_upadd(tv(L.in), tv(L.in2), tv(L.out), s); break;
+      case LKind::UpCat: {
+        TV ins[4];
+        int sh[4] = {L.kh, L.kw, L.sh, L.sw}, nin = 0;
+        for (int k = 0; k < 4 && L.ins[k] >= 0; ++k) { ins[k] = tv(L.ins[k]); ++nin; }
+        launch_upcat(ins, sh, nin, tv(L.out), s);
+        break;
+      }
+      case LKind::Pool: launch_pool(tv(L.in), tv(L.out), L.kh, L.kw, L.sh, L.sw, L.pool_max, s); break;
+      case LKind::Add: launch_add(tv(L.in), tv(L.in2), tv(L.out), s); break;
+      case LKind::LayerNorm: launch_layernorm(tv(L.in), tv(L.out), d_wf_ + L.wf_off, L.eps, s); break;
+      case LKind::Attn: launch_attention(tv(L.in), tv(L.out), L.heads, L.head_dim, L.attn_scale, s); break;
+      case LKind::DbHead: {
+        TV in = tv(L.in);
+        float* prob = vecp(L.out);
+        uint8_t* bm = reinterpret_cast<uint8_t*>(prob) + align_up(size_t(in.n) * in.h * in.w * 16 * 4, 256);
+        launch_dbhead(in, d_wf_ + L.wf_off, L.cmid, prob, thresh_u8 >= 0 ? bm : nullptr, thresh_u8, s);
+        break;
+      }
+      case LKind::FcSoftmax:
+        launch_fc_softmax(vecp(L.in), I.splits[L.in], I.hw[L.in], I.ts[L.in].n, L.cin, L.cout,
+                          d_wf_ + L.wf_off, vecp(L.out), s);
+        break;
+      case LKind::CtcHead: {
+        TV in = tv(L.in);
+        float* prob = vecp(L.out);
+        int* idx = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(prob) + align_up(size_t(in.n) * in.w * 4, 256));
+        if (!opt_.force_simt && ctc_tc_eligible(in, L.cin_pad))
+          launch_ctc_head_tc(in, d_wh_ + L.wh_off, d_wf_ + L.bias_off, L.cin_pad, L.cout, L.cout_pad, idx, prob, s);
+        else
+          launch_ctc_head_simt(in, d_wh_ + L.wh_off, d_wf_ + L.bias_off, L.cin_pad, L.cout, L.cout_pad, idx, prob, s);
+        break;
+      }
+    }
+    ++launches;
+  }
+  I.launches = launches;
+}
+
+void Net::run(cudaStream_t stream, int thresh_u8) {
+  if (!cur_) throw std::runtime_error("Net::run before prepare");
+  Inst& I = *cur_;
+  ++I.runs;
+  if (!opt_.use_graph || I.runs == 1) {
+    // first run of a shape is eager: encodes tensor maps, sets function attributes
+    record(I, stream, thresh_u8);
+    cuda_check(cudaGetLastError(), "forward launch");
+    return;
+  }
+  if (!I.graph || I.graph_thresh != thresh_u8) {
+    if (I.graph) { cudaGraphExecDestroy(I.graph); I.graph = nullptr; }
+    cudaGraph_t g = nullptr;
+    cuda_check(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal), "begin capture");
+    record(I, stream, thresh_u8);
+    cuda_check(cudaStreamEndCapture(stream, &g), "end capture");
+    cuda_check(cudaGraphInstantiate(&I.graph, g, 0), "graph instantiate");
+    cudaGraphDestroy(g);
+    I.graph_thresh = thresh_u8;
+  }
+  cuda_check(cudaGraphLaunch(I.graph, stream), "graph launch");
+}
+
+int Net::launches_per_run() const { return cur_ ? cur_->launches : 0; }
+
+Shape3 Net::out_shape() const {
+  if (!cur_) return Shape3();
+  const Layer& L = plan_.layers.back();
+  const Shape3 in = cur_->ts[L.in];
+  if (L.kind == LKind::DbHead) return Shape3{in.n, in.h * 4, in.w * 4};
+  if (L.kind == LKind::CtcHead) return Shape3{in.n, 1, in.w};
+  return Shape3{in.n, 1, 1};
+}
+
+const float* Net::out_f32() const {
+  return reinterpret_cast<const float*>(arena_ + cur_->boff[plan_.tensors[plan_.output].buf]);
+}
+
+const uint8_t* Net::out_bitmap() const {
+  const Layer& L = plan_.layers.back();
+  if (L.kind != LKind::DbHead) return nullptr;
+  const Shape3 in = cur_->ts[L.in];
+  return reinterpret_cast<const uint8_t*>(out_f32()) + align_up(size_t(in.n) * in.h * in.w * 16 * 4, 256);
+}
+
+const int* Net::out_idx() const {
+  const Layer& L = plan_.layers.back();
+  if (L.kind != LKind::CtcHead) return nullptr;
+  const Shape3 in = cur_->ts[L.in];
+  return reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(out_f32()) +
+                                      align_up(size_t(in.n) * in.w * 4, 256));
+}
+
+bool Net::fetch(const std::string& var, std::vector<float>* out, int dims[4]) {
+  if (!cur_) return false;
+  const int t = plan_.find_tensor(var);
+  if (t < 0) return false;
+  const TensorDesc& td = plan_.tensors[t];
+  cuda_check(cudaDeviceSynchronize(), "sync before fetch");
+  if (td.vec) {
+    // find the producing layer to know the layout
+    for (const Layer& L : plan_.layers) {
+      if (L.out != t) continue;
+      const Shape3 in = cur_->ts[L.in];
+      const float* p = reinterpret_cast<const float*>(arena_ + cur_->boff[td.buf]);
+      size_t count = 0;
+      if (L.kind == LKind::DbHead) { dims[0] = in.n; dims[1] = 1; dims[2] = in.h * 4; dims[3] = in.w * 4; }
+      else if (L.kind == LKind::FcSoftmax) { dims[0] = in.n; dims[1] = L.cout; dims[2] = dims[3] = 1; }
+      else if (L.kind == LKind::SeFc) { dims[0] = in.n; dims[1] = round_up(L.cin, 8); dims[2] = dims[3] = 1; }
+      else if (L.kind == LKind::CtcHead) { dims[0] = in.n; dims[1] = in.w; dims[2] = dims[3] = 1; }
+      else return false;
+      count = size_t(dims[0]) * dims[1] * dims[2] * dims[3];
+      out->resize(count);
+      cuda_check(cudaMemcpy(out->data(), p, count * 4, cudaMemcpyDeviceToHost), "fetch");
+      return true;
+    }
+    return false;
+  }
+  TV v = make_tv(arena_, plan_, cur_->boff, cur_->ts, t);
+  const size_t count = size_t(v.n) * v.c * v.h * v.w;
+  float* d = nullptr;
+  cuda_check(cudaMalloc(&d, count * 4), "fetch scratch");
+  launch_nhwc_to_nchw_f32(v, d, 0);
+  out->resize(count);
+  cuda_check(cudaMemcpy(out->data(), d, count * 4, cudaMemcpyDeviceToHost), "fetch");
+  cudaFree(d);
+  dims[0] = v.n; dims[1] = v.c; dims[2] = v.h; dims[3] = v.w;
+  return true;
+}
+
+}  // namespace b200ocr

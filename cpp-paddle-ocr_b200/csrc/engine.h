@@ -1,0 +1,79 @@
+// Net: one loaded Paddle graph executing on one GPU as a sequence of fused sm_100a kernels.
+//
+// Takes the place of `paddle_infer::Predictor` in the reference stages
+// (predictor_->Run(), reference src/ocr_det.cpp:120, src/ocr_cls.cpp:76, src/ocr_rec.cpp:85).
+// A Net is single-threaded like the predictor it replaces; one instance per worker.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "kernels.h"
+#include "plan.h"
+
+namespace b200ocr {
+
+struct NetOptions {
+  bool keep_all = false;    // debug: every tensor keeps its own memory so it can be fetched after a run
+  bool use_graph = true;    // replay the layer sequence as a CUDA graph per input shape
+  bool force_simt = false;  // debug: run dense convs / CTC head on the CUDA-core kernels
+};
+
+struct Shape3 {
+  int n = 0, h = 0, w = 0;
+};
+
+class Net {
+ public:
+  // Loads <model_dir>/inference.pdmodel + .pdiparams, builds the fused plan, uploads weights.
+  Net(const std::string& model_dir, int device, const NetOptions& opt);
+  ~Net();
+  Net(const Net&) = delete;
+  Net& operator=(const Net&) = delete;
+
+  const Plan& plan() const { return plan_; }
+  const std::string& kind() const { return plan_.kind; }
+  int device() const { return device_; }
+
+  // Prepare buffers (and the CUDA graph) for an input of n x h x w.  The returned pointer is the
+  // network input: NHWC fp16 with channel pitch 8 (channels 3..7 must be written as zero).
+  __half* prepare(int n, int h, int w);
+  // Execute the forward pass for the last prepared shape on `stream`.
+  //   det: `thresh_u8` >= 0 also writes the thresholded bitmap.
+  void run(cudaStream_t stream, int thresh_u8 = -1);
+
+  // Outputs of the last prepared shape (device pointers, valid until the next prepare()).
+  Shape3 out_shape() const;              // det: (n, H, W); cls: (n,1,1); rec: (n, 1, T)
+  const float* out_f32() const;          // det: prob [n,H,W]; cls: softmax [n,2]; rec: max prob [n*T]
+  const uint8_t* out_bitmap() const;     // det only
+  const int* out_idx() const;            // rec only: argmax class per (n,t)
+
+  // debug: copy a tensor (by Paddle var name) of the last run to host as fp32 NCHW.
+  bool fetch(const std::string& var, std::vector<float>* out, int dims[4]);
+
+  size_t arena_bytes() const { return arena_bytes_; }
+  int launches_per_run() const;
+
+ private:
+  struct Inst;
+  Inst* instantiate(int n, int h, int w);
+  void record(Inst& I, cudaStream_t s, int thresh_u8);
+
+  Plan plan_;
+  NetOptions opt_;
+  int device_ = 0;
+  __half* d_wh_ = nullptr;
+  float* d_wf_ = nullptr;
+  uint8_t* arena_ = nullptr;
+  size_t arena_bytes_ = 0;
+  std::map<std::tuple<int, int, int>, std::unique_ptr<Inst>> cache_;
+  Inst* cur_ = nullptr;
+};
+
+void cuda_check(cudaError_t e, const char* what);
+
+}  // namespace b200ocr

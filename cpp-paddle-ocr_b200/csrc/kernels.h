@@ -1,0 +1,81 @@
+// Launchers for the sm_100a kernels of the det/cls/rec forward passes.
+// Everything here runs on the GPU; there is no host fallback for any of it.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace b200ocr {
+
+// NHWC fp16 view: element (n,y,x,ch) lives at p[((n*h + y)*w + x)*pitch + ch].
+struct TV {
+  __half* p = nullptr;
+  int n = 0, h = 0, w = 0, c = 0, pitch = 0;
+};
+
+// y = s2 * act(acc + bias[c]) + t2 (+ residual)
+struct Epi {
+  int act = 0;
+  float a = 0.f, b = 0.f, s2 = 1.f, t2 = 0.f;
+  const __half* res = nullptr;
+  int res_pitch = 0;
+};
+
+struct ConvGeom {
+  int kh = 1, kw = 1, sh = 1, sw = 1, ph = 0, pw = 0;
+  int cin_pad = 0;  // weight row stride per tap
+  int cout_pad = 0;
+};
+
+// ---- convolution family -----------------------------------------------------
+// CUDA-core direct convolution (stems with C_in=3 and shapes the tensor-core path does not take).
+void launch_conv_simt(const TV& in, const TV& out, const __half* w, const float* bias,
+                      const ConvGeom& g, const Epi& e, cudaStream_t s);
+// tcgen05 implicit-GEMM convolution (stride 1; 1x1, 1x3, 3x3): TMA -> smem -> UMMA -> TMEM -> epilogue.
+// Returns false if the shape is not eligible (caller then uses the CUDA-core kernel).
+// Tensor maps are encoded once per (layer, shape) by make_conv_tc_plan.
+struct ConvTcPlanImpl;
+struct ConvTcPlan { ConvTcPlanImpl* impl = nullptr; };
+bool conv_tc_eligible(const TV& in, const TV& out, const ConvGeom& g);
+ConvTcPlan make_conv_tc_plan(const TV& in, const TV& out, const __half* w, const ConvGeom& g);
+void free_conv_tc_plan(ConvTcPlan* p);
+void launch_conv_tc(const ConvTcPlan& p, const float* bias, const Epi& e, cudaStream_t s);
+void launch_dwconv(const TV& in, const TV& out, const float* w_bias, const ConvGeom& g,
+                   const Epi& e, cudaStream_t s);
+
+// ---- SE block ---------------------------------------------------------------
+int gap_splits(int hw);
+void launch_gap_partial(const TV& in, float* partial, int splits, cudaStream_t s);
+void launch_se_fc(const float* partial, int splits, int hw, int n, int c, int cmid, const float* blk,
+                  float slope, float offset, float* gate, cudaStream_t s);
+void launch_scale(const TV& in, const float* gate, bool add_x, const TV& out, cudaStream_t s);
+
+// ---- glue ---------------------------------------------------------------------
+void launch_upadd(const TV& a, const TV& b_half_res, const TV& out, cudaStream_t s);
+void launch_upcat(const TV in[4], const int shift[4], int nin, const TV& out, cudaStream_t s);
+void launch_add(const TV& a, const TV& b, const TV& out, cudaStream_t s);
+void launch_pool(const TV& in, const TV& out, int kh, int kw, int sh, int sw, bool is_max, cudaStream_t s);
+
+// ---- SVTR neck ----------------------------------------------------------------
+void launch_layernorm(const TV& in, const TV& out, const float* gamma_beta, float eps, cudaStream_t s);
+void launch_attention(const TV& qkv, const TV& out, int heads, int head_dim, float scale, cudaStream_t s);
+
+// ---- heads ----------------------------------------------------------------------
+// DB head tail: deconv2x2+BN+relu -> deconv2x2 -> sigmoid, plus cbuf=(u8)(p*255) > thresh bitmap.
+void launch_dbhead(const TV& in, const float* blk, int cmid, float* prob, uint8_t* bitmap,
+                   int thresh_u8, cudaStream_t s);
+void launch_fc_softmax(const float* partial, int splits, int hw, int n, int cin, int cout,
+                       const float* blk, float* out, cudaStream_t s);
+// CTC head: logits = feat . W^T + b; per (n,t): argmax index and softmax probability of the max.
+void launch_ctc_head_simt(const TV& feat, const __half* w, const float* bias, int cin_pad, int ncls,
+                          int ncls_pad, int* idx, float* prob, cudaStream_t s);
+bool ctc_tc_eligible(const TV& feat, int cin_pad);
+void launch_ctc_head_tc(const TV& feat, const __half* w, const float* bias, int cin_pad, int ncls,
+                        int ncls_pad, int* idx, float* prob, cudaStream_t s);
+
+// debug / test helpers
+void launch_nhwc_to_nchw_f32(const TV& in, float* out, cudaStream_t s);
+// fp32 NCHW (3 channels) -> network input NHWC fp16, channel pitch 8, channels 3..7 zero
+void launch_nchw3_to_input(const float* in, int n, int h, int w, __half* out, cudaStream_t s);
+
+}  // namespace b200ocr

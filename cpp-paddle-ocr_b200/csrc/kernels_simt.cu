@@ -1,0 +1,743 @@
+// CUDA-core kernels of the forward passes: stem / odd-shape direct conv, depthwise conv,
+// SE block, FPN glue, pooling, LayerNorm, attention, DB head tail, cls head, CTC head (CUDA-core
+// variant).  All activations are NHWC fp16 with 16-byte (8-channel) vector access; accumulation
+// is fp32.  HBM/L2-bound kernels: one thread per (pixel, 8-channel group), coalesced along C.
+#include "kernels.h"
+
+#include <cfloat>
+
+namespace b200ocr {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float apply_act(float v, int act, float a, float b) {
+  switch (act) {
+    case 1: return fmaxf(v, 0.f);
+    case 2: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    case 3: return v / (1.f + __expf(-v));
+    case 4: return fminf(fmaxf(v * a + b, 0.f), 1.f);
+    case 5: return 1.f / (1.f + __expf(-v));
+    default: return v;
+  }
+}
+
+struct H8 {
+  uint4 u;
+  __device__ __forceinline__ void to_float(float* f) const {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __half22float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ __forceinline__ void from_float(const float* f) {
+    __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  }
+};
+
+__device__ __forceinline__ H8 ld8(const __half* p) {
+  H8 r;
+  r.u = *reinterpret_cast<const uint4*>(p);
+  return r;
+}
+__device__ __forceinline__ void st8(__half* p, const H8& v) { *reinterpret_cast<uint4*>(p) = v.u; }
+
+// Shared epilogue for 8 consecutive channels starting at c0 of pixel `pix`.
+__device__ __forceinline__ void epilogue8(float* acc, const float* bias, int c0, int cout, const Epi& e,
+                                          const TV& out, long pix) {
+  float r[8];
+  if (e.res) ld8(e.res + pix * e.res_pitch + c0).to_float(r);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float v = acc[i] + bias[c0 + i];
+    v = e.s2 * apply_act(v, e.act, e.a, e.b) + e.t2;
+    if (e.res) v += r[i];
+    acc[i] = (c0 + i < cout) ? v : 0.f;
+  }
+  H8 o;
+  o.from_float(acc);
+  st8(out.p + pix * out.pitch + c0, o);
+}
+
+// ---------------------------------------------------------------- direct conv
+__global__ void __launch_bounds__(kThreads)
+conv_simt_kernel(TV in, TV out, const __half* __restrict__ w, const float* __restrict__ bias,
+                 ConvGeom g, Epi e) {
+  const int cgs = (out.c + 7) >> 3;
+  const long npix = long(out.n) * out.h * out.w;
+  const long total = npix * cgs;
+  const int taps = g.kh * g.kw;
+  const int cin8 = (in.c + 7) >> 3;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    // consecutive threads -> consecutive pixels of one channel group (weights broadcast)
+    const int cg = int(t / npix);
+    const long pix = t - long(cg) * npix;
+    const int ox = int(pix % out.w);
+    const int oy = int((pix / out.w) % out.h);
+    const int n = int(pix / (long(out.w) * out.h));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int ky = 0; ky < g.kh; ++ky) {
+      const int iy = oy * g.sh - g.ph + ky;
+      if (iy < 0 || iy >= in.h) continue;
+      for (int kx = 0; kx < g.kw; ++kx) {
+        const int ix = ox * g.sw - g.pw + kx;
+        if (ix < 0 || ix >= in.w) continue;
+        const __half* ip = in.p + ((long(n) * in.h + iy) * in.w + ix) * in.pitch;
+        const __half* wp = w + (long(cg) * 8 * taps + (ky * g.kw + kx)) * g.cin_pad;
+        for (int c8 = 0; c8 < cin8; ++c8) {
+          float x[8];
+          ld8(ip + c8 * 8).to_float(x);
+#pragma unroll
+          for (int o = 0; o < 8; ++o) {
+            float wv[8];
+            ld8(wp + long(o) * taps * g.cin_pad + c8 * 8).to_float(wv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[o] = fmaf(x[i], wv[i], acc[o]);
+          }
+        }
+      }
+    }
+    epilogue8(acc, bias, cg * 8, out.c, e, out, pix);
+  }
+}
+
+// ---------------------------------------------------------------- depthwise conv
+template <int KH, int KW>
+__global__ void __launch_bounds__(kThreads)
+dwconv_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi e) {
+  const int cgs = (out.c + 7) >> 3;
+  const int cp = g.cout_pad;
+  const long total = long(out.n) * out.h * out.w * cgs;
+  const float* bias = wb + long(KH * KW) * cp;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const int cg = int(t % cgs);
+    const long pix = t / cgs;
+    const int ox = int(pix % out.w);
+    const int oy = int((pix / out.w) % out.h);
+    const int n = int(pix / (long(out.w) * out.h));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int ky = 0; ky < KH; ++ky) {
+      const int iy = oy * g.sh - g.ph + ky;
+      if (iy < 0 || iy >= in.h) continue;
+#pragma unroll
+      for (int kx = 0; kx < KW; ++kx) {
+        const int ix = ox * g.sw - g.pw + kx;
+        if (ix < 0 || ix >= in.w) continue;
+        float x[8];
+        ld8(in.p + ((long(n) * in.h + iy) * in.w + ix) * in.pitch + cg * 8).to_float(x);
+        const float4* wp = reinterpret_cast<const float4*>(wb + long(ky * KW + kx) * cp + cg * 8);
+        const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+        acc[0] = fmaf(x[0], w0.x, acc[0]); acc[1] = fmaf(x[1], w0.y, acc[1]);
+        acc[2] = fmaf(x[2], w0.z, acc[2]); acc[3] = fmaf(x[3], w0.w, acc[3]);
+        acc[4] = fmaf(x[4], w1.x, acc[4]); acc[5] = fmaf(x[5], w1.y, acc[5]);
+        acc[6] = fmaf(x[6], w1.z, acc[6]); acc[7] = fmaf(x[7], w1.w, acc[7]);
+      }
+    }
+    epilogue8(acc, bias, cg * 8, out.c, e, out, pix);
+  }
+}
+
+// ---------------------------------------------------------------- SE block
+// partial[n][split][cp] = sum over the split's pixels (fp32, fixed order -> deterministic)
+__global__ void __launch_bounds__(kThreads)
+gap_partial_kernel(TV in, float* __restrict__ partial, int splits) {
+  extern __shared__ float sm[];
+  const int cgs = (in.c + 7) >> 3;
+  const int cp = cgs * 8;
+  const int lanes = max(1, kThreads / cgs);
+  const int split = blockIdx.x, n = blockIdx.y;
+  const int hw = in.h * in.w;
+  const int chunk = (hw + splits - 1) / splits;
+  const int p0 = split * chunk, p1 = min(hw, p0 + chunk);
+  const int cg = threadIdx.x % cgs, lane = threadIdx.x / cgs;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (lane < lanes) {
+    const __half* base = in.p + long(n) * hw * in.pitch + cg * 8;
+    for (int p = p0 + lane; p < p1; p += lanes) {
+      float x[8];
+      ld8(base + long(p) * in.pitch).to_float(x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += x[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm[lane * cp + cg * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cp; c += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += sm[l * cp + c];
+    partial[(long(n) * splits + split) * cp + c] = s;
+  }
+}
+
+// blk: w1[cmid][c], b1[cmid], w2[c][cmid], b2[c]
+__global__ void __launch_bounds__(kThreads)
+se_fc_kernel(const float* __restrict__ partial, int splits, float inv_hw, int c, int cmid,
+             const float* __restrict__ blk, float slope, float offset, float* __restrict__ gate) {
+  extern __shared__ float sm[];
+  const int cp = (c + 7) / 8 * 8;
+  float* pooled = sm;        // [cp]
+  float* hidden = sm + cp;   // [cmid]
+  const int n = blockIdx.x;
+  for (int i = threadIdx.x; i < cp; i += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[(long(n) * splits + k) * cp + i];
+    pooled[i] = s * inv_hw;
+  }
+  __syncthreads();
+  const float* w1 = blk;
+  const float* b1 = w1 + long(cmid) * c;
+  const float* w2 = b1 + cmid;
+  const float* b2 = w2 + long(c) * cmid;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int m = warp; m < cmid; m += nwarps) {
+    float s = 0.f;
+    for (int i = lane; i < c; i += 32) s = fmaf(w1[long(m) * c + i], pooled[i], s);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) hidden[m] = fmaxf(s + b1[m], 0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cp; i += blockDim.x) {
+    float v = 0.f;
+    if (i < c) {
+      float s = b2[i];
+      for (int m = 0; m < cmid; ++m) s = fmaf(w2[long(i) * cmid + m], hidden[m], s);
+      v = fminf(fmaxf(s * slope + offset, 0.f), 1.f);
+    }
+    gate[long(n) * cp + i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+scale_kernel(TV in, const float* __restrict__ gate, int add_x, TV out) {
+  const int cgs = (in.c + 7) >> 3;
+  const int cp = cgs * 8;
+  const long hw = long(in.h) * in.w;
+  const long total = long(in.n) * hw * cgs;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const int cg = int(t % cgs);
+    const long pix = t / cgs;
+    const int n = int(pix / hw);
+    float x[8];
+    ld8(in.p + pix * in.pitch + cg * 8).to_float(x);
+    const float4* gp = reinterpret_cast<const float4*>(gate + long(n) * cp + cg * 8);
+    const float4 g0 = gp[0], g1 = gp[1];
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = add_x ? fmaf(x[i], g[i], x[i]) : x[i] * g[i];
+    H8 o;
+    o.from_float(x);
+    st8(out.p + pix * out.pitch + cg * 8, o);
+  }
+}
+
+// ---------------------------------------------------------------- glue
+__global__ void __launch_bounds__(kThreads) upadd_kernel(TV a, TV b, TV out) {
+  const int cgs = (a.c + 7) >> 3;
+  const long total = long(a.n) * a.h * a.w * cgs;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const int cg = int(t % cgs);
+    const long pix = t / cgs;
+    const int x = int(pix % a.w), y = int((pix / a.w) % a.h), n = int(pix / (long(a.w) * a.h));
+    float u[8], v[8];
+    ld8(a.p + pix * a.pitch + cg * 8).to_float(u);
+    ld8(b.p + ((long(n) * b.h + (y >> 1)) * b.w + (x >> 1)) * b.pitch + cg * 8).to_float(v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] += v[i];
+    H8 o;
+    o.from_float(u);
+    st8(out.p + pix * out.pitch + cg * 8, o);
+  }
+}
+
+struct UpCatArgs {
+  TV in[4];
+  int shift[4];
+  int coff[4];
+  int nin;
+};
+
+__global__ void __launch_bounds__(kThreads) upcat_kernel(UpCatArgs a, TV out) {
+  const int cgs = (out.c + 7) >> 3;
+  const long total = long(out.n) * out.h * out.w * cgs;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const int cg = int(t % cgs);
+    const long pix = t / cgs;
+    const int x = int(pix % out.w), y = int((pix / out.w) % out.h), n = int(pix / (long(out.w) * out.h));
+    const int c0 = cg * 8;
+    int k = 0;
+#pragma unroll
+    for (int j = 1; j < 4; ++j)
+      if (j < a.nin && c0 >= a.coff[j]) k = j;
+    const TV& s = a.in[k];
+    const int sh = a.shift[k];
+    H8 v = ld8(s.p + ((long(n) * s.h + (y >> sh)) * s.w + (x >> sh)) * s.pitch + (c0 - a.coff[k]));
+    st8(out.p + pix * out.pitch + c0, v);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) add_kernel(TV a, TV b, TV out) {
+  const int cgs = (a.c + 7) >> 3;
+  const long total = long(a.n) * a.h * a.w * cgs;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const int cg = int(t % cgs);
+    const long pix = t / cgs;
+    float u[8], v[8];
+    ld8(a.p + pix * a.pitch + cg * 8).to_float(u);
+    ld8(b.p + pix * b.pitch + cg * 8).to_float(v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] += v[i];
+    H8 o;
+    o.from_float(u);
+    st8(out.p + pix * out.pitch + cg * 8, o);
+  }
+}
+
+// windows are clipped to the input; avg divides by the clipped size (Paddle exclusive=true)
+__global__ void __launch_bounds__(kThreads)
+pool_kernel(TV in, TV out, int kh, int kw, int sh, int sw, int is_max) {
+  const int cgs = (in.c + 7) >> 3;
+  const long total = long(out.n) * out.h * out.w * cgs;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const int cg = int(t % cgs);
+    const long pix = t / cgs;
+    const int ox = int(pix % out.w), oy = int((pix / out.w) % out.h), n = int(pix / (long(out.w) * out.h));
+    const int y0 = oy * sh, y1 = min(y0 + kh, in.h), x0 = ox * sw, x1 = min(x0 + kw, in.w);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = is_max ? -FLT_MAX : 0.f;
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) {
+        float v[8];
+        ld8(in.p + ((long(n) * in.h + y) * in.w + x) * in.pitch + cg * 8).to_float(v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = is_max ? fmaxf(acc[i], v[i]) : acc[i] + v[i];
+      }
+    if (!is_max) {
+      const float inv = 1.f / float((y1 - y0) * (x1 - x0));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] *= inv;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (cg * 8 + i >= in.c) acc[i] = 0.f;
+    H8 o;
+    o.from_float(acc);
+    st8(out.p + pix * out.pitch + cg * 8, o);
+  }
+}
+
+// ---------------------------------------------------------------- SVTR neck
+// one warp per token; C <= 256
+__global__ void __launch_bounds__(kThreads)
+layernorm_kernel(TV in, TV out, const float* __restrict__ gb, float eps) {
+  const long rows = long(in.n) * in.h * in.w;
+  const int lane = threadIdx.x & 31;
+  const long row = (blockIdx.x * long(blockDim.x) + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const int c0 = lane * 8;
+  const bool have = c0 < in.c;
+  float x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (have) ld8(in.p + row * in.pitch + c0).to_float(x);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += (c0 + i < in.c) ? x[i] : 0.f;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / float(in.c);
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float d = (c0 + i < in.c) ? x[i] - mean : 0.f;
+    v = fmaf(d, d, v);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = rsqrtf(v / float(in.c) + eps);
+  if (have) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      x[i] = (c < in.c) ? (x[i] - mean) * rstd * gb[c] + gb[in.c + c] : 0.f;
+    }
+    H8 o;
+    o.from_float(x);
+    st8(out.p + row * out.pitch + c0, o);
+  }
+}
+
+// qkv row layout (Paddle reshape [N,T,3,heads,d]): [which(3)][head][d].  One block per (n, head).
+// smem: K[T][d], V[T][d], P[warps][T]
+__global__ void __launch_bounds__(128)
+attention_kernel(TV qkv, TV out, int heads, int hd, float scale) {
+  extern __shared__ float sm[];
+  const int T = qkv.h * qkv.w;
+  const int n = blockIdx.x / heads, head = blockIdx.x % heads;
+  float* K = sm;
+  float* V = K + T * hd;
+  float* P = V + T * hd;
+  const __half* base = qkv.p + long(n) * T * qkv.pitch;
+  const int C = heads * hd;
+  for (int i = threadIdx.x; i < T * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    K[i] = __half2float(base[long(t) * qkv.pitch + C + head * hd + d]);
+    V[i] = __half2float(base[long(t) * qkv.pitch + 2 * C + head * hd + d]);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* p = P + warp * T;
+  for (int tq = warp; tq < T; tq += nwarps) {
+    float q[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d)
+      q[d] = d < hd ? __half2float(base[long(tq) * qkv.pitch + head * hd + d]) * scale : 0.f;
+    float mx = -FLT_MAX;
+    for (int j = lane; j < T; j += 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d)
+        if (d < hd) s = fmaf(q[d], K[j * hd + d], s);
+      p[j] = s;
+      mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float e = __expf(p[j] - mx);
+      p[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    // lane d accumulates output dim d (hd <= 32)
+    float acc = 0.f;
+    if (lane < hd)
+      for (int j = 0; j < T; ++j) acc = fmaf(p[j], V[j * hd + lane], acc);
+    if (lane < hd)
+      out.p[(long(n) * T + tq) * out.pitch + head * hd + lane] = __float2half_rn(acc / sum);
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- heads
+// blk: w1[q][ci][cm], b1[cm], w2[cm][4], b2.  One thread per 1/4-scale pixel -> 4x4 output block.
+template <int CIN, int CMID>
+__global__ void __launch_bounds__(128)
+dbhead_kernel(TV in, const float* __restrict__ blk, float* __restrict__ prob,
+              uint8_t* __restrict__ bitmap, int thresh_u8) {
+  __shared__ float sw1[4 * CIN * CMID];
+  __shared__ float sb1[CMID];
+  __shared__ float sw2[CMID * 4];
+  __shared__ float sb2;
+  for (int i = threadIdx.x; i < 4 * CIN * CMID; i += blockDim.x) sw1[i] = blk[i];
+  for (int i = threadIdx.x; i < CMID; i += blockDim.x) sb1[i] = blk[4 * CIN * CMID + i];
+  for (int i = threadIdx.x; i < CMID * 4; i += blockDim.x) sw2[i] = blk[4 * CIN * CMID + CMID + i];
+  if (threadIdx.x == 0) sb2 = blk[4 * CIN * CMID + CMID + CMID * 4];
+  __syncthreads();
+  const long npix = long(in.n) * in.h * in.w;
+  const long pix = blockIdx.x * long(blockDim.x) + threadIdx.x;
+  if (pix >= npix) return;
+  const int x = int(pix % in.w), y = int((pix / in.w) % in.h), n = int(pix / (long(in.w) * in.h));
+  float xin[CIN];
+#pragma unroll
+  for (int c8 = 0; c8 < CIN / 8; ++c8) ld8(in.p + pix * in.pitch + c8 * 8).to_float(xin + c8 * 8);
+  const int OW = in.w * 4, OH = in.h * 4;
+  float pv[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float mid[CMID];
+#pragma unroll
+    for (int cm = 0; cm < CMID; ++cm) mid[cm] = sb1[cm];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float xv = xin[ci];
+#pragma unroll
+      for (int cm = 0; cm < CMID; ++cm) mid[cm] = fmaf(xv, sw1[(q * CIN + ci) * CMID + cm], mid[cm]);
+    }
+    float o[4] = {sb2, sb2, sb2, sb2};
+#pragma unroll
+    for (int cm = 0; cm < CMID; ++cm) {
+      const float m = fmaxf(mid[cm], 0.f);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) o[r] = fmaf(m, sw2[cm * 4 + r], o[r]);
+    }
+    const int dy = q >> 1, dx = q & 1;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) pv[dy * 2 + (r >> 1)][dx * 2 + (r & 1)] = 1.f / (1.f + __expf(-o[r]));
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const long o = (long(n) * OH + (y * 4 + r)) * OW + x * 4;
+    *reinterpret_cast<float4*>(prob + o) = make_float4(pv[r][0], pv[r][1], pv[r][2], pv[r][3]);
+    if (bitmap) {
+      uchar4 b;
+      // reference src/ocr_det.cpp:146,151-154: cbuf = (uchar)(p*255); bit = cbuf > floor(thresh*255)
+      b.x = (int((unsigned char)(pv[r][0] * 255.f)) > thresh_u8) ? 255 : 0;
+      b.y = (int((unsigned char)(pv[r][1] * 255.f)) > thresh_u8) ? 255 : 0;
+      b.z = (int((unsigned char)(pv[r][2] * 255.f)) > thresh_u8) ? 255 : 0;
+      b.w = (int((unsigned char)(pv[r][3] * 255.f)) > thresh_u8) ? 255 : 0;
+      *reinterpret_cast<uchar4*>(bitmap + o) = b;
+    }
+  }
+}
+
+// blk: w[cin][cout], b[cout]; one warp per image
+__global__ void fc_softmax_kernel(const float* __restrict__ partial, int splits, float inv_hw, int cin,
+                                  int cout, const float* __restrict__ blk, float* __restrict__ out) {
+  const int n = blockIdx.x, lane = threadIdx.x;
+  const int cp = (cin + 7) / 8 * 8;
+  float logit[8];
+  for (int o = 0; o < cout; ++o) {
+    float s = 0.f;
+    for (int i = lane; i < cin; i += 32) {
+      float p = 0.f;
+      for (int k = 0; k < splits; ++k) p += partial[(long(n) * splits + k) * cp + i];
+      s = fmaf(p * inv_hw, blk[long(i) * cout + o], s);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    logit[o] = s + blk[long(cin) * cout + o];
+  }
+  if (lane == 0) {
+    float mx = logit[0];
+    for (int o = 1; o < cout; ++o) mx = fmaxf(mx, logit[o]);
+    float sum = 0.f;
+    for (int o = 0; o < cout; ++o) { logit[o] = expf(logit[o] - mx); sum += logit[o]; }
+    for (int o = 0; o < cout; ++o) out[long(n) * cout + o] = logit[o] / sum;
+  }
+}
+
+// CUDA-core CTC head: 8 tokens per block share each weight row; per token running (max, argmax, sum).
+__global__ void __launch_bounds__(kThreads)
+ctc_head_simt_kernel(TV feat, const __half* __restrict__ w, const float* __restrict__ bias, int cin_pad,
+                     int ncls_pad, int* __restrict__ idx, float* __restrict__ prob) {
+  constexpr int ROWS = 8;
+  extern __shared__ float sm[];  // feat[ROWS][cin_pad]
+  const long rows = long(feat.n) * feat.h * feat.w;
+  const long r0 = long(blockIdx.x) * ROWS;
+  for (int i = threadIdx.x; i < ROWS * cin_pad; i += blockDim.x) {
+    const int r = i / cin_pad, c = i % cin_pad;
+    sm[i] = (r0 + r < rows && c < feat.c) ? __half2float(feat.p[(r0 + r) * feat.pitch + c]) : 0.f;
+  }
+  __syncthreads();
+  float mx[ROWS], sum[ROWS];
+  int am[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) { mx[r] = -FLT_MAX; sum[r] = 0.f; am[r] = 0; }
+  for (int o = threadIdx.x; o < ncls_pad; o += blockDim.x) {
+    float acc[ROWS];
+    const float b = bias[o];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = b;
+    const __half* wp = w + long(o) * cin_pad;
+    for (int c8 = 0; c8 < cin_pad; c8 += 8) {
+      float wv[8];
+      ld8(wp + c8).to_float(wv);
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[r] = fmaf(wv[i], sm[r * cin_pad + c8 + i], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const float v = acc[r];
+      if (v > mx[r]) { sum[r] = sum[r] * __expf(mx[r] - v) + 1.f; mx[r] = v; am[r] = o; }
+      else sum[r] += __expf(v - mx[r]);
+    }
+  }
+  // block reduce (max, first argmax, rescaled sum)
+  __shared__ float smx[kThreads / 32][ROWS], ssum[kThreads / 32][ROWS];
+  __shared__ int sam[kThreads / 32][ROWS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    float m = mx[r], s = sum[r];
+    int a = am[r];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, d);
+      const float s2 = __shfl_xor_sync(0xffffffffu, s, d);
+      const int a2 = __shfl_xor_sync(0xffffffffu, a, d);
+      const float nm = fmaxf(m, m2);
+      s = s * __expf(m - nm) + s2 * __expf(m2 - nm);
+      if (m2 > m || (m2 == m && a2 < a)) a = a2;
+      m = nm;
+    }
+    if (lane == 0) { smx[warp][r] = m; ssum[warp][r] = s; sam[warp][r] = a; }
+  }
+  __syncthreads();
+  if (threadIdx.x < ROWS && r0 + threadIdx.x < rows) {
+    const int r = threadIdx.x;
+    float m = smx[0][r], s = ssum[0][r];
+    int a = sam[0][r];
+    for (int k = 1; k < kThreads / 32; ++k) {
+      const float m2 = smx[k][r], s2 = ssum[k][r];
+      const int a2 = sam[k][r];
+      const float nm = fmaxf(m, m2);
+      s = s * __expf(m - nm) + s2 * __expf(m2 - nm);
+      if (m2 > m || (m2 == m && a2 < a)) a = a2;
+      m = nm;
+    }
+    idx[r0 + r] = a;
+    prob[r0 + r] = 1.f / s;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) nhwc_to_nchw_f32_kernel(TV in, float* __restrict__ out) {
+  const long total = long(in.n) * in.c * in.h * in.w;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const int x = int(t % in.w);
+    const int y = int((t / in.w) % in.h);
+    const int c = int((t / (long(in.w) * in.h)) % in.c);
+    const int n = int(t / (long(in.w) * in.h * in.c));
+    out[t] = __half2float(in.p[((long(n) * in.h + y) * in.w + x) * in.pitch + c]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+nchw3_to_input_kernel(const float* __restrict__ in, int n, int h, int w, __half* __restrict__ out) {
+  const long total = long(n) * h * w;
+  const long hw = long(h) * w;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const long img = t / hw, p = t - img * hw;
+    float f[8] = {in[(img * 3 + 0) * hw + p], in[(img * 3 + 1) * hw + p], in[(img * 3 + 2) * hw + p], 0, 0, 0, 0, 0};
+    H8 o;
+    o.from_float(f);
+    st8(out + t * 8, o);
+  }
+}
+
+inline int grid_for(long total, int threads = kThreads) {
+  long b = (total + threads - 1) / threads;
+  const long cap = 148L * 16;  // grid-stride: a few waves over the 148 SMs
+  return int(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+void launch_conv_simt(const TV& in, const TV& out, const __half* w, const float* bias,
+                      const ConvGeom& g, const Epi& e, cudaStream_t s) {
+  const long total = long(out.n) * out.h * out.w * ((out.c + 7) / 8);
+  conv_simt_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, w, bias, g, e);
+}
+
+void launch_dwconv(const TV& in, const TV& out, const float* wb, const ConvGeom& g, const Epi& e,
+                   cudaStream_t s) {
+  const long total = long(out.n) * out.h * out.w * ((out.c + 7) / 8);
+  const int grid = grid_for(total);
+  if (g.kh == 3 && g.kw == 3) dwconv_kernel<3, 3><<<grid, kThreads, 0, s>>>(in, out, wb, g, e);
+  else if (g.kh == 5 && g.kw == 5) dwconv_kernel<5, 5><<<grid, kThreads, 0, s>>>(in, out, wb, g, e);
+  else abort();
+}
+
+int gap_splits(int hw) {
+  int s = (hw + 2047) / 2048;
+  return s < 1 ? 1 : (s > 64 ? 64 : s);
+}
+
+void launch_gap_partial(const TV& in, float* partial, int splits, cudaStream_t s) {
+  const int cgs = (in.c + 7) / 8;
+  const int lanes = kThreads / cgs > 0 ? kThreads / cgs : 1;
+  const size_t smem = size_t(lanes) * cgs * 8 * sizeof(float);
+  gap_partial_kernel<<<dim3(splits, in.n), kThreads, smem, s>>>(in, partial, splits);
+}
+
+void launch_se_fc(const float* partial, int splits, int hw, int n, int c, int cmid, const float* blk,
+                  float slope, float offset, float* gate, cudaStream_t s) {
+  const int cp = (c + 7) / 8 * 8;
+  se_fc_kernel<<<n, kThreads, (cp + cmid) * sizeof(float), s>>>(partial, splits, 1.f / float(hw), c, cmid,
+                                                                 blk, slope, offset, gate);
+}
+
+void launch_scale(const TV& in, const float* gate, bool add_x, const TV& out, cudaStream_t s) {
+  const long total = long(in.n) * in.h * in.w * ((in.c + 7) / 8);
+  scale_kernel<<<grid_for(total), kThreads, 0, s>>>(in, gate, add_x ? 1 : 0, out);
+}
+
+void launch_upadd(const TV& a, const TV& b, const TV& out, cudaStream_t s) {
+  const long total = long(a.n) * a.h * a.w * ((a.c + 7) / 8);
+  upadd_kernel<<<grid_for(total), kThreads, 0, s>>>(a, b, out);
+}
+
+void launch_upcat(const TV in[4], const int shift[4], int nin, const TV& out, cudaStream_t s) {
+  UpCatArgs a;
+  int off = 0;
+  for (int i = 0; i < 4; ++i) {
+    a.in[i] = i < nin ? in[i] : TV();
+    a.shift[i] = i < nin ? shift[i] : 0;
+    a.coff[i] = off;
+    if (i < nin) off += in[i].c;
+  }
+  a.nin = nin;
+  const long total = long(out.n) * out.h * out.w * ((out.c + 7) / 8);
+  upcat_kernel<<<grid_for(total), kThreads, 0, s>>>(a, out);
+}
+
+void launch_add(const TV& a, const TV& b, const TV& out, cudaStream_t s) {
+  const long total = long(a.n) * a.h * a.w * ((a.c + 7) / 8);
+  add_kernel<<<grid_for(total), kThreads, 0, s>>>(a, b, out);
+}
+
+void launch_pool(const TV& in, const TV& out, int kh, int kw, int sh, int sw, bool is_max, cudaStream_t s) {
+  const long total = long(out.n) * out.h * out.w * ((out.c + 7) / 8);
+  pool_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, kh, kw, sh, sw, is_max ? 1 : 0);
+}
+
+void launch_layernorm(const TV& in, const TV& out, const float* gb, float eps, cudaStream_t s) {
+  const long rows = long(in.n) * in.h * in.w;
+  const long blocks = (rows * 32 + kThreads - 1) / kThreads;
+  layernorm_kernel<<<int(blocks), kThreads, 0, s>>>(in, out, gb, eps);
+}
+
+void launch_attention(const TV& qkv, const TV& out, int heads, int hd, float scale, cudaStream_t s) {
+  const int T = qkv.h * qkv.w;
+  const size_t smem = (size_t(2) * T * hd + size_t(4) * T) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    configured = smem;
+  }
+  attention_kernel<<<qkv.n * heads, 128, smem, s>>>(qkv, out, heads, hd, scale);
+}
+
+void launch_dbhead(const TV& in, const float* blk, int cmid, float* prob, uint8_t* bitmap, int thresh_u8,
+                   cudaStream_t s) {
+  const long npix = long(in.n) * in.h * in.w;
+  if (in.c != 24 || cmid != 24) abort();
+  dbhead_kernel<24, 24><<<int((npix + 127) / 128), 128, 0, s>>>(in, blk, prob, bitmap, thresh_u8);
+}
+
+void launch_fc_softmax(const float* partial, int splits, int hw, int n, int cin, int cout, const float* blk,
+                       float* out, cudaStream_t s) {
+  if (cout > 8) abort();
+  fc_softmax_kernel<<<n, 32, 0, s>>>(partial, splits, 1.f / float(hw), cin, cout, blk, out);
+}
+
+void launch_ctc_head_simt(const TV& feat, const __half* w, const float* bias, int cin_pad, int ncls,
+                          int ncls_pad, int* idx, float* prob, cudaStream_t s) {
+  (void)ncls;
+  const long rows = long(feat.n) * feat.h * feat.w;
+  ctc_head_simt_kernel<<<int((rows + 7) / 8), kThreads, size_t(8) * cin_pad * sizeof(float), s>>>(
+      feat, w, bias, cin_pad, ncls_pad, idx, prob);
+}
+
+void launch_nchw3_to_input(const float* in, int n, int h, int w, __half* out, cudaStream_t s) {
+  nchw3_to_input_kernel<<<grid_for(long(n) * h * w), kThreads, 0, s>>>(in, n, h, w, out);
+}
+
+void launch_nhwc_to_nchw_f32(const TV& in, float* out, cudaStream_t s) {
+  const long total = long(in.n) * in.c * in.h * in.w;
+  nhwc_to_nchw_f32_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out);
+}
+
+}  // namespace b200ocr
