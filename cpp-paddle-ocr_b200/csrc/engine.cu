@@ -69,9 +69,16 @@ Net::Inst* Net::instantiate(int n, int h, int w) {
   auto fail = [&](const Layer& L, const char* why) {
     throw std::runtime_error("shape error at layer " + L.name + ": " + why);
   };
-  // ---- shape inference
+  // ---- shape inference (concat views made by re-homing have no producer: they take a member's shape)
+  auto resolve = [&](int t) {
+    if (I->ts[t].n == 0)
+      for (int u = 0; u < nt; ++u)
+        if (u != t && plan_.tensors[u].buf == plan_.tensors[t].buf && I->ts[u].n) { I->ts[t] = I->ts[u]; break; }
+    return I->ts[t];
+  };
   for (const Layer& L : plan_.layers) {
-    const Shape3 in = I->ts[L.in];
+    const Shape3 in = resolve(L.in);
+    if (in.n == 0) fail(L, "input shape unknown");
     Shape3 o = in;
     switch (L.kind) {
       case LKind::Conv:
@@ -121,12 +128,7 @@ Net::Inst* Net::instantiate(int n, int h, int w) {
     }
     I->ts[L.out] = o;
   }
-  // concat views created by re-homing have no producing layer: take the shape of a member
-  for (int t = 0; t < nt; ++t)
-    if (I->ts[t].n == 0) {
-      for (int u = 0; u < nt; ++u)
-        if (u != t && plan_.tensors[u].buf == plan_.tensors[t].buf && I->ts[u].n) { I->ts[t] = I->ts[u]; break; }
-    }
+  for (int t = 0; t < nt; ++t) resolve(t);
   // ---- buffer sizes
   I->boff.assign(nb, 0);
   I->bbytes.assign(nb, 0);

@@ -13,6 +13,7 @@ struct b200ocr_net {
   Net* net = nullptr;
   float* d_in = nullptr;
   size_t d_in_bytes = 0;
+  cudaStream_t stream = nullptr;
 };
 
 extern "C" {
@@ -27,7 +28,9 @@ int b200ocr_net_create(const char* model_dir, int device, int flags, b200ocr_net
     auto* h = new b200ocr_net();
     try {
       h->net = new Net(model_dir, device, o);
+      cuda_check(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate");
     } catch (...) {
+      delete h->net;
       delete h;
       throw;
     }
@@ -39,6 +42,7 @@ void b200ocr_net_destroy(b200ocr_net_t h) {
   if (!h) return;
   delete h->net;
   cudaFree(h->d_in);
+  if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
 
@@ -74,10 +78,10 @@ int b200ocr_net_forward(b200ocr_net_t h, const float* nchw, int n, int height, i
       cuda_check(cudaMalloc(&h->d_in, bytes), "cudaMalloc input staging");
       h->d_in_bytes = bytes;
     }
-    cuda_check(cudaMemcpy(h->d_in, nchw, bytes, cudaMemcpyHostToDevice), "input upload");
-    launch_nchw3_to_input(h->d_in, n, height, width, in, 0);
-    net.run(0, thresh_u8);
-    cuda_check(cudaDeviceSynchronize(), "forward");
+    cuda_check(cudaMemcpyAsync(h->d_in, nchw, bytes, cudaMemcpyHostToDevice, h->stream), "input upload");
+    launch_nchw3_to_input(h->d_in, n, height, width, in, h->stream);
+    net.run(h->stream, thresh_u8);
+    cuda_check(cudaStreamSynchronize(h->stream), "forward");
   });
 }
 

@@ -775,7 +775,9 @@ std::string Plan::dump() const {
      << wh.size() << " wf " << wf.size() << "\n";
   for (size_t i = 0; i < layers.size(); ++i) {
     const Layer& L = layers[i];
-    os << i << " " << kind_name(L.kind) << " " << L.name << " in=" << L.in;
+    // third column: the Paddle variable whose value the output tensor holds (last op of the fused chain)
+    const TensorDesc& ot = tensors[L.out];
+    os << i << " " << kind_name(L.kind) << " " << (ot.aliases.empty() ? ot.name : ot.aliases.back()) << " in=" << L.in;
     if (L.in2 >= 0) os << " in2=" << L.in2;
     if (L.kind == LKind::UpCat) os << " ins=" << L.ins[0] << "," << L.ins[1] << "," << L.ins[2] << "," << L.ins[3];
     os << " out=" << L.out << " c=" << L.cin << "->" << L.cout;

@@ -64,7 +64,7 @@ def synth_param(name: str, dims, model: str) -> np.ndarray:
         fan_in = dims[1] * dims[2] * dims[3]
         if name.startswith("conv2d_transpose"):
             fan_in = dims[0]
-        gain = 1.3 if model == "det" else 1.6  # keeps activations O(1) through both backbones
+        gain = 1.25 if model == "det" else 1.6  # keeps activations O(1) through both backbones
         a = rng.normal(0.0, gain / np.sqrt(fan_in), n)
     elif len(dims) == 2:  # linear [in, out]
         gain = 4.0 if dims[1] > 1000 else 1.2  # CTC fc: spread the logits so arg-max has a margin
