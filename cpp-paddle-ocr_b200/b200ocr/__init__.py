@@ -35,6 +35,7 @@ _sig("b200ocr_last_error", C.c_char_p)
 _sig("b200ocr_version", C.c_char_p)
 _sig("b200ocr_free", None, C.c_void_p)
 _sig("b200ocr_model_params_json", C.c_int, C.c_char_p, C.POINTER(C.c_void_p))
+_sig("b200ocr_model_plan_text", C.c_int, C.c_char_p, C.POINTER(C.c_void_p))
 _sig("b200ocr_net_create", C.c_int, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p))
 _sig("b200ocr_net_destroy", None, C.c_void_p)
 _sig("b200ocr_net_kind", C.c_int, C.c_void_p, C.c_char_p, C.c_int)
@@ -66,6 +67,13 @@ def model_params(pdmodel_path: str):
     p = C.c_void_p()
     check(lib.b200ocr_model_params_json(pdmodel_path.encode(), C.byref(p)))
     return [(d["name"], tuple(d["dims"])) for d in json.loads(_take_string(p))]
+
+
+def model_plan_text(model_dir: str) -> str:
+    """Fused-layer plan of a model directory, built on the host (no GPU)."""
+    p = C.c_void_p()
+    check(lib.b200ocr_model_plan_text(model_dir.encode(), C.byref(p)))
+    return _take_string(p)
 
 
 class Net:

@@ -4,6 +4,7 @@
 #include "../../include/b200ocr.h"
 #include "capi_util.h"
 #include "pd_model.h"
+#include "plan.h"
 #include <cstring>
 #include <sstream>
 
@@ -38,6 +39,24 @@ int b200ocr_model_params_json(const char* pdmodel_path, char** json) {
     *json = static_cast<char*>(malloc(s.size() + 1));
     if (!*json) throw std::bad_alloc();
     memcpy(*json, s.c_str(), s.size() + 1);
+  });
+}
+
+int b200ocr_model_plan_text(const char* model_dir, char** text) {
+  return b200ocr::capi_guard([&] {
+    if (!model_dir || !text) throw std::invalid_argument("null argument");
+    std::string mfile, pfile;
+    if (!b200ocr::find_model_files(model_dir, &mfile, &pfile))
+      throw std::runtime_error(std::string("No valid model file found in ") + model_dir);
+    b200ocr::PdProgram prog;
+    b200ocr::load_program(mfile, &prog);
+    b200ocr::load_params(pfile, &prog);
+    b200ocr::Plan plan;
+    b200ocr::build_plan(prog, &plan);
+    std::string s = plan.dump();
+    *text = static_cast<char*>(malloc(s.size() + 1));
+    if (!*text) throw std::bad_alloc();
+    memcpy(*text, s.c_str(), s.size() + 1);
   });
 }
 }

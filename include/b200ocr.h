@@ -43,6 +43,9 @@ void b200ocr_free(void* p);
 /* Lists the persistable parameters of a .pdmodel in `.pdiparams` order (ascending name) as JSON
  * [{"name":..., "dims":[...]}, ...].  Host-only (no GPU needed); free *json with b200ocr_free. */
 int b200ocr_model_params_json(const char* pdmodel_path, char** json);
+/* Builds the fused-layer plan of <model_dir> on the host (no GPU needed) and returns its text dump
+ * (one line per fused kernel).  Free *text with b200ocr_free. */
+int b200ocr_model_plan_text(const char* model_dir, char** text);
 
 /* ------------------------------------------------------------------ network-level entry points
  * One loaded .pdmodel/.pdiparams pair executing on one GPU; what `paddle_infer::Predictor`
