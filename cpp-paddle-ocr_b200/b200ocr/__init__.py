@@ -136,3 +136,262 @@ class Net:
     @property
     def launches(self) -> int:
         return lib.b200ocr_net_launches(self._h)
+
+
+# ----------------------------------------------------------------------------------------- stages
+class Image(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int), ("step", C.c_size_t)]
+
+
+class DetConfig(C.Structure):
+    _fields_ = [("model_dir", C.c_char_p), ("use_gpu", C.c_int), ("gpu_id", C.c_int), ("gpu_mem", C.c_int),
+                ("cpu_math_library_num_threads", C.c_int), ("use_mkldnn", C.c_int), ("limit_type", C.c_char_p),
+                ("limit_side_len", C.c_int), ("det_db_thresh", C.c_double), ("det_db_box_thresh", C.c_double),
+                ("det_db_unclip_ratio", C.c_double), ("det_db_score_mode", C.c_char_p), ("use_dilation", C.c_int),
+                ("use_tensorrt", C.c_int), ("precision", C.c_char_p)]
+
+
+class ClsConfig(C.Structure):
+    _fields_ = [("model_dir", C.c_char_p), ("use_gpu", C.c_int), ("gpu_id", C.c_int), ("gpu_mem", C.c_int),
+                ("cpu_math_library_num_threads", C.c_int), ("use_mkldnn", C.c_int), ("cls_thresh", C.c_double),
+                ("use_tensorrt", C.c_int), ("precision", C.c_char_p), ("cls_batch_num", C.c_int)]
+
+
+class RecConfig(C.Structure):
+    _fields_ = [("model_dir", C.c_char_p), ("use_gpu", C.c_int), ("gpu_id", C.c_int), ("gpu_mem", C.c_int),
+                ("cpu_math_library_num_threads", C.c_int), ("use_mkldnn", C.c_int), ("label_path", C.c_char_p),
+                ("use_tensorrt", C.c_int), ("precision", C.c_char_p), ("rec_batch_num", C.c_int),
+                ("rec_img_h", C.c_int), ("rec_img_w", C.c_int)]
+
+
+_P = C.POINTER
+_sig("b200ocr_host_alloc", C.c_void_p, C.c_size_t)
+_sig("b200ocr_host_free", None, C.c_void_p)
+_sig("b200ocr_device_count", C.c_int)
+_sig("b200ocr_det_create", C.c_int, _P(DetConfig), _P(C.c_void_p))
+_sig("b200ocr_det_destroy", None, C.c_void_p)
+_sig("b200ocr_det_run", C.c_int, C.c_void_p, _P(Image), C.c_void_p, C.c_int, _P(C.c_int), _P(C.c_double))
+_sig("b200ocr_det_run_batch", C.c_int, C.c_void_p, _P(Image), C.c_int, C.c_void_p, C.c_int, C.c_void_p, _P(C.c_double))
+_sig("b200ocr_det_postprocess", C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+     C.c_int, _P(C.c_int), C.c_void_p)
+_sig("b200ocr_det_preprocess", C.c_int, C.c_void_p, _P(Image), C.c_void_p, _P(C.c_int), _P(C.c_int), _P(C.c_float),
+     _P(C.c_float))
+_sig("b200ocr_cls_create", C.c_int, _P(ClsConfig), _P(C.c_void_p))
+_sig("b200ocr_cls_destroy", None, C.c_void_p)
+_sig("b200ocr_cls_run", C.c_int, C.c_void_p, _P(Image), C.c_int, C.c_void_p, C.c_void_p, _P(C.c_double))
+_sig("b200ocr_rec_create", C.c_int, _P(RecConfig), _P(C.c_void_p))
+_sig("b200ocr_rec_destroy", None, C.c_void_p)
+_sig("b200ocr_rec_run", C.c_int, C.c_void_p, _P(Image), C.c_int, _P(C.c_void_p), C.c_void_p, _P(C.c_double))
+_sig("b200ocr_worker_create", C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, _P(C.c_void_p))
+_sig("b200ocr_worker_destroy", None, C.c_void_p)
+_sig("b200ocr_worker_process", C.c_int, C.c_void_p, C.c_int, _P(Image), _P(C.c_void_p))
+_sig("b200ocr_worker_process_batch", C.c_int, C.c_void_p, _P(C.c_int), _P(Image), C.c_int, _P(C.c_void_p))
+_sig("b200ocr_worker_launches", C.c_longlong, C.c_void_p)
+_sig("b200ocr_pool_create", C.c_int, C.c_char_p, C.c_int, _P(C.c_int), C.c_int, C.c_int, C.c_int, _P(C.c_void_p))
+_sig("b200ocr_pool_destroy", None, C.c_void_p)
+_sig("b200ocr_pool_submit", C.c_int, C.c_void_p, C.c_int, _P(Image), _P(C.c_longlong))
+_sig("b200ocr_pool_wait", C.c_int, C.c_void_p, C.c_longlong, _P(C.c_void_p))
+_sig("b200ocr_pool_worker_count", C.c_int, C.c_void_p)
+_sig("b200ocr_pool_idle_count", C.c_int, C.c_void_p)
+_sig("b200ocr_resize_u8", C.c_int, C.c_int, _P(Image), C.c_int, C.c_int, C.c_void_p)
+_sig("b200ocr_crop_preprocess", C.c_int, C.c_int, _P(Image), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p)
+
+
+def device_count() -> int:
+    return lib.b200ocr_device_count()
+
+
+def as_image(a: np.ndarray) -> Image:
+    """View of a uint8 HxWx3 BGR array (what cv::Mat describes); an empty array maps to an empty image."""
+    if a is None or a.size == 0:
+        return Image(None, 0, 0, 0)
+    assert a.dtype == np.uint8 and a.ndim == 3 and a.shape[2] == 3 and a.strides[2] == 1 and a.strides[1] == 3
+    return Image(a.ctypes.data, a.shape[0], a.shape[1], a.strides[0])
+
+
+def _images(arrs):
+    keep = [a if (a is None or a.size == 0 or a.strides[1:] == (3, 1)) else np.ascontiguousarray(a) for a in arrs]
+    return (Image * len(keep))(*[as_image(a) for a in keep]), keep
+
+
+def pinned_array(shape, dtype=np.uint8) -> np.ndarray:
+    """numpy array over page-locked host memory from b200ocr_host_alloc (freed when the array is collected)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib.b200ocr_host_alloc(n)
+    if not p:
+        raise Error("b200ocr_host_alloc failed")
+    buf = (C.c_uint8 * n).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    import weakref
+    weakref.finalize(buf, lib.b200ocr_host_free, p)
+    return arr
+
+
+class _Handle:
+    _destroy = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Detector(_Handle):
+    """DBDetector (reference include/paddle_ocr/ocr_det.h:60-97)."""
+    _destroy = staticmethod(lib.b200ocr_det_destroy)
+
+    def __init__(self, model_dir, gpu_id=0, limit_type="max", limit_side_len=960, det_db_thresh=0.3,
+                 det_db_box_thresh=0.5, det_db_unclip_ratio=2.0, det_db_score_mode="fast", use_dilation=False):
+        cfg = DetConfig(model_dir.encode(), 1, gpu_id, 0, 1, 0, limit_type.encode(), limit_side_len, det_db_thresh,
+                        det_db_box_thresh, det_db_unclip_ratio, det_db_score_mode.encode(), int(use_dilation), 0, b"fp32")
+        self._h = C.c_void_p()
+        check(lib.b200ocr_det_create(C.byref(cfg), C.byref(self._h)))
+
+    def run_batch(self, imgs, cap=1000):
+        arr, keep = _images(imgs)
+        n = len(imgs)
+        boxes = np.zeros((n, cap, 4, 2), np.int32)
+        counts = np.zeros(n, np.int32)
+        times = (C.c_double * 3)()
+        check(lib.b200ocr_det_run_batch(self._h, arr, n, boxes.ctypes.data, cap, counts.ctypes.data, times))
+        self.times = list(times)
+        return [boxes[i, :min(int(counts[i]), cap)].copy() for i in range(n)]
+
+    def run(self, img, cap=1000):
+        return self.run_batch([img], cap)[0]
+
+    def preprocess(self, img):
+        arr, keep = _images([img])
+        rh, rw, a, b = C.c_int(), C.c_int(), C.c_float(), C.c_float()
+        check(lib.b200ocr_det_preprocess(self._h, arr, None, C.byref(rh), C.byref(rw), C.byref(a), C.byref(b)))
+        out = np.empty((3, rh.value, rw.value), np.float32)
+        check(lib.b200ocr_det_preprocess(self._h, arr, out.ctypes.data, C.byref(rh), C.byref(rw), C.byref(a), C.byref(b)))
+        return out, a.value, b.value
+
+    def postprocess(self, pred, src_h, src_w, cap=1000, want_bitmap=False):
+        pred = np.ascontiguousarray(pred, np.float32)
+        h, w = pred.shape
+        boxes = np.zeros((cap, 4, 2), np.int32)
+        n = C.c_int()
+        bm = np.empty((h, w), np.uint8) if want_bitmap else None
+        check(lib.b200ocr_det_postprocess(self._h, pred.ctypes.data, h, w, src_h, src_w, boxes.ctypes.data, cap,
+                                          C.byref(n), bm.ctypes.data if want_bitmap else None))
+        out = boxes[:min(n.value, cap)].copy()
+        return (out, bm) if want_bitmap else out
+
+
+class Classifier(_Handle):
+    """Classifier (reference include/paddle_ocr/ocr_cls.h:57-82)."""
+    _destroy = staticmethod(lib.b200ocr_cls_destroy)
+
+    def __init__(self, model_dir, gpu_id=0, cls_thresh=0.9, cls_batch_num=1):
+        cfg = ClsConfig(model_dir.encode(), 1, gpu_id, 0, 1, 0, cls_thresh, 0, b"fp32", cls_batch_num)
+        self._h = C.c_void_p()
+        check(lib.b200ocr_cls_create(C.byref(cfg), C.byref(self._h)))
+
+    def run(self, imgs):
+        arr, keep = _images(imgs)
+        n = len(imgs)
+        labels = np.zeros(n, np.int32)
+        scores = np.zeros(n, np.float32)
+        times = (C.c_double * 3)()
+        check(lib.b200ocr_cls_run(self._h, arr, n, labels.ctypes.data, scores.ctypes.data, times))
+        return labels, scores
+
+
+class Recognizer(_Handle):
+    """CRNNRecognizer (reference include/paddle_ocr/ocr_rec.h:61-95)."""
+    _destroy = staticmethod(lib.b200ocr_rec_destroy)
+
+    def __init__(self, model_dir, label_path, gpu_id=0, rec_batch_num=6, rec_img_h=48, rec_img_w=320):
+        cfg = RecConfig(model_dir.encode(), 1, gpu_id, 0, 1, 0, label_path.encode(), 0, b"fp32", rec_batch_num,
+                        rec_img_h, rec_img_w)
+        self._h = C.c_void_p()
+        check(lib.b200ocr_rec_create(C.byref(cfg), C.byref(self._h)))
+
+    def run(self, imgs):
+        arr, keep = _images(imgs)
+        n = len(imgs)
+        texts = (C.c_void_p * n)()
+        scores = np.zeros(n, np.float32)
+        times = (C.c_double * 3)()
+        check(lib.b200ocr_rec_run(self._h, arr, n, texts, scores.ctypes.data, times))
+        self.times = list(times)
+        return [_take_string(C.c_void_p(t)) for t in texts], scores
+
+
+class Worker(_Handle):
+    """OCRWorker::processRequest + result JSON (reference src/ocr_worker.cpp:133-311)."""
+    _destroy = staticmethod(lib.b200ocr_worker_destroy)
+
+    def __init__(self, worker_id, model_dir, gpu_id=0, enable_cls=False):
+        self._h = C.c_void_p()
+        check(lib.b200ocr_worker_create(worker_id, model_dir.encode(), 1, gpu_id, int(enable_cls), C.byref(self._h)))
+
+    def process(self, request_id, img) -> str:
+        arr, keep = _images([img])
+        p = C.c_void_p()
+        check(lib.b200ocr_worker_process(self._h, request_id, arr, C.byref(p)))
+        return _take_string(p)
+
+    def process_batch(self, request_ids, imgs):
+        arr, keep = _images(imgs)
+        n = len(imgs)
+        ids = (C.c_int * n)(*request_ids)
+        out = (C.c_void_p * n)()
+        check(lib.b200ocr_worker_process_batch(self._h, ids, arr, n, out))
+        return [_take_string(C.c_void_p(t)) for t in out]
+
+    @property
+    def launches(self) -> int:
+        return lib.b200ocr_worker_launches(self._h)
+
+
+class Pool(_Handle):
+    """Per-device worker pool (replaces the reference's GPUWorkerPool, src/gpu_worker_pool.cpp:8-59)."""
+    _destroy = staticmethod(lib.b200ocr_pool_destroy)
+
+    def __init__(self, model_dir, devices=(0,), workers_per_device=1, enable_cls=False, max_batch=64):
+        self._h = C.c_void_p()
+        dv = (C.c_int * len(devices))(*devices)
+        check(lib.b200ocr_pool_create(model_dir.encode(), len(devices), dv, workers_per_device, int(enable_cls),
+                                      max_batch, C.byref(self._h)))
+
+    def submit(self, request_id, img) -> int:
+        arr, keep = _images([img])
+        t = C.c_longlong()
+        check(lib.b200ocr_pool_submit(self._h, request_id, arr, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket) -> str:
+        p = C.c_void_p()
+        check(lib.b200ocr_pool_wait(self._h, ticket, C.byref(p)))
+        return _take_string(p)
+
+    @property
+    def worker_count(self):
+        return lib.b200ocr_pool_worker_count(self._h)
+
+    @property
+    def idle_count(self):
+        return lib.b200ocr_pool_idle_count(self._h)
+
+
+def resize_u8(img, dst_rows, dst_cols, device=0):
+    arr, keep = _images([img])
+    out = np.empty((dst_rows, dst_cols, 3), np.uint8)
+    check(lib.b200ocr_resize_u8(device, arr, dst_rows, dst_cols, out.ctypes.data))
+    return out
+
+
+def crop_preprocess(crops, kind, img_h, img_w, device=0):
+    arr, keep = _images(crops)
+    out = np.empty((len(crops), 3, img_h, img_w), np.float32)
+    check(lib.b200ocr_crop_preprocess(device, arr, len(crops), 0 if kind == "rec" else 1, img_h, img_w, out.ctypes.data))
+    return out

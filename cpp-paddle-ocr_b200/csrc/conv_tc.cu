@@ -366,11 +366,8 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
   impl->args = a;
   impl->grid = dim3(unsigned(a.tiles_x * a.tiles_y * tiles_n), unsigned(n_tiles));
   impl->smem = size_t(a.stages) * (kATileBytes + a.bn * 128) + 1024 + 128;
-  static size_t configured = 0;
-  if (impl->smem > configured) {
-    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = 200 * 1024;
-  }
+  // per device (function attributes live in the context): cheap, done once per (layer, shape)
+  cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   ConvTcPlan p;
   p.impl = impl;
   return p;

@@ -73,6 +73,43 @@ bool ctc_tc_eligible(const TV& feat, int cin_pad);
 void launch_ctc_head_tc(const TV& feat, const __half* w, const float* bias, int cin_pad, int ncls,
                         int ncls_pad, int* idx, float* prob, cudaStream_t s);
 
+// ---- pre-processing (preproc.cu) ---------------------------------------------------
+struct NormParams { float scale[3], shift[3]; };  // y = (u8 * (1/255.f)) * scale + shift, per BGR channel
+NormParams make_norm(const float mean[3], const float scale[3]);
+struct DetPreItem { const uint8_t* src; int w, h; long stride; };          // one source image (device memory)
+struct CropItem { const uint8_t* img; long stride; int x, y, w, h, resize_w; };  // ROI of a device image
+// [n] images -> [n, dh, dw] network input; every image is resized to the same dh x dw
+void launch_det_preprocess(const DetPreItem* items_dev, int n, int dh, int dw, const NormParams& np, __half* out,
+                           cudaStream_t s);
+// [n] ROIs -> [n, dh, dw]; columns >= resize_w hold pad_value (rec: -1 = normalised u8 zero; cls: 0)
+void launch_crop_preprocess(const CropItem* items_dev, int n, int dh, int dw, const NormParams& np, float pad_value,
+                            __half* out, cudaStream_t s);
+void launch_rotate180_if(uint8_t* img, long stride, int x0, int y0, int w, int h, const int* label_dev, cudaStream_t s);
+void launch_resize_u8(const uint8_t* src, int sw, int sh, long stride, int dw, int dh, uint8_t* out, cudaStream_t s);
+
+// ---- DB post-process (dbpost.cu) ------------------------------------------------------
+struct DbPostParams {
+  int n, h, w;            // batch of bitmaps / probability maps
+  float box_thresh, unclip_ratio;
+  int max_candidates;     // 1000 in the reference
+};
+struct DbImageInfo { float ratio_h, ratio_w; int src_h, src_w; };
+struct DbBox { int valid; int pts[8]; float score; int start; };  // start = start pixel (y*w+x) of the contour
+size_t dbpost_workspace_bytes(const DbPostParams& p);
+// prob [n,h,w] fp32, bitmap [n,h,w] u8 (0/255), info [n] (device).  Writes counts[n] and boxes[n][max_candidates]
+// (device), contour order = the reference's (cv::findContours RETR_LIST order).
+void launch_dbpost(const DbPostParams& p, const float* prob, const uint8_t* bitmap, const DbImageInfo* info_dev,
+                   void* workspace, int* counts_dev, DbBox* boxes_dev, cudaStream_t s);
+// cbuf = (uchar)(p * 255); bit = cbuf > thresh_u8 ? 255 : 0   (reference src/ocr_det.cpp:143-154)
+void launch_threshold(const float* prob, long n, int thresh_u8, uint8_t* bitmap, cudaStream_t s);
+void launch_dilate2x2(const uint8_t* in, uint8_t* out, int n, int h, int w, cudaStream_t s);
+// debug: contour start pixels + bounding boxes of the last launch_dbpost are left in the workspace; see dbpost.cu
+
+// ---- CTC collapse (ctc.cu) -------------------------------------------------------------
+// idx/prob [n, T] from the CTC head -> out_idx [n, T] (collapsed label ids), out_len [n], out_score [n]
+void launch_ctc_collapse(const int* idx, const float* prob, int n, int T, int* out_idx, int* out_len,
+                         float* out_score, cudaStream_t s);
+
 // debug / test helpers
 void launch_nhwc_to_nchw_f32(const TV& in, float* out, cudaStream_t s);
 // fp32 NCHW (3 channels) -> network input NHWC fp16, channel pitch 8, channels 3..7 zero

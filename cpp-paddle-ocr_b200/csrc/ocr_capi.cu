@@ -1,0 +1,481 @@
+// C ABI of the stages, the worker and the per-device pool (declared in include/b200ocr.h).
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <thread>
+
+#include "../../include/b200ocr.h"
+#include "capi_util.h"
+#include "stages.h"
+
+using namespace b200ocr;
+
+namespace {
+
+char* dup_string(const std::string& s) {
+  char* p = static_cast<char*>(malloc(s.size() + 1));
+  if (!p) throw std::bad_alloc();
+  memcpy(p, s.c_str(), s.size() + 1);
+  return p;
+}
+
+HostImage to_host(const b200ocr_image& im) {
+  HostImage h;
+  h.data = im.data; h.rows = im.rows; h.cols = im.cols;
+  h.step = im.step ? im.step : size_t(im.cols) * 3;
+  return h;
+}
+
+void need_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
+    throw std::runtime_error("no CUDA device is available: b200ocr has no CPU fallback");
+  if (device < 0 || device >= n) throw std::invalid_argument("gpu_id " + std::to_string(device) + " out of range");
+}
+
+struct StageBase {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  ImageBatch batch;
+  void init(int dev) {
+    need_device(dev);
+    device = dev;
+    cuda_check(cudaSetDevice(dev), "cudaSetDevice");
+    cuda_check(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  }
+  ~StageBase() { if (stream) { cudaSetDevice(device); cudaStreamDestroy(stream); } }
+  const std::vector<DevImg>& upload(const b200ocr_image* imgs, int n) {
+    std::vector<HostImage> h(n);
+    for (int i = 0; i < n; ++i) {
+      if (!imgs[i].data || imgs[i].rows <= 0 || imgs[i].cols <= 0) throw std::invalid_argument("empty image");
+      h[i] = to_host(imgs[i]);
+    }
+    cuda_check(cudaSetDevice(device), "cudaSetDevice");
+    batch.upload(h.data(), n, stream);
+    return batch.images();
+  }
+};
+
+std::vector<Roi> full_rois(const std::vector<DevImg>& d) {
+  std::vector<Roi> r(d.size());
+  for (size_t i = 0; i < d.size(); ++i) { r[i].img = int(i); r[i].x = 0; r[i].y = 0; r[i].w = d[i].cols; r[i].h = d[i].rows; }
+  return r;
+}
+
+}  // namespace
+
+struct b200ocr_det : StageBase { std::unique_ptr<DetStage> st; DetParams p; };
+struct b200ocr_cls : StageBase { std::unique_ptr<ClsStage> st; };
+struct b200ocr_rec : StageBase { std::unique_ptr<RecStage> st; };
+struct b200ocr_worker { std::unique_ptr<Worker> w; };
+
+// ------------------------------------------------------------------------------------------------ pool
+struct b200ocr_pool {
+  struct Request {
+    long long ticket;
+    int request_id;
+    std::vector<uint8_t> pixels;  // deep copy, like OCRRequest (reference include/paddle_ocr/ocr_worker.h:28-29)
+    int rows, cols;
+  };
+  struct Device {
+    int device;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::shared_ptr<Request>> queue;
+    std::vector<std::thread> threads;
+    std::vector<std::unique_ptr<Worker>> workers;
+    std::atomic<int> busy{0};
+  };
+  std::vector<std::unique_ptr<Device>> devs;
+  std::atomic<bool> running{true};
+  std::atomic<long long> next_ticket{1};
+  std::atomic<size_t> rr{0};
+  std::mutex res_mu;
+  std::condition_variable res_cv;
+  std::map<long long, std::string> results;
+  int max_batch = 64;
+
+  void loop(Device* d, Worker* w) {
+    while (true) {
+      std::vector<std::shared_ptr<Request>> take;
+      {
+        std::unique_lock<std::mutex> lk(d->mu);
+        d->cv.wait(lk, [&] { return !d->queue.empty() || !running; });
+        if (d->queue.empty()) { if (!running) return; continue; }
+        while (!d->queue.empty() && int(take.size()) < max_batch) { take.push_back(d->queue.front()); d->queue.pop_front(); }
+        d->busy += 1;
+      }
+      std::vector<int> ids(take.size());
+      std::vector<HostImage> imgs(take.size());
+      for (size_t i = 0; i < take.size(); ++i) {
+        ids[i] = take[i]->request_id;
+        imgs[i].data = take[i]->pixels.empty() ? nullptr : take[i]->pixels.data();
+        imgs[i].rows = take[i]->rows; imgs[i].cols = take[i]->cols; imgs[i].step = size_t(take[i]->cols) * 3;
+      }
+      std::vector<std::string> out;
+      try {
+        w->process_batch(ids.data(), imgs.data(), int(take.size()), &out);
+      } catch (const std::exception& e) {
+        // reference src/ocr_worker.cpp:192-206: request_id, success=false, error, worker_id
+        out.assign(take.size(), std::string());
+        for (size_t i = 0; i < take.size(); ++i)
+          out[i] = "{\"error\":" + json_quote(e.what()) + ",\"request_id\":" + std::to_string(ids[i]) +
+                   ",\"success\":false,\"worker_id\":" + std::to_string(w->worker_id()) + "}";
+      }
+      {
+        std::lock_guard<std::mutex> lk(res_mu);
+        for (size_t i = 0; i < take.size(); ++i) results[take[i]->ticket] = std::move(out[i]);
+      }
+      res_cv.notify_all();
+      d->busy -= 1;
+    }
+  }
+
+  ~b200ocr_pool() {
+    running = false;
+    for (auto& d : devs) {
+      { std::lock_guard<std::mutex> lk(d->mu); }
+      d->cv.notify_all();
+      for (auto& t : d->threads) if (t.joinable()) t.join();
+    }
+  }
+};
+
+extern "C" {
+
+void* b200ocr_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void b200ocr_host_free(void* p) { if (p) cudaFreeHost(p); }
+int b200ocr_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// ---- det
+int b200ocr_det_create(const b200ocr_det_config* c, b200ocr_det_t* out) {
+  return capi_guard([&] {
+    if (!c || !out || !c->model_dir) throw std::invalid_argument("null argument");
+    auto h = std::make_unique<b200ocr_det>();
+    h->init(c->gpu_id);
+    h->p.limit_type = c->limit_type ? c->limit_type : "max";
+    h->p.limit_side_len = c->limit_side_len;
+    h->p.det_db_thresh = c->det_db_thresh;
+    h->p.det_db_box_thresh = c->det_db_box_thresh;
+    h->p.det_db_unclip_ratio = c->det_db_unclip_ratio;
+    h->p.det_db_score_mode = c->det_db_score_mode ? c->det_db_score_mode : "slow";
+    h->p.use_dilation = c->use_dilation != 0;
+    h->st = std::make_unique<DetStage>(c->model_dir, c->gpu_id, h->p);
+    *out = h.release();
+  });
+}
+void b200ocr_det_destroy(b200ocr_det_t d) { if (d) { cudaSetDevice(d->device); delete d; } }
+
+int b200ocr_det_run_batch(b200ocr_det_t d, const b200ocr_image* imgs, int n, int32_t* boxes, int cap, int* counts,
+                          double times[3]) {
+  return capi_guard([&] {
+    if (!d || !imgs || n < 0 || !counts || (cap > 0 && !boxes)) throw std::invalid_argument("null argument");
+    const auto& dev = d->upload(imgs, n);
+    std::vector<std::vector<Box>> res;
+    std::vector<double> t;
+    d->st->run(dev, &res, d->stream, &t);
+    for (int i = 0; i < n; ++i) {
+      counts[i] = int(res[i].size());
+      for (int k = 0; k < counts[i] && k < cap; ++k) memcpy(boxes + (size_t(i) * cap + k) * 8, res[i][k].data(), 32);
+    }
+    if (times) for (int k = 0; k < 3; ++k) times[k] = t[k];
+  });
+}
+int b200ocr_det_run(b200ocr_det_t d, const b200ocr_image* img, int32_t* boxes, int cap, int* n_boxes, double times[3]) {
+  return b200ocr_det_run_batch(d, img, 1, boxes, cap, n_boxes, times);
+}
+
+int b200ocr_det_preprocess(b200ocr_det_t d, const b200ocr_image* img, float* nchw, int* rh, int* rw, float* ratio_h,
+                           float* ratio_w) {
+  return capi_guard([&] {
+    if (!d || !img || !rh || !rw) throw std::invalid_argument("null argument");
+    float a, b;
+    DetStage::resized_dims(img->rows, img->cols, d->p.limit_type, d->p.limit_side_len, rh, rw, &a, &b);
+    if (ratio_h) *ratio_h = a;
+    if (ratio_w) *ratio_w = b;
+    if (!nchw) return;
+    const auto& dev = d->upload(img, 1);
+    DevBuf items, in, out;
+    items.ensure(sizeof(DetPreItem));
+    in.ensure(size_t(*rh) * *rw * 8 * sizeof(__half));
+    out.ensure(size_t(*rh) * *rw * 3 * sizeof(float));
+    DetPreItem it{dev[0].p, dev[0].cols, dev[0].rows, dev[0].stride};
+    cuda_check(cudaMemcpyAsync(items.p, &it, sizeof it, cudaMemcpyHostToDevice, d->stream), "items");
+    static const float mean[3] = {0.485f, 0.456f, 0.406f};
+    static const float scale[3] = {1 / 0.229f, 1 / 0.224f, 1 / 0.225f};
+    launch_det_preprocess(items.as<DetPreItem>(), 1, *rh, *rw, make_norm(mean, scale), in.as<__half>(), d->stream);
+    TV v;
+    v.p = in.as<__half>(); v.n = 1; v.h = *rh; v.w = *rw; v.c = 3; v.pitch = 8;
+    launch_nhwc_to_nchw_f32(v, out.as<float>(), d->stream);
+    cuda_check(cudaMemcpyAsync(nchw, out.p, size_t(*rh) * *rw * 3 * sizeof(float), cudaMemcpyDeviceToHost, d->stream), "copy");
+    cuda_check(cudaStreamSynchronize(d->stream), "det preprocess");
+  });
+}
+
+int b200ocr_det_postprocess(b200ocr_det_t d, const float* pred, int h, int w, int src_h, int src_w, int32_t* boxes,
+                            int cap, int* n_boxes, uint8_t* bitmap_out) {
+  return capi_guard([&] {
+    if (!d || !pred || h < 1 || w < 1 || !n_boxes) throw std::invalid_argument("bad argument");
+    cuda_check(cudaSetDevice(d->device), "cudaSetDevice");
+    cudaStream_t s = d->stream;
+    const size_t px = size_t(h) * w;
+    DevBuf dp, db, dd, info, ws, counts, bx;
+    dp.ensure(px * 4); db.ensure(px); dd.ensure(px);
+    cuda_check(cudaMemcpyAsync(dp.p, pred, px * 4, cudaMemcpyHostToDevice, s), "pred upload");
+    const int thr = int(std::floor(double(float(d->p.det_db_thresh)) * 255));
+    launch_threshold(dp.as<float>(), long(px), thr, db.as<uint8_t>(), s);
+    const uint8_t* bm = db.as<uint8_t>();
+    if (d->p.use_dilation) { launch_dilate2x2(bm, dd.as<uint8_t>(), 1, h, w, s); bm = dd.as<uint8_t>(); }
+    DbPostParams pp;
+    pp.n = 1; pp.h = h; pp.w = w;
+    pp.box_thresh = float(d->p.det_db_box_thresh);
+    pp.unclip_ratio = float(d->p.det_db_unclip_ratio);
+    pp.max_candidates = 1000;
+    DbImageInfo inf;
+    // the detector feeds a map of the resized size; ratios as DBDetector::Run computes them (src/preprocess_op.cpp:91-92)
+    inf.ratio_h = float(h) / float(src_h);
+    inf.ratio_w = float(w) / float(src_w);
+    inf.src_h = src_h; inf.src_w = src_w;
+    info.ensure(sizeof inf);
+    cuda_check(cudaMemcpyAsync(info.p, &inf, sizeof inf, cudaMemcpyHostToDevice, s), "info");
+    ws.ensure(dbpost_workspace_bytes(pp));
+    counts.ensure(4);
+    bx.ensure(sizeof(DbBox) * pp.max_candidates);
+    launch_dbpost(pp, dp.as<float>(), bm, info.as<DbImageInfo>(), ws.p, counts.as<int>(), bx.as<DbBox>(), s);
+    int cnt = 0;
+    std::vector<DbBox> hb(pp.max_candidates);
+    cuda_check(cudaMemcpyAsync(&cnt, counts.p, 4, cudaMemcpyDeviceToHost, s), "counts");
+    cuda_check(cudaMemcpyAsync(hb.data(), bx.p, sizeof(DbBox) * pp.max_candidates, cudaMemcpyDeviceToHost, s), "boxes");
+    if (bitmap_out) cuda_check(cudaMemcpyAsync(bitmap_out, bm, px, cudaMemcpyDeviceToHost, s), "bitmap");
+    cuda_check(cudaStreamSynchronize(s), "det postprocess");
+    int m = 0;
+    for (int c = 0; c < cnt; ++c) {
+      if (!hb[c].valid) continue;
+      if (m < cap && boxes) memcpy(boxes + size_t(m) * 8, hb[c].pts, 32);
+      ++m;
+    }
+    *n_boxes = m;
+  });
+}
+
+// ---- cls
+int b200ocr_cls_create(const b200ocr_cls_config* c, b200ocr_cls_t* out) {
+  return capi_guard([&] {
+    if (!c || !out || !c->model_dir) throw std::invalid_argument("null argument");
+    auto h = std::make_unique<b200ocr_cls>();
+    h->init(c->gpu_id);
+    h->st = std::make_unique<ClsStage>(c->model_dir, c->gpu_id, c->cls_batch_num > 0 ? c->cls_batch_num : 1,
+                                       float(c->cls_thresh));
+    *out = h.release();
+  });
+}
+void b200ocr_cls_destroy(b200ocr_cls_t c) { if (c) { cudaSetDevice(c->device); delete c; } }
+int b200ocr_cls_run(b200ocr_cls_t c, const b200ocr_image* imgs, int n, int* cls_labels, float* cls_scores,
+                    double times[3]) {
+  return capi_guard([&] {
+    if (!c || (n > 0 && (!imgs || !cls_labels || !cls_scores)) || n < 0) throw std::invalid_argument("null argument");
+    std::vector<double> t;
+    if (n > 0) {
+      const auto& dev = c->upload(imgs, n);
+      std::vector<int> labels;
+      std::vector<float> scores;
+      c->st->run(dev, full_rois(dev), &labels, &scores, c->stream, true, &t);
+      memcpy(cls_labels, labels.data(), sizeof(int) * n);
+      memcpy(cls_scores, scores.data(), sizeof(float) * n);
+    } else t.assign(3, 0.0);
+    if (times) for (int k = 0; k < 3; ++k) times[k] = t[k];
+  });
+}
+
+// ---- rec
+int b200ocr_rec_create(const b200ocr_rec_config* c, b200ocr_rec_t* out) {
+  return capi_guard([&] {
+    if (!c || !out || !c->model_dir || !c->label_path) throw std::invalid_argument("null argument");
+    auto h = std::make_unique<b200ocr_rec>();
+    h->init(c->gpu_id);
+    h->st = std::make_unique<RecStage>(c->model_dir, c->gpu_id, c->label_path, c->rec_batch_num > 0 ? c->rec_batch_num : 1,
+                                       c->rec_img_h, c->rec_img_w);
+    *out = h.release();
+  });
+}
+void b200ocr_rec_destroy(b200ocr_rec_t r) { if (r) { cudaSetDevice(r->device); delete r; } }
+int b200ocr_rec_run(b200ocr_rec_t r, const b200ocr_image* imgs, int n, char** rec_texts, float* rec_text_scores,
+                    double times[3]) {
+  return capi_guard([&] {
+    if (!r || (n > 0 && (!imgs || !rec_texts || !rec_text_scores)) || n < 0) throw std::invalid_argument("null argument");
+    std::vector<double> t(3, 0.0);
+    if (n > 0) {
+      const auto& dev = r->upload(imgs, n);
+      std::vector<std::vector<Roi>> calls(1, full_rois(dev));
+      std::vector<std::vector<std::string>> texts;
+      std::vector<std::vector<float>> scores;
+      t.clear();
+      r->st->run(dev, calls, &texts, &scores, r->stream, &t);
+      for (int i = 0; i < n; ++i) { rec_texts[i] = dup_string(texts[0][i]); rec_text_scores[i] = scores[0][i]; }
+    }
+    if (times) for (int k = 0; k < 3; ++k) times[k] = t[k];
+  });
+}
+
+// ---- worker
+int b200ocr_worker_create(int worker_id, const char* model_dir, int use_gpu, int gpu_id, int enable_cls,
+                          b200ocr_worker_t* out) {
+  return capi_guard([&] {
+    (void)use_gpu;
+    if (!model_dir || !out) throw std::invalid_argument("null argument");
+    need_device(gpu_id);
+    auto h = std::make_unique<b200ocr_worker>();
+    WorkerOptions o;
+    o.enable_cls = enable_cls != 0;
+    h->w = std::make_unique<Worker>(worker_id, model_dir, gpu_id, o);
+    *out = h.release();
+  });
+}
+void b200ocr_worker_destroy(b200ocr_worker_t w) { delete w; }
+int b200ocr_worker_process_batch(b200ocr_worker_t w, const int* request_ids, const b200ocr_image* imgs, int n,
+                                 char** jsons) {
+  return capi_guard([&] {
+    if (!w || n < 0 || (n > 0 && (!request_ids || !imgs || !jsons))) throw std::invalid_argument("null argument");
+    std::vector<HostImage> h(n);
+    for (int i = 0; i < n; ++i) h[i] = to_host(imgs[i]);
+    std::vector<std::string> out;
+    w->w->process_batch(request_ids, h.data(), n, &out);
+    for (int i = 0; i < n; ++i) jsons[i] = dup_string(out[i]);
+  });
+}
+int b200ocr_worker_process(b200ocr_worker_t w, int request_id, const b200ocr_image* img, char** json) {
+  return b200ocr_worker_process_batch(w, &request_id, img, 1, json);
+}
+long long b200ocr_worker_launches(b200ocr_worker_t w) { return w ? w->w->launches() : 0; }
+
+// ---- pool
+int b200ocr_pool_create(const char* model_dir, int n_devices, const int* devices, int workers_per_device,
+                        int enable_cls, int max_batch, b200ocr_pool_t* out) {
+  return capi_guard([&] {
+    if (!model_dir || !out || n_devices < 1 || workers_per_device < 1) throw std::invalid_argument("bad argument");
+    auto p = std::make_unique<b200ocr_pool>();
+    p->max_batch = max_batch > 0 ? max_batch : 64;
+    int wid = 0;
+    for (int i = 0; i < n_devices; ++i) {
+      const int dev = devices ? devices[i] : i;
+      need_device(dev);
+      auto d = std::make_unique<b200ocr_pool::Device>();
+      d->device = dev;
+      WorkerOptions o;
+      o.enable_cls = enable_cls != 0;
+      o.max_batch = p->max_batch;
+      for (int k = 0; k < workers_per_device; ++k) d->workers.push_back(std::make_unique<Worker>(wid++, model_dir, dev, o));
+      p->devs.push_back(std::move(d));
+    }
+    for (auto& d : p->devs)
+      for (auto& w : d->workers) d->threads.emplace_back(&b200ocr_pool::loop, p.get(), d.get(), w.get());
+    *out = p.release();
+  });
+}
+void b200ocr_pool_destroy(b200ocr_pool_t pool) { delete pool; }
+
+int b200ocr_pool_submit(b200ocr_pool_t pool, int request_id, const b200ocr_image* img, long long* ticket) {
+  return capi_guard([&] {
+    if (!pool || !img || !ticket) throw std::invalid_argument("null argument");
+    auto r = std::make_shared<b200ocr_pool::Request>();
+    r->ticket = pool->next_ticket++;
+    r->request_id = request_id;
+    r->rows = img->rows; r->cols = img->cols;
+    if (img->data && img->rows > 0 && img->cols > 0) {
+      const size_t row = size_t(img->cols) * 3, step = img->step ? img->step : row;
+      r->pixels.resize(row * img->rows);
+      for (int y = 0; y < img->rows; ++y) memcpy(r->pixels.data() + y * row, img->data + y * step, row);
+    }
+    // shortest queue first; ties broken round-robin (reference src/gpu_worker_pool.cpp:46-59: idle worker, else round-robin)
+    const size_t nd = pool->devs.size(), start = pool->rr++ % nd;
+    size_t best = start, best_load = ~size_t(0);
+    for (size_t k = 0; k < nd; ++k) {
+      auto& d = *pool->devs[(start + k) % nd];
+      std::lock_guard<std::mutex> lk(d.mu);
+      const size_t load = d.queue.size() + size_t(d.busy.load()) * size_t(pool->max_batch);
+      if (load < best_load) { best_load = load; best = (start + k) % nd; }
+    }
+    auto& d = *pool->devs[best];
+    { std::lock_guard<std::mutex> lk(d.mu); d.queue.push_back(r); }
+    d.cv.notify_one();
+    *ticket = r->ticket;
+  });
+}
+
+int b200ocr_pool_wait(b200ocr_pool_t pool, long long ticket, char** json) {
+  return capi_guard([&] {
+    if (!pool || !json) throw std::invalid_argument("null argument");
+    std::unique_lock<std::mutex> lk(pool->res_mu);
+    pool->res_cv.wait(lk, [&] { return pool->results.count(ticket) != 0; });
+    *json = dup_string(pool->results[ticket]);
+    pool->results.erase(ticket);
+  });
+}
+int b200ocr_pool_worker_count(b200ocr_pool_t pool) {
+  int n = 0;
+  if (pool) for (auto& d : pool->devs) n += int(d->workers.size());
+  return n;
+}
+int b200ocr_pool_idle_count(b200ocr_pool_t pool) {
+  int n = 0;
+  if (pool) for (auto& d : pool->devs) n += int(d->workers.size()) - d->busy.load();
+  return n;
+}
+
+// ---- stand-alone image ops
+int b200ocr_resize_u8(int device, const b200ocr_image* src, int dst_rows, int dst_cols, uint8_t* dst) {
+  return capi_guard([&] {
+    if (!src || !src->data || !dst || dst_rows < 1 || dst_cols < 1) throw std::invalid_argument("bad argument");
+    StageBase b;
+    b.init(device);
+    const auto& dev = b.upload(src, 1);
+    DevBuf out;
+    out.ensure(size_t(dst_rows) * dst_cols * 3);
+    launch_resize_u8(dev[0].p, dev[0].cols, dev[0].rows, dev[0].stride, dst_cols, dst_rows, out.as<uint8_t>(), b.stream);
+    cuda_check(cudaMemcpyAsync(dst, out.p, size_t(dst_rows) * dst_cols * 3, cudaMemcpyDeviceToHost, b.stream), "copy");
+    cuda_check(cudaStreamSynchronize(b.stream), "resize");
+  });
+}
+
+int b200ocr_crop_preprocess(int device, const b200ocr_image* crops, int n, int kind, int img_h, int img_w, float* nchw) {
+  return capi_guard([&] {
+    if (!crops || n < 1 || !nchw || img_h < 1 || img_w < 1) throw std::invalid_argument("bad argument");
+    StageBase b;
+    b.init(device);
+    const auto& dev = b.upload(crops, n);
+    std::vector<CropItem> items(n);
+    for (int i = 0; i < n; ++i) {
+      const float ratio = float(dev[i].cols) / float(dev[i].rows);
+      int rw = std::ceil(float(img_h) * ratio) > float(img_w) ? img_w : int(std::ceil(float(img_h) * ratio));
+      items[i] = CropItem{dev[i].p, dev[i].stride, 0, 0, dev[i].cols, dev[i].rows, rw};
+    }
+    DevBuf di, in, out;
+    di.ensure(sizeof(CropItem) * n);
+    const size_t px = size_t(n) * img_h * img_w;
+    in.ensure(px * 8 * sizeof(__half));
+    out.ensure(px * 3 * sizeof(float));
+    cuda_check(cudaMemcpyAsync(di.p, items.data(), sizeof(CropItem) * n, cudaMemcpyHostToDevice, b.stream), "items");
+    static const float mean[3] = {0.5f, 0.5f, 0.5f};
+    static const float scale[3] = {1 / 0.5f, 1 / 0.5f, 1 / 0.5f};
+    launch_crop_preprocess(di.as<CropItem>(), n, img_h, img_w, make_norm(mean, scale), kind == 0 ? -1.f : 0.f,
+                           in.as<__half>(), b.stream);
+    TV v;
+    v.p = in.as<__half>(); v.n = n; v.h = img_h; v.w = img_w; v.c = 3; v.pitch = 8;
+    launch_nhwc_to_nchw_f32(v, out.as<float>(), b.stream);
+    cuda_check(cudaMemcpyAsync(nchw, out.p, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, b.stream), "copy");
+    cuda_check(cudaStreamSynchronize(b.stream), "crop preprocess");
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+// Pre-processing kernels: one fused pass per stage from 8-bit BGR pixels to the network input
+// (NHWC fp16, channel pitch 8, channels 3..7 zero).
+//
+//   det_preprocess   = ResizeImgType0 (cv::resize, reference src/preprocess_op.cpp:57-93) + Normalize (:40-55)
+//                      + Permute (:19-26)
+//   crop_preprocess  = ROI crop (src/ocr_worker.cpp:244-259) + CrnnResizeImg (:95-118) / ClsResizeImg (:120-137)
+//                      + right padding + Normalize + PermuteBatch (:28-38), batched, variable width
+//   rotate180        = cv::rotate(ROTATE_180) in place on an ROI (src/ocr_worker.cpp:277-281)
+//
+// cv::resize(INTER_LINEAR) on 8-bit data is fixed point: 11-bit horizontal coefficients, the vertical
+// pass computes (((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2, an exact 2x2 shrink goes through the
+// INTER_AREA box average, equal sizes copy.  resize_px() restates that per output pixel and is bit-identical
+// to cv2.resize (tests/test_preproc_gpu.py).  HBM-bound: every source byte is read once (neighbouring
+// threads share rows through L1), every output pixel is one 16-byte store.
+#include "kernels.h"
+
+namespace b200ocr {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct Coef {
+  int s;       // source index of the first tap
+  int c0, c1;  // 11-bit weights
+};
+
+// x axis: indices outside the image collapse onto the edge pixel with weight 1 (cv::resize xofs/alpha set-up)
+__device__ __forceinline__ Coef coef_x(int d, double scale, int sn) {
+  float f = float((double(d) + 0.5) * scale - 0.5);
+  int s = int(floorf(f));
+  f -= float(s);
+  if (s < 0) { f = 0.f; s = 0; }
+  if (s >= sn - 1) { f = 0.f; s = sn - 1; }
+  Coef c;
+  c.s = s;
+  c.c0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  c.c1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  return c;
+}
+// y axis: weights are kept, row indices are clamped when read
+__device__ __forceinline__ Coef coef_y(int d, double scale) {
+  float f = float((double(d) + 0.5) * scale - 0.5);
+  int s = int(floorf(f));
+  f -= float(s);
+  Coef c;
+  c.s = s;
+  c.c0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  c.c1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  return c;
+}
+
+struct Src {
+  const uint8_t* p;  // top-left pixel of the (cropped) source
+  int w, h;
+  long stride;  // bytes per row
+};
+
+// One output pixel (3 channels) of cv::resize(src -> dw x dh, INTER_LINEAR) on CV_8UC3.
+__device__ __forceinline__ void resize_px(const Src& s, int dw, int dh, int dx, int dy, int out[3]) {
+  if (s.w == dw && s.h == dh) {
+    const uint8_t* q = s.p + dy * s.stride + dx * 3;
+    out[0] = q[0]; out[1] = q[1]; out[2] = q[2];
+    return;
+  }
+  if (s.w == 2 * dw && s.h == 2 * dh) {  // INTER_LINEAR with an exact 2x2 shrink runs as INTER_AREA
+    const uint8_t* q0 = s.p + (2 * dy) * s.stride + (2 * dx) * 3;
+    const uint8_t* q1 = q0 + s.stride;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[c] = (int(q0[c]) + int(q0[c + 3]) + int(q1[c]) + int(q1[c + 3]) + 2) >> 2;
+    return;
+  }
+  const double scale_x = 1.0 / (double(dw) / double(s.w));
+  const double scale_y = 1.0 / (double(dh) / double(s.h));
+  const Coef cx = coef_x(dx, scale_x, s.w);
+  const Coef cy = coef_y(dy, scale_y);
+  const int x1 = min(cx.s + 1, s.w - 1);
+  const int y0 = min(max(cy.s, 0), s.h - 1), y1 = min(max(cy.s + 1, 0), s.h - 1);
+  const uint8_t* r0 = s.p + y0 * s.stride;
+  const uint8_t* r1 = s.p + y1 * s.stride;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int S0 = int(r0[cx.s * 3 + c]) * cx.c0 + int(r0[x1 * 3 + c]) * cx.c1;
+    const int S1 = int(r1[cx.s * 3 + c]) * cx.c0 + int(r1[x1 * 3 + c]) * cx.c1;
+    int v = (((cy.c0 * (S0 >> 4)) >> 16) + ((cy.c1 * (S1 >> 4)) >> 16) + 2) >> 2;
+    out[c] = min(max(v, 0), 255);
+  }
+}
+
+// Normalize::Run: f = u8 * (1/255.f); f * scale + shift, two fp32 roundings, no contraction.
+__device__ __forceinline__ float norm1(int v, float scale, float shift) {
+  return __fadd_rn(__fmul_rn(__fmul_rn(float(v), 0.0039215688593685627f /* (float)(1/255.) */), scale), shift);
+}
+
+__device__ __forceinline__ void store_px(__half* out, long pix, float a, float b, float c) {
+  uint4 o;
+  __half2* h = reinterpret_cast<__half2*>(&o);
+  h[0] = __floats2half2_rn(a, b);
+  h[1] = __floats2half2_rn(c, 0.f);
+  h[2] = __floats2half2_rn(0.f, 0.f);
+  h[3] = h[2];
+  *reinterpret_cast<uint4*>(out + pix * 8) = o;
+}
+
+__global__ void __launch_bounds__(kThreads)
+det_preprocess_kernel(const DetPreItem* __restrict__ items, int n, int dh, int dw, NormParams np,
+                      __half* __restrict__ out) {
+  const long per = long(dh) * dw;
+  const long total = per * n;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const int img = int(t / per);
+    const int r = int(t - long(img) * per);
+    const int dy = r / dw, dx = r - dy * dw;
+    const DetPreItem it = items[img];
+    Src s{it.src, it.w, it.h, it.stride};
+    int v[3];
+    resize_px(s, dw, dh, dx, dy, v);
+    store_px(out, t, norm1(v[0], np.scale[0], np.shift[0]), norm1(v[1], np.scale[1], np.shift[1]),
+             norm1(v[2], np.scale[2], np.shift[2]));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+crop_preprocess_kernel(const CropItem* __restrict__ items, int n, int dh, int dw, NormParams np, float pad_value,
+                       __half* __restrict__ out) {
+  const long per = long(dh) * dw;
+  const long total = per * n;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const int b = int(t / per);
+    const int r = int(t - long(b) * per);
+    const int dy = r / dw, dx = r - dy * dw;
+    const CropItem it = items[b];
+    if (dx >= it.resize_w) {
+      store_px(out, t, pad_value, pad_value, pad_value);
+      continue;
+    }
+    Src s{it.img + long(it.y) * it.stride + long(it.x) * 3, it.w, it.h, it.stride};
+    int v[3];
+    resize_px(s, it.resize_w, dh, dx, dy, v);
+    store_px(out, t, norm1(v[0], np.scale[0], np.shift[0]), norm1(v[1], np.scale[1], np.shift[1]),
+             norm1(v[2], np.scale[2], np.shift[2]));
+  }
+}
+
+// In-place 180 degree rotation of one ROI, executed only when *label == 1.
+__global__ void __launch_bounds__(kThreads)
+rotate180_kernel(uint8_t* __restrict__ img, long stride, int x0, int y0, int w, int h, const int* __restrict__ label) {
+  if (*label != 1) return;
+  const long total = long(w) * h;
+  const long half = total / 2;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < half; t += long(gridDim.x) * blockDim.x) {
+    const long u = total - 1 - t;
+    const int ay = int(t / w), ax = int(t - long(ay) * w);
+    const int by = int(u / w), bx = int(u - long(by) * w);
+    uint8_t* a = img + long(y0 + ay) * stride + long(x0 + ax) * 3;
+    uint8_t* b = img + long(y0 + by) * stride + long(x0 + bx) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { const uint8_t v = a[c]; a[c] = b[c]; b[c] = v; }
+  }
+}
+
+// Plain resized 8-bit image (test hook for the fixed-point resize; also used by the warp path tests).
+__global__ void __launch_bounds__(kThreads)
+resize_u8_kernel(const uint8_t* __restrict__ src, int sw, int sh, long stride, int dw, int dh, uint8_t* __restrict__ out) {
+  const long total = long(dw) * dh;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const int dy = int(t / dw), dx = int(t - long(dy) * dw);
+    Src s{src, sw, sh, stride};
+    int v[3];
+    resize_px(s, dw, dh, dx, dy, v);
+    out[t * 3] = uint8_t(v[0]); out[t * 3 + 1] = uint8_t(v[1]); out[t * 3 + 2] = uint8_t(v[2]);
+  }
+}
+
+inline int grid_for(long total) {
+  long b = (total + kThreads - 1) / kThreads;
+  const long cap = 148L * 8;
+  return int(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+NormParams make_norm(const float mean[3], const float scale[3]) {
+  NormParams p;
+  for (int i = 0; i < 3; ++i) {
+    p.scale[i] = scale[i];                                       // (float)(1.0 * scale[i])
+    p.shift[i] = float((0.0 - double(mean[i])) * double(scale[i]));  // (float)((0.0 - mean[i]) * scale[i])
+  }
+  return p;
+}
+
+void launch_det_preprocess(const DetPreItem* items_dev, int n, int dh, int dw, const NormParams& np, __half* out,
+                           cudaStream_t s) {
+  det_preprocess_kernel<<<grid_for(long(n) * dh * dw), kThreads, 0, s>>>(items_dev, n, dh, dw, np, out);
+}
+
+void launch_crop_preprocess(const CropItem* items_dev, int n, int dh, int dw, const NormParams& np, float pad_value,
+                            __half* out, cudaStream_t s) {
+  crop_preprocess_kernel<<<grid_for(long(n) * dh * dw), kThreads, 0, s>>>(items_dev, n, dh, dw, np, pad_value, out);
+}
+
+void launch_rotate180_if(uint8_t* img, long stride, int x0, int y0, int w, int h, const int* label_dev,
+                         cudaStream_t s) {
+  rotate180_kernel<<<grid_for(long(w) * h / 2 + 1), kThreads, 0, s>>>(img, stride, x0, y0, w, h, label_dev);
+}
+
+void launch_resize_u8(const uint8_t* src, int sw, int sh, long stride, int dw, int dh, uint8_t* out, cudaStream_t s) {
+  resize_u8_kernel<<<grid_for(long(dw) * dh), kThreads, 0, s>>>(src, sw, sh, stride, dw, dh, out);
+}
+
+}  // namespace b200ocr

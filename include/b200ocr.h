@@ -47,6 +47,128 @@ int b200ocr_model_params_json(const char* pdmodel_path, char** json);
  * (one line per fused kernel).  Free *text with b200ocr_free. */
 int b200ocr_model_plan_text(const char* model_dir, char** text);
 
+/* ------------------------------------------------------------------ images
+ * What cv::Mat::data / rows / cols / step describe: 8-bit, 3 channels, BGR, row-major HOST memory
+ * (pinned memory from b200ocr_host_alloc makes the upload asynchronous; any host pointer works). */
+typedef struct b200ocr_image {
+  const uint8_t* data;
+  int rows, cols;
+  size_t step; /* bytes per row */
+} b200ocr_image;
+
+void* b200ocr_host_alloc(size_t bytes); /* page-locked host memory; NULL on failure */
+void b200ocr_host_free(void* p);
+int b200ocr_device_count(void);
+
+/* ------------------------------------------------------------------ DBDetector
+ * Constructor arguments of PaddleOCR::DBDetector (include/paddle_ocr/ocr_det.h:60-69), same order and meaning.
+ * use_gpu, gpu_mem, cpu_math_library_num_threads, use_mkldnn, use_tensorrt and precision are accepted for
+ * signature compatibility and ignored: this implementation always runs on GPU `gpu_id` in fp16 with fp32
+ * accumulation.  det_db_score_mode must be "fast" (the worker's setting); "slow" returns B200OCR_ERR_INVALID. */
+typedef struct b200ocr_det_config {
+  const char* model_dir;
+  int use_gpu, gpu_id, gpu_mem, cpu_math_library_num_threads, use_mkldnn;
+  const char* limit_type; /* "max" | "min" */
+  int limit_side_len;
+  double det_db_thresh, det_db_box_thresh, det_db_unclip_ratio;
+  const char* det_db_score_mode;
+  int use_dilation, use_tensorrt;
+  const char* precision;
+} b200ocr_det_config;
+typedef struct b200ocr_det* b200ocr_det_t;
+int b200ocr_det_create(const b200ocr_det_config* cfg, b200ocr_det_t* out);
+void b200ocr_det_destroy(b200ocr_det_t det);
+/* DBDetector::Run (ocr_det.h:95-97, src/ocr_det.cpp:93-176).  boxes: [cap][4][2] int32, points ordered
+ * tl,tr,br,bl in source pixels, in the reference's order; *n_boxes = number found (may exceed cap; only cap are
+ * written).  times: 3 values appended by the reference (ms: pre, infer, post); may be NULL. */
+int b200ocr_det_run(b200ocr_det_t det, const b200ocr_image* img, int32_t* boxes, int cap, int* n_boxes, double times[3]);
+/* Batched form: n images in one pass; boxes [n][cap][4][2], counts [n]. */
+int b200ocr_det_run_batch(b200ocr_det_t det, const b200ocr_image* imgs, int n, int32_t* boxes, int cap, int* counts,
+                          double times[3]);
+/* Post-processing only (BoxesFromBitmap + FilterTagDetRes, src/postprocess_op.cpp:255-362) on a caller-supplied
+ * probability map pred [h][w] fp32 (host): bitmap = (uchar)(p*255) > det_db_thresh*255, as src/ocr_det.cpp:143-154.
+ * src_h/src_w: size of the image the boxes are mapped back to. */
+int b200ocr_det_postprocess(b200ocr_det_t det, const float* pred, int h, int w, int src_h, int src_w, int32_t* boxes,
+                            int cap, int* n_boxes, uint8_t* bitmap_out /* [h][w] or NULL */);
+/* Pre-processing only (ResizeImgType0 + Normalize + Permute): writes the network input as fp32 NCHW [3][rh][rw]
+ * (host; pass NULL to query the size) and the resize ratios. */
+int b200ocr_det_preprocess(b200ocr_det_t det, const b200ocr_image* img, float* nchw, int* rh, int* rw, float* ratio_h,
+                           float* ratio_w);
+
+/* ------------------------------------------------------------------ Classifier
+ * PaddleOCR::Classifier (include/paddle_ocr/ocr_cls.h:57-62). */
+typedef struct b200ocr_cls_config {
+  const char* model_dir;
+  int use_gpu, gpu_id, gpu_mem, cpu_math_library_num_threads, use_mkldnn;
+  double cls_thresh;
+  int use_tensorrt;
+  const char* precision;
+  int cls_batch_num;
+} b200ocr_cls_config;
+typedef struct b200ocr_cls* b200ocr_cls_t;
+int b200ocr_cls_create(const b200ocr_cls_config* cfg, b200ocr_cls_t* out);
+void b200ocr_cls_destroy(b200ocr_cls_t cls);
+/* Classifier::Run (ocr_cls.h:81-82, src/ocr_cls.cpp:23-106): cls_labels / cls_scores are caller-sized [n]. */
+int b200ocr_cls_run(b200ocr_cls_t cls, const b200ocr_image* imgs, int n, int* cls_labels, float* cls_scores,
+                    double times[3]);
+
+/* ------------------------------------------------------------------ CRNNRecognizer
+ * PaddleOCR::CRNNRecognizer (include/paddle_ocr/ocr_rec.h:61-68). */
+typedef struct b200ocr_rec_config {
+  const char* model_dir;
+  int use_gpu, gpu_id, gpu_mem, cpu_math_library_num_threads, use_mkldnn;
+  const char* label_path;
+  int use_tensorrt;
+  const char* precision;
+  int rec_batch_num, rec_img_h, rec_img_w;
+} b200ocr_rec_config;
+typedef struct b200ocr_rec* b200ocr_rec_t;
+int b200ocr_rec_create(const b200ocr_rec_config* cfg, b200ocr_rec_t* out);
+void b200ocr_rec_destroy(b200ocr_rec_t rec);
+/* CRNNRecognizer::Run (ocr_rec.h:92-95, src/ocr_rec.cpp:24-135).  rec_texts: [n] UTF-8 strings, each allocated by the
+ * library (free every entry with b200ocr_free); rec_text_scores: caller-sized [n].  Lines that decode to nothing
+ * keep "" and 0, like the reference's untouched pre-sized vectors. */
+int b200ocr_rec_run(b200ocr_rec_t rec, const b200ocr_image* imgs, int n, char** rec_texts, float* rec_text_scores,
+                    double times[3]);
+
+/* ------------------------------------------------------------------ OCRWorker
+ * PaddleOCR::OCRWorker(worker_id, model_dir, use_gpu, gpu_id, enable_cls) (include/paddle_ocr/ocr_worker.h:57) with the
+ * hyper-parameters of src/ocr_worker.cpp:21-63.  process() = processRequest + the result JSON of
+ * src/ocr_worker.cpp:155-190 (one compact line, jsoncpp key order).  Free *json with b200ocr_free. */
+typedef struct b200ocr_worker* b200ocr_worker_t;
+int b200ocr_worker_create(int worker_id, const char* model_dir, int use_gpu, int gpu_id, int enable_cls,
+                          b200ocr_worker_t* out);
+void b200ocr_worker_destroy(b200ocr_worker_t w);
+int b200ocr_worker_process(b200ocr_worker_t w, int request_id, const b200ocr_image* img, char** json);
+/* Throughput form: n requests through the GPU together (results are per image, identical to n process() calls). */
+int b200ocr_worker_process_batch(b200ocr_worker_t w, const int* request_ids, const b200ocr_image* imgs, int n,
+                                 char** jsons);
+/* kernels launched by this worker so far */
+long long b200ocr_worker_launches(b200ocr_worker_t w);
+
+/* ------------------------------------------------------------------ per-device worker pool
+ * Replaces PaddleOCR::GPUWorkerPool (include/paddle_ocr/gpu_worker_pool.h:14-31, src/gpu_worker_pool.cpp:8-59), which
+ * pins every worker to GPU 0: here workers are spread over `n_devices` GPUs (devices[i], or 0..n-1 when NULL),
+ * `workers_per_device` each; submit() is thread-safe, copies the image (like OCRRequest's clone) and returns a
+ * ticket; a worker drains up to `max_batch` queued requests at a time.  Dispatch: the device with the shortest queue
+ * (the reference's idle-first / round-robin, generalised). */
+typedef struct b200ocr_pool* b200ocr_pool_t;
+int b200ocr_pool_create(const char* model_dir, int n_devices, const int* devices, int workers_per_device,
+                        int enable_cls, int max_batch, b200ocr_pool_t* out);
+void b200ocr_pool_destroy(b200ocr_pool_t pool);
+int b200ocr_pool_submit(b200ocr_pool_t pool, int request_id, const b200ocr_image* img, long long* ticket);
+/* Blocks until the request is done; *json is the worker's result line (free with b200ocr_free). */
+int b200ocr_pool_wait(b200ocr_pool_t pool, long long ticket, char** json);
+int b200ocr_pool_worker_count(b200ocr_pool_t pool);
+int b200ocr_pool_idle_count(b200ocr_pool_t pool);
+
+/* ------------------------------------------------------------------ stand-alone image ops (test / utility surface)
+ * cv::resize(INTER_LINEAR) of an 8-bit BGR image on the GPU (the kernel inside det/cls/rec pre-processing). */
+int b200ocr_resize_u8(int device, const b200ocr_image* src, int dst_rows, int dst_cols, uint8_t* dst);
+/* Rec / cls pre-processing of one batch of crops to fp32 NCHW [n][3][img_h][img_w] (host), for parity tests:
+ * kind 0 = rec (CrnnResizeImg, pad -1 after normalisation of u8 zeros), 1 = cls (ClsResizeImg, pad 0). */
+int b200ocr_crop_preprocess(int device, const b200ocr_image* crops, int n, int kind, int img_h, int img_w, float* nchw);
+
 /* ------------------------------------------------------------------ network-level entry points
  * One loaded .pdmodel/.pdiparams pair executing on one GPU; what `paddle_infer::Predictor`
  * is to the reference stages (predictor_->Run(), src/ocr_det.cpp:120).  Used by the stages below

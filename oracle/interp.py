@@ -70,16 +70,21 @@ def _reshape_target(x, shape):
     return shape
 
 
-def run_program(prog: Program, params: dict, feed: np.ndarray, keep=None, want_all=False):
-    """Execute `prog` on `feed` (NCHW fp32). Returns (output ndarray, {name: ndarray} for `keep`)."""
-    env = {k: torch.from_numpy(np.asarray(v, dtype=np.float32)) for k, v in params.items()}
+def run_program(prog: Program, params: dict, feed, keep=None, want_all=False, grad=False):
+    """Execute `prog` on `feed` (NCHW fp32). Returns (output ndarray, {name: ndarray} for `keep`).
+    grad=True (tools/train_synth_det.py only): `params` / `feed` are torch tensors, autograd stays on and the
+    output is returned as a torch tensor."""
+    if grad:
+        env = dict(params)
+    else:
+        env = {k: torch.from_numpy(np.asarray(v, dtype=np.float32)) for k, v in params.items()}
     kept = {}
     out = None
-    with torch.no_grad():
+    with (torch.enable_grad() if grad else torch.no_grad()):
         for op in prog.ops:
             t, a = op.type, op.attrs
             if t == 'feed':
-                env[op.o('Out')] = torch.from_numpy(np.ascontiguousarray(feed, dtype=np.float32)); continue
+                env[op.o('Out')] = feed if grad else torch.from_numpy(np.ascontiguousarray(feed, dtype=np.float32)); continue
             if t == 'fetch':
                 out = env[op.i('X')]; continue
             if t in ('conv2d', 'depthwise_conv2d'):
@@ -178,5 +183,5 @@ def run_program(prog: Program, params: dict, feed: np.ndarray, keep=None, want_a
                 for k, names in op.outputs.items():
                     for n in names:
                         if n in env and (want_all or n in keep) and k in ('Out', 'Output', 'Y'):
-                            kept[n] = env[n].numpy()
-    return out.numpy(), kept
+                            kept[n] = env[n].detach().numpy()
+    return (out if grad else out.numpy()), kept

@@ -1,8 +1,11 @@
 """Assemble the model directory the tests / smoke / bench use:
 
   models/cls : the shipped graph + the shipped (real) weights
-  models/det, models/rec : the shipped graphs + SEEDED SYNTHETIC weights, because the reference
+  models/det, models/rec : the shipped graphs + SYNTHETIC weights, because the reference
       mount lacks models/{det,rec}/inference.pdiparams (.MISSING_LARGE_BLOBS).
+      rec: seeded random.  det: tests/golden/models/det/inference.pdiparams, which tools/train_synth_det.py
+      fitted (from the seeded random initialisation) to the synthetic card generator so that the detector
+      finds the rendered text lines; without that file the seeded random det weights are used.
 
 Parameter names / shapes come from the product's own .pdmodel reader (b200ocr_model_params_json),
 the records are written in the `.pdiparams` layout.  If real det/rec weights are
@@ -74,6 +77,15 @@ def synth_param(name: str, dims, model: str) -> np.ndarray:
     return a.astype(np.float32).reshape(dims)
 
 
+def _is_synth(path, params, model) -> bool:
+    """True when `path` already holds the seeded weights (checked on the first tensor)."""
+    name, dims = params[0]
+    want = synth_param(name, dims, model).astype("<f4").tobytes()
+    with open(path, "rb") as f:
+        head = f.read(64 + len(want))
+    return want[:32] in head
+
+
 def ensure_models(verbose=False) -> str:
     import b200ocr  # the product library lists the parameters; no oracle code involved
     for m in ("det", "cls", "rec"):
@@ -85,13 +97,13 @@ def ensure_models(verbose=False) -> str:
         src_w = os.path.join(SRC, m, "inference.pdiparams")
         dst_w = os.path.join(DST, m, "inference.pdiparams")
         if os.path.exists(src_w):
-            if not os.path.exists(dst_w) or os.path.getsize(dst_w) != os.path.getsize(src_w):
+            if not os.path.exists(dst_w) or open(dst_w, "rb").read() != open(src_w, "rb").read():
                 shutil.copyfile(src_w, dst_w)
             continue
         params = b200ocr.model_params(src_model)
         expect = sum(16 + 4 + 2 + sum(1 + len(_varint(int(d))) for d in dims) + 4 * int(np.prod(dims))
                      for _n, dims in params)
-        if os.path.exists(dst_w) and os.path.getsize(dst_w) == expect:
+        if os.path.exists(dst_w) and os.path.getsize(dst_w) == expect and _is_synth(dst_w, params, m):
             continue
         if verbose:
             print(f"[synth] {m}: {len(params)} tensors, {expect} bytes")

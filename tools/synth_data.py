@@ -1,0 +1,98 @@
+"""Seeded synthetic inputs named in SURVEY.md §8(d): S-card, S-page, S-rec crops, S-prob maps.
+Rendered with cv2.putText (Hershey fonts), the same primitive the reference's own test image uses
+(reference tests/test_ocr_worker.cpp:70-83)."""
+from __future__ import annotations
+import cv2
+import numpy as np
+
+_FONTS = [cv2.FONT_HERSHEY_SIMPLEX, cv2.FONT_HERSHEY_DUPLEX, cv2.FONT_HERSHEY_COMPLEX, cv2.FONT_HERSHEY_TRIPLEX]
+_WORDS = ["Order", "No", "2026", "Total", "Amount", "Name", "Address", "Phone", "Card", "Member", "Date", "Valid",
+          "Invoice", "Price", "Qty", "Pharmacy", "Receipt", "Street", "Code", "ID", "8812", "4471", "0093", "Thank", "you"]
+
+
+def _line(rng, nwords):
+    return " ".join(_WORDS[int(i)] for i in rng.integers(0, len(_WORDS), nwords))
+
+
+def reference_test_image():
+    """createTestImage() of the reference test (tests/test_ocr_worker.cpp:70-83): 600x200 white, three lines."""
+    img = np.full((200, 600, 3), 255, np.uint8)
+    cv2.putText(img, "Hello World", (50, 50), cv2.FONT_HERSHEY_SIMPLEX, 1.0, (0, 0, 0), 2)
+    cv2.putText(img, "PaddleOCR Test", (50, 100), cv2.FONT_HERSHEY_SIMPLEX, 1.0, (0, 0, 0), 2)
+    cv2.putText(img, "123456789", (50, 150), cv2.FONT_HERSHEY_SIMPLEX, 1.0, (0, 0, 0), 2)
+    return img
+
+
+def card(seed: int, width=1024, height=640, out=None, boxes=None):
+    """S-card: light background, 8-12 horizontal text lines, scales 0.6-1.2.
+    `boxes` (optional list) receives (x0, y0, x1, y1) of every rendered line."""
+    rng = np.random.default_rng(seed)
+    img = out if out is not None else np.empty((height, width, 3), np.uint8)
+    img[:] = rng.integers(225, 256, 3, dtype=np.uint8)
+    n = int(rng.integers(8, 13))
+    y = 40
+    for _ in range(n):
+        scale = float(rng.uniform(0.6, 1.2))
+        text = _line(rng, int(rng.integers(2, 6)))
+        x = int(rng.integers(20, 200))
+        color = tuple(int(c) for c in rng.integers(0, 90, 3))
+        font, thick = _FONTS[int(rng.integers(0, len(_FONTS)))], int(rng.integers(1, 3))
+        cv2.putText(img, text, (x, y), font, scale, color, thick, cv2.LINE_AA)
+        if boxes is not None:
+            (tw, th), base = cv2.getTextSize(text, font, scale, thick)
+            boxes.append((x, y - th, min(x + tw, width - 1), y + base // 2))
+        y += int(28 * scale + rng.integers(18, 30))
+        if y > height - 20:
+            break
+    return img
+
+
+def page(seed: int, size=2048, lines=220):
+    """S-page: 2048x2048, >= 200 lines in 3 columns, widths 80..900 px."""
+    rng = np.random.default_rng(seed)
+    img = np.full((size, size, 3), 250, np.uint8)
+    cols = [30, 710, 1390]
+    per = (lines + 2) // 3
+    for cx in cols:
+        y = 30
+        for _ in range(per):
+            scale = float(rng.uniform(0.5, 0.9))
+            text = _line(rng, int(rng.integers(1, 7)))
+            cv2.putText(img, text, (cx, y), _FONTS[int(rng.integers(0, len(_FONTS)))], scale, (20, 20, 20), 1, cv2.LINE_AA)
+            y += int(rng.integers(24, 29))
+            if y > size - 10:
+                break
+    return img
+
+
+def rec_crops(n: int, height=48, width=320, seed=0):
+    """S-rec: n text-line crops of height x width u8 with rendered text."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((n, height, width, 3), np.uint8)
+    for i in range(n):
+        out[i] = rng.integers(215, 256, 3, dtype=np.uint8)
+        cv2.putText(out[i], _line(rng, 3), (4, int(height * 0.72)), _FONTS[i % 4], height / 44.0, (10, 10, 10), 2, cv2.LINE_AA)
+    return out
+
+
+def prob_map(seed: int, height=320, width=512, n_boxes=12, rings=2, lines=2):
+    """S-prob: synthetic DB probability map: blurred rotated rectangles, rings (hole contours), 1-px lines."""
+    rng = np.random.default_rng(seed)
+    p = np.zeros((height, width), np.float32)
+    for _ in range(n_boxes):
+        c = (float(rng.uniform(20, width - 20)), float(rng.uniform(10, height - 10)))
+        sz = (float(rng.uniform(20, 160)), float(rng.uniform(6, 28)))
+        ang = float(rng.uniform(-20, 20)) if rng.random() < 0.7 else float(rng.uniform(-90, 90))
+        pts = cv2.boxPoints((c, sz, ang)).astype(np.int32)
+        cv2.fillPoly(p, [pts], float(rng.uniform(0.5, 0.98)))
+    for _ in range(rings):
+        c = (int(rng.uniform(40, width - 40)), int(rng.uniform(30, height - 30)))
+        cv2.ellipse(p, c, (int(rng.uniform(15, 40)), int(rng.uniform(10, 25))), float(rng.uniform(0, 180)), 0, 360,
+                    float(rng.uniform(0.6, 0.95)), int(rng.integers(2, 6)))
+    for _ in range(lines):
+        a = (int(rng.uniform(0, width)), int(rng.uniform(0, height)))
+        b = (int(rng.uniform(0, width)), int(rng.uniform(0, height)))
+        cv2.line(p, a, b, 0.9, 1)
+    p = cv2.GaussianBlur(p, (5, 5), 1.0)
+    p += rng.normal(0, 0.02, p.shape).astype(np.float32)
+    return np.clip(p, 0.0, 1.0).astype(np.float32)
