@@ -1,0 +1,298 @@
+"""Headline benchmark: OCR images/s for the full det -> cls -> rec path (BASELINE.json metric, config 4:
+synthetic 1024x640 card images), one process per GPU, images sharded across ranks, no collective on the data path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (through the C ABI)
+    python bench.py --impl reference ...                      # the reference's CPU path, restated (oracle/), on host cores
+
+A step = one pass of the hot path over one batch of `--batch` images per GPU.
+  value : images/s with the batch already resident in HBM (b200ocr_worker_process_resident), CUDA events on the
+          worker's stream around the K timed steps, max over ranks.
+  e2e   : images/s through b200ocr_worker_process_batch with PINNED HOST buffers: H2D of the images and D2H of the
+          boxes / decoded ids inside the timed region.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "cpp-paddle-ocr_b200"), os.path.join(ROOT, "tools")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "OCR images/sec (det+cls+rec)"
+UNIT = "images/s"
+WORKLOAD = "C4: full det->cls->rec on synthetic 1024x640 card images (cv2.putText, 8-12 lines each), worker defaults"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_cards(n, seed0, pinned):
+    import numpy as np
+    import synth_data
+    import b200ocr
+    arr = b200ocr.pinned_array((n, 640, 1024, 3)) if pinned else np.empty((n, 640, 1024, 3), np.uint8)
+    for i in range(n):
+        synth_data.card(seed0 + i, out=arr[i])
+    return arr
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def _ref_worker_init(models, enable_cls, threads):
+    global _W
+    import torch
+    torch.set_num_threads(threads)
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle.pipeline import OracleWorker
+    _W = OracleWorker(os.getpid() % 1000, models, enable_cls=enable_cls)
+
+
+def _ref_worker_run(seed):
+    import synth_data
+    t0 = time.perf_counter()
+    line = _W.process(seed, synth_data.card(seed))
+    return time.perf_counter() - t0, line.count('"text"')
+
+
+def cpu_reference(models, n_images, seed0, enable_cls=True, workers=None, warm=True):
+    """The reference's cpu_worker_pool arrangement (src/cpu_worker_pool.cpp, src/ocr_worker.cpp:16-18): W worker
+    processes with private det/cls/rec instances, 2 intra-op threads each, fed from one queue."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    workers = workers or max(1, cores // 2)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers, initializer=_ref_worker_init, initargs=(models, enable_cls, 2)) as pool:
+        if warm:
+            pool.map(_ref_worker_run, [seed0 - 1 - k for k in range(workers)])
+        t0 = time.perf_counter()
+        res = pool.map(_ref_worker_run, [seed0 + i for i in range(n_images)], chunksize=1)
+        dt = time.perf_counter() - t0
+    lat = sorted(r[0] for r in res)
+    return {"value": n_images / dt, "seconds": dt, "workers": workers, "threads": workers * 2, "cores": cores,
+            "p50_ms": lat[len(lat) // 2] * 1e3, "words_per_image": sum(r[1] for r in res) / n_images}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import make_synth_weights
+    models = make_synth_weights.ensure_models()
+    per_step = args.ref_images
+    vals, last = [], None
+    for s in range(args.warmup + args.steps):
+        last = cpu_reference(models, per_step, 5000 + s * per_step, True, warm=(s == 0))
+        if s >= args.warmup:
+            vals.append(last)
+    total_img = per_step * len(vals)
+    total_s = sum(v["seconds"] for v in vals)
+    value = total_img / total_s
+    sample = f"{per_step} S-card images per step x {len(vals)} steps, {last['workers']} workers x 2 threads (cpu_worker_pool layout)"
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": total_s / len(vals) * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "images_per_step": per_step, "enable_cls": True,
+                      "weights": "cls: shipped; det: synthetic-trained; rec: seeded random (reference det/rec weights absent)",
+                      "note": "reference CPU path restated (torch-CPU fp32 graphs + cv2 + reference Clipper); Paddle Inference itself is not installable here"},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["threads"], "kind": "port", "sample": sample,
+                            "p50_ms": last["p50_ms"], "host_cores": last["cores"]},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------- this repo's arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import b200ocr
+    import make_synth_weights
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if b200ocr.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the b200ocr path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        models = make_synth_weights.ensure_models()
+    if dist:
+        dist.barrier()
+    models = make_synth_weights.ensure_models()
+
+    B, K, W = args.batch, args.steps, args.warmup
+    worker = b200ocr.Worker(rank, models, gpu_id=local, enable_cls=True)
+    n_sets = min(K, 4) if K > 0 else 1
+    # distinct images per rank and per set; each set is B x 1.97 MB (>= L2 at B = 64), sets rotate between steps
+    host_sets = [make_cards(B, 1_000_000 * rank + 10_000 * s, pinned=True) for s in range(n_sets)]
+    dev_sets = [b200ocr.DeviceBatch(list(h), device=local) for h in host_sets]
+    ids = list(range(B))
+    stream = torch.cuda.ExternalStream(worker.stream, device=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for s in range(W):
+            fn(s)
+        barrier()
+        l0 = worker.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        words = 0
+        for s in range(K):
+            words += fn(s)
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, wall * 1e3], device="cuda", dtype=torch.float64)
+        cnt = torch.tensor([float(worker.launches - l0), float(words)], device="cuda", dtype=torch.float64)
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        return float(t[0]), float(t[1]), int(cnt[0]), float(cnt[1])
+
+    def step_resident(s):
+        out = worker.process_resident(ids, dev_sets[s % n_sets])
+        return sum(o.count('"text"') for o in out)
+
+    def step_host(s):
+        out = worker.process_batch(ids, list(host_sets[s % n_sets]))
+        return sum(o.count('"text"') for o in out)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, wall_dev, launches, words = timed(step_resident)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, wall_e2e, _, _ = timed(step_host)
+    total_images = B * K * world
+    value = total_images / (ms_dev / 1e3)
+    e2e = total_images / (max(ms_e2e, wall_e2e) / 1e3)
+
+    # ---- roofline of the dominant kernel: per-layer CUDA-event times at the shapes of the last step
+    roof = None
+    if rank == 0:
+        hbm, tf_burst, tf_sust, which = peaks()
+        prof = worker.profile(warmup=2, reps=5)
+        rows = [(net, r) for net, lst in prof.items() for r in lst]
+        net, top = max(rows, key=lambda t: t[1]["ms"])
+        sec = top["ms"] / 1e3
+        ai = top["flops"] / max(top["bytes"], 1.0)
+        if top["flops"] and ai > tf_sust * 1e12 / (hbm * 1e9):
+            roof = {"bound": "tensor", "achieved": top["flops"] / sec / 1e12, "peak": tf_sust, "unit": "TFLOP/s"}
+        else:
+            roof = {"bound": "hbm", "achieved": top["bytes"] / sec / 1e9, "peak": hbm, "unit": "GB/s"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["traffic"] = None
+        roof["kernel"] = f"{net}:{top['kind']}:{top['name']}" + (" (tcgen05)" if top["tensor_core"] else "")
+        roof["peak_source"] = which + " (MEASURED_PEAKS.json)" if which == "measured" else "fallback (B200_PROFILING.md)"
+        roof["launch_us"] = top["ms"] * 1e3
+        roof["algorithmic_bytes"] = top["bytes"]
+        roof["algorithmic_flops"] = top["flops"]
+        tot = {n: sum(r["ms"] for r in lst) for n, lst in prof.items()}
+        roof["net_ms_at_last_shape"] = tot
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        r = cpu_reference(models, args.cpu_images, 7000, True)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+               "sample": f"{args.cpu_images} S-card images of the same generator through the restated reference CPU path "
+                         f"(oracle/: torch-CPU fp32 + cv2 + reference Clipper), {r['workers']} workers x 2 threads",
+               "p50_ms": r["p50_ms"], "host_cores": r["cores"], "words_per_image": r["words_per_image"]}
+
+    if rank == 0:
+        bytes_in = B * 640 * 1024 * 3
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+               "data": "synthetic",
+               "config": {"workload": WORKLOAD, "images_per_gpu_per_step": B, "enable_cls": True,
+                          "words_per_image": words / max(1, total_images),
+                          "weights": "cls: shipped; det: synthetic-trained; rec: seeded random (reference det/rec weights absent)",
+                          "l2": f"inputs rotate through {n_sets} distinct batches of {bytes_in / 1e6:.0f} MB each (>= L2)",
+                          "p50_latency_ms_per_batch": ms_dev / K},
+               "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+               "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": bytes_in,
+                       "d2h_bytes_per_step": int(words / max(1, K * world) * (24 * 8 + 8) + B * 4), "ms_per_step": ms_e2e / K},
+               "gpu_launches": launches}
+        print(json.dumps(out))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-images", type=int, default=24, help="size of the cpu_baseline sample")
+    ap.add_argument("--ref-images", type=int, default=16, help="images per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

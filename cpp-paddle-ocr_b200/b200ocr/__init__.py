@@ -395,3 +395,49 @@ def crop_preprocess(crops, kind, img_h, img_w, device=0):
     out = np.empty((len(crops), 3, img_h, img_w), np.float32)
     check(lib.b200ocr_crop_preprocess(device, arr, len(crops), 0 if kind == "rec" else 1, img_h, img_w, out.ctypes.data))
     return out
+
+
+_sig("b200ocr_batch_upload", C.c_int, C.c_int, _P(Image), C.c_int, _P(C.c_void_p))
+_sig("b200ocr_batch_destroy", None, C.c_void_p)
+_sig("b200ocr_worker_process_resident", C.c_int, C.c_void_p, C.c_void_p, _P(C.c_int), _P(C.c_void_p))
+_sig("b200ocr_worker_stream", C.c_void_p, C.c_void_p)
+_sig("b200ocr_worker_profile", C.c_int, C.c_void_p, C.c_int, C.c_int, _P(C.c_void_p))
+_sig("b200ocr_net_profile", C.c_int, C.c_void_p, C.c_int, C.c_int, _P(C.c_void_p))
+
+
+class DeviceBatch(_Handle):
+    """Images uploaded once and kept in device memory (b200ocr_batch_upload)."""
+    _destroy = staticmethod(lib.b200ocr_batch_destroy)
+
+    def __init__(self, imgs, device=0):
+        arr, keep = _images(imgs)
+        self.n = len(imgs)
+        self._h = C.c_void_p()
+        check(lib.b200ocr_batch_upload(device, arr, self.n, C.byref(self._h)))
+
+
+def _worker_process_resident(self, request_ids, batch: DeviceBatch):
+    ids = (C.c_int * batch.n)(*request_ids)
+    out = (C.c_void_p * batch.n)()
+    check(lib.b200ocr_worker_process_resident(self._h, batch._h, ids, out))
+    return [_take_string(C.c_void_p(t)) for t in out]
+
+
+def _worker_profile(self, warmup=2, reps=5):
+    p = C.c_void_p()
+    check(lib.b200ocr_worker_profile(self._h, warmup, reps, C.byref(p)))
+    return json.loads(_take_string(p))
+
+
+Worker.process_resident = _worker_process_resident
+Worker.profile = _worker_profile
+Worker.stream = property(lambda self: lib.b200ocr_worker_stream(self._h))
+
+
+def _net_profile(self, warmup=2, reps=5):
+    p = C.c_void_p()
+    check(lib.b200ocr_net_profile(self._h, warmup, reps, C.byref(p)))
+    return json.loads(_take_string(p))
+
+
+Net.profile = _net_profile

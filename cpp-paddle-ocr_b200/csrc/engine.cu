@@ -229,12 +229,13 @@ __half* Net::prepare(int n, int h, int w) {
   return reinterpret_cast<__half*>(arena_ + I->boff[plan_.tensors[plan_.input].buf]);
 }
 
-void Net::record(Inst& I, cudaStream_t s, int thresh_u8) {
+void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<void(int, bool)>* hook) {
   auto tv = [&](int t) { return make_tv(arena_, plan_, I.boff, I.ts, t); };
   auto vecp = [&](int t) { return reinterpret_cast<float*>(arena_ + I.boff[plan_.tensors[t].buf]); };
   int launches = 0;
   for (size_t li = 0; li < plan_.layers.size(); ++li) {
     const Layer& L = plan_.layers[li];
+    if (hook) (*hook)(int(li), true);
     Epi e;
     e.act = int(L.act); e.a = L.act_a; e.b = L.act_b; e.s2 = L.post_scale; e.t2 = L.post_shift;
     if (L.residual >= 0) {
@@ -300,8 +301,74 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8) {
       }
     }
     ++launches;
+    if (hook) (*hook)(int(li), false);
   }
   I.launches = launches;
+}
+
+std::vector<Net::LayerProfile> Net::profile(cudaStream_t stream, int warmup, int reps, int thresh_u8) {
+  if (!cur_) throw std::runtime_error("Net::profile before prepare");
+  Inst& I = *cur_;
+  const int nl = int(plan_.layers.size());
+  for (int k = 0; k < warmup; ++k) record(I, stream, thresh_u8);
+  std::vector<cudaEvent_t> ev(size_t(nl) * 2);
+  for (auto& e : ev) cuda_check(cudaEventCreate(&e), "cudaEventCreate");
+  std::vector<double> ms(nl, 0.0);
+  std::function<void(int, bool)> hook = [&](int li, bool before) {
+    cudaEventRecord(ev[size_t(li) * 2 + (before ? 0 : 1)], stream);
+  };
+  for (int r = 0; r < reps; ++r) {
+    record(I, stream, thresh_u8, &hook);
+    cuda_check(cudaStreamSynchronize(stream), "profile pass");
+    for (int li = 0; li < nl; ++li) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev[size_t(li) * 2], ev[size_t(li) * 2 + 1]);
+      ms[li] += t;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  static const char* kn[] = {"Conv", "DwConv", "Gap", "SeFc", "Scale", "UpAdd", "UpCat", "Pool",
+                             "Add", "LayerNorm", "Attn", "DbHead", "FcSoftmax", "CtcHead"};
+  std::vector<LayerProfile> out;
+  for (int li = 0; li < nl; ++li) {
+    const Layer& L = plan_.layers[li];
+    const Shape3 in = I.ts[L.in];
+    const Shape3 o = I.ts[L.out];
+    LayerProfile p;
+    p.name = L.name;
+    p.kind = kn[int(L.kind)];
+    p.ms = ms[li] / reps;
+    p.tensor_core = I.tc[li].impl != nullptr;
+    const double pin = double(in.n) * in.h * in.w, pout = double(o.n) * o.h * o.w;
+    const int taps = L.kh * L.kw;
+    p.flops = 0;
+    p.bytes = (pin * L.cin + pout * L.cout) * 2;
+    switch (L.kind) {
+      case LKind::Conv:
+        p.flops = 2.0 * pout * L.cout * L.cin * taps;
+        p.bytes += double(L.cout) * L.cin * taps * 2 + (L.residual >= 0 ? pout * L.cout * 2 : 0);
+        break;
+      case LKind::DwConv: p.flops = 2.0 * pout * L.cout * taps; break;
+      case LKind::CtcHead:
+        p.flops = 2.0 * pin * L.cin * L.cout;
+        p.bytes = pin * L.cin * 2 + double(L.cout) * L.cin * 2 + pin * 8;
+        break;
+      case LKind::DbHead:
+        p.flops = 2.0 * pin * 4 * (double(L.cin) * L.cmid + L.cmid * 4);
+        p.bytes = pin * L.cin * 2 + pin * 16 * 5;
+        break;
+      case LKind::Attn:
+        p.flops = 4.0 * in.n * double(in.w) * in.w * L.heads * L.head_dim;
+        break;
+      case LKind::UpAdd: p.bytes = pout * L.cout * 2 * 2 + pout / 4 * L.cout * 2; break;
+      case LKind::Add: p.bytes = pout * L.cout * 2 * 3; break;
+      case LKind::Gap: p.bytes = pin * L.cin * 2; break;
+      case LKind::SeFc: case LKind::FcSoftmax: p.bytes = 0; break;
+      default: break;
+    }
+    out.push_back(p);
+  }
+  return out;
 }
 
 void Net::run(cudaStream_t stream, int thresh_u8) {

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -55,13 +56,19 @@ class Net {
   // debug: copy a tensor (by Paddle var name) of the last run to host as fp32 NCHW.
   bool fetch(const std::string& var, std::vector<float>* out, int dims[4]);
 
+  // Per-layer device time of the last prepared shape: every fused layer is launched on its own between two
+  // CUDA events on `stream` (after `warmup` untimed passes), averaged over `reps`.  Also reports the layer's
+  // algorithmic FLOPs and HBM bytes (activations in + out + weights) so that a caller can place it on a roofline.
+  struct LayerProfile { std::string name, kind; double ms, flops, bytes; int tensor_core; };
+  std::vector<LayerProfile> profile(cudaStream_t stream, int warmup, int reps, int thresh_u8 = -1);
+
   size_t arena_bytes() const { return arena_bytes_; }
   int launches_per_run() const;
 
  private:
   struct Inst;
   Inst* instantiate(int n, int h, int w);
-  void record(Inst& I, cudaStream_t s, int thresh_u8);
+  void record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<void(int, bool)>* hook = nullptr);
 
   Plan plan_;
   NetOptions opt_;

@@ -145,7 +145,7 @@ GEOM_HD void rotating_calipers_min_area(const P2* pts, int n, float* vx, float* 
     dy = pts[seq[2]].y - pts[seq[0]].y;
     const float height = -dx * base_b + dy * base_a;
     const float area = width * height;
-    if (area < minarea) {
+    if (area <= minarea) {
       minarea = area;
       b_left = seq[3]; b_a = base_a; b_w = width; b_b = base_b; b_h = height; b_bottom = seq[0];
     }

@@ -16,6 +16,20 @@ struct b200ocr_net {
   cudaStream_t stream = nullptr;
 };
 
+std::string profile_json(Net& net, cudaStream_t stream, int warmup, int reps, int thresh) {
+  std::string o = "[";
+  bool first = true;
+  for (const auto& p : net.profile(stream, warmup, reps, thresh)) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s{\"name\":\"%s\",\"kind\":\"%s\",\"ms\":%.6f,\"flops\":%.0f,\"bytes\":%.0f,\"tensor_core\":%d}",
+             first ? "" : ",", p.name.c_str(), p.kind.c_str(), p.ms, p.flops, p.bytes, p.tensor_core);
+    o += buf;
+    first = false;
+  }
+  return o + "]";
+}
+
+
 extern "C" {
 
 int b200ocr_net_create(const char* model_dir, int device, int flags, b200ocr_net_t* out) {
@@ -118,6 +132,16 @@ int b200ocr_net_fetch(b200ocr_net_t h, const char* var, float* out, size_t cap_e
       if (v.size() > cap_elems) throw std::runtime_error("fetch buffer too small");
       memcpy(out, v.data(), v.size() * 4);
     }
+  });
+}
+
+int b200ocr_net_profile(b200ocr_net_t h, int warmup, int reps, char** json) {
+  return capi_guard([&] {
+    if (!h || !json || reps < 1) throw std::invalid_argument("bad argument");
+    std::string s = profile_json(*h->net, h->stream, warmup, reps, h->net->kind() == "det" ? 51 : -1);
+    *json = static_cast<char*>(malloc(s.size() + 1));
+    if (!*json) throw std::bad_alloc();
+    memcpy(*json, s.c_str(), s.size() + 1);
   });
 }
 

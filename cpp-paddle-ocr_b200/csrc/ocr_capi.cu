@@ -71,6 +71,8 @@ struct b200ocr_det : StageBase { std::unique_ptr<DetStage> st; DetParams p; };
 struct b200ocr_cls : StageBase { std::unique_ptr<ClsStage> st; };
 struct b200ocr_rec : StageBase { std::unique_ptr<RecStage> st; };
 struct b200ocr_worker { std::unique_ptr<Worker> w; };
+struct b200ocr_batch { int device = 0; ImageBatch b; };
+std::string profile_json(Net& net, cudaStream_t stream, int warmup, int reps, int thresh);
 
 // ------------------------------------------------------------------------------------------------ pool
 struct b200ocr_pool {
@@ -358,6 +360,48 @@ int b200ocr_worker_process(b200ocr_worker_t w, int request_id, const b200ocr_ima
   return b200ocr_worker_process_batch(w, &request_id, img, 1, json);
 }
 long long b200ocr_worker_launches(b200ocr_worker_t w) { return w ? w->w->launches() : 0; }
+void* b200ocr_worker_stream(b200ocr_worker_t w) { return w ? static_cast<void*>(w->w->stream()) : nullptr; }
+
+int b200ocr_batch_upload(int device, const b200ocr_image* imgs, int n, b200ocr_batch_t* out) {
+  return capi_guard([&] {
+    if (!imgs || n < 1 || !out) throw std::invalid_argument("bad argument");
+    need_device(device);
+    cuda_check(cudaSetDevice(device), "cudaSetDevice");
+    auto h = std::make_unique<b200ocr_batch>();
+    h->device = device;
+    std::vector<HostImage> hi(n);
+    for (int i = 0; i < n; ++i) {
+      if (!imgs[i].data || imgs[i].rows <= 0 || imgs[i].cols <= 0) throw std::invalid_argument("empty image");
+      hi[i] = to_host(imgs[i]);
+    }
+    h->b.upload(hi.data(), n, nullptr);
+    cuda_check(cudaDeviceSynchronize(), "batch upload");
+    *out = h.release();
+  });
+}
+void b200ocr_batch_destroy(b200ocr_batch_t b) { if (b) { cudaSetDevice(b->device); delete b; } }
+
+int b200ocr_worker_process_resident(b200ocr_worker_t w, b200ocr_batch_t batch, const int* request_ids, char** jsons) {
+  return capi_guard([&] {
+    if (!w || !batch || !request_ids || !jsons) throw std::invalid_argument("null argument");
+    if (batch->device != w->w->device()) throw std::invalid_argument("batch and worker live on different devices");
+    std::vector<std::string> out;
+    w->w->process_resident(request_ids, batch->b.images(), &out);
+    for (size_t i = 0; i < out.size(); ++i) jsons[i] = dup_string(out[i]);
+  });
+}
+
+int b200ocr_worker_profile(b200ocr_worker_t w, int warmup, int reps, char** json) {
+  return capi_guard([&] {
+    if (!w || !json || reps < 1) throw std::invalid_argument("bad argument");
+    Worker& k = *w->w;
+    cuda_check(cudaSetDevice(k.device()), "cudaSetDevice");
+    std::string o = "{\"det\":" + profile_json(k.det().net(), k.stream(), warmup, reps, 51);
+    if (k.cls()) o += ",\"cls\":" + profile_json(k.cls()->net(), k.stream(), warmup, reps, -1);
+    o += ",\"rec\":" + profile_json(k.rec().net(), k.stream(), warmup, reps, -1) + "}";
+    *json = dup_string(o);
+  });
+}
 
 // ---- pool
 int b200ocr_pool_create(const char* model_dir, int n_devices, const int* devices, int workers_per_device,

@@ -510,6 +510,78 @@ Worker::~Worker() {
 
 long Worker::launches() const { return det_->launches + rec_->launches + (cls_ ? cls_->launches : 0); }
 
+// det -> ROI -> (cls -> rotate) -> rec for one batch of device images (reference src/ocr_worker.cpp:228-300)
+void Worker::run_device(const std::vector<DevImg>& dimgs, std::vector<std::vector<WordOut>>* words) {
+  const int nb = int(dimgs.size());
+  words->assign(nb, {});
+  std::vector<std::vector<Box>> boxes;
+  det_->run(dimgs, &boxes, stream_);
+  // ROI = cv::boundingRect(points) & image (src/ocr_worker.cpp:244-259); boundingRect of integer-valued
+  // float points is (minx, miny, maxx - minx + 1, maxy - miny + 1)
+  std::vector<std::vector<Roi>> calls(nb);
+  std::vector<Roi> all;
+  for (int i = 0; i < nb; ++i)
+    for (const Box& b : boxes[i]) {
+      int minx = b[0], maxx = b[0], miny = b[1], maxy = b[1];
+      for (int k = 1; k < 4; ++k) {
+        minx = std::min(minx, b[2 * k]); maxx = std::max(maxx, b[2 * k]);
+        miny = std::min(miny, b[2 * k + 1]); maxy = std::max(maxy, b[2 * k + 1]);
+      }
+      const int x0 = std::max(minx, 0), y0 = std::max(miny, 0);
+      const int x1 = std::min(maxx + 1, dimgs[i].cols), y1 = std::min(maxy + 1, dimgs[i].rows);
+      Roi r;
+      r.img = i; r.x = x0; r.y = y0; r.w = x1 - x0; r.h = y1 - y0;
+      if (r.w > 0 && r.h > 0) { calls[i].push_back(r); all.push_back(r); }
+    }
+  if (cls_ && !all.empty()) {
+    cls_->run(dimgs, all, nullptr, nullptr, stream_, /*fetch_to_host=*/false);
+    cls_->rotate_rois(dimgs, all, stream_);
+  }
+  std::vector<std::vector<std::string>> texts;
+  std::vector<std::vector<float>> scores;
+  rec_->run(dimgs, calls, &texts, &scores, stream_);
+  for (int i = 0; i < nb; ++i) {
+    std::vector<WordOut>& w = (*words)[i];
+    // words[i] = (rec_texts[i], rec_scores[i], det_boxes[i])  (src/ocr_worker.cpp:293-300)
+    for (size_t k = 0; k < texts[i].size(); ++k) w.push_back(WordOut{texts[i][k], scores[i][k], boxes[i][k]});
+  }
+}
+
+void Worker::process_resident(const int* request_ids, const std::vector<DevImg>& resident, std::vector<std::string>* json) {
+  cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+  const int n = int(resident.size());
+  json->assign(n, std::string());
+  const auto t_start = Clock::now();
+  std::vector<std::vector<WordOut>> words(n);
+  std::string error;
+  try {
+    for (int b0 = 0; b0 < n; b0 += opt_.max_batch) {
+      const int nb = std::min(opt_.max_batch, n - b0);
+      std::vector<DevImg> dimgs(resident.begin() + b0, resident.begin() + b0 + nb);
+      if (cls_) {  // rotations are in place: work on a copy
+        size_t total = 0;
+        for (auto& d : dimgs) total += (size_t(d.rows) * d.stride + 255) & ~size_t(255);
+        copy_.ensure(total);
+        size_t off = 0;
+        for (auto& d : dimgs) {
+          uint8_t* dst = copy_.as<uint8_t>() + off;
+          cuda_check(cudaMemcpyAsync(dst, d.p, size_t(d.rows) * d.stride, cudaMemcpyDeviceToDevice, stream_), "batch copy");
+          off += (size_t(d.rows) * d.stride + 255) & ~size_t(255);
+          d.p = dst;
+        }
+      }
+      std::vector<std::vector<WordOut>> w;
+      run_device(dimgs, &w);
+      for (int i = 0; i < nb; ++i) words[b0 + i] = std::move(w[i]);
+    }
+  } catch (const std::exception& e) {
+    error = e.what();
+  }
+  const double ms = ms_since(t_start);
+  for (int i = 0; i < n; ++i)
+    (*json)[i] = result_json(request_ids[i], worker_id_, error.empty(), resident[i].cols, resident[i].rows, ms, words[i], error);
+}
+
 void Worker::process_batch(const int* request_ids, const HostImage* imgs, int n, std::vector<std::string>* json) {
   cuda_check(cudaSetDevice(device_), "cudaSetDevice");
   json->assign(n, std::string());
@@ -529,38 +601,9 @@ void Worker::process_batch(const int* request_ids, const HostImage* imgs, int n,
     for (size_t b0 = 0; b0 < live.size(); b0 += size_t(opt_.max_batch)) {
       const int nb = int(std::min(live.size() - b0, size_t(opt_.max_batch)));
       batch_.upload(live_imgs.data() + b0, nb, stream_);
-      const std::vector<DevImg>& dimgs = batch_.images();
-      std::vector<std::vector<Box>> boxes;
-      det_->run(dimgs, &boxes, stream_);
-      // ROI = cv::boundingRect(points) & image (src/ocr_worker.cpp:244-259); boundingRect of integer-valued
-      // float points is (minx, miny, maxx - minx + 1, maxy - miny + 1)
-      std::vector<std::vector<Roi>> calls(nb);
-      std::vector<Roi> all;
-      for (int i = 0; i < nb; ++i)
-        for (const Box& b : boxes[i]) {
-          int minx = b[0], maxx = b[0], miny = b[1], maxy = b[1];
-          for (int k = 1; k < 4; ++k) {
-            minx = std::min(minx, b[2 * k]); maxx = std::max(maxx, b[2 * k]);
-            miny = std::min(miny, b[2 * k + 1]); maxy = std::max(maxy, b[2 * k + 1]);
-          }
-          const int x0 = std::max(minx, 0), y0 = std::max(miny, 0);
-          const int x1 = std::min(maxx + 1, dimgs[i].cols), y1 = std::min(maxy + 1, dimgs[i].rows);
-          Roi r;
-          r.img = i; r.x = x0; r.y = y0; r.w = x1 - x0; r.h = y1 - y0;
-          if (r.w > 0 && r.h > 0) { calls[i].push_back(r); all.push_back(r); }
-        }
-      if (cls_ && !all.empty()) {
-        cls_->run(dimgs, all, nullptr, nullptr, stream_, /*fetch_to_host=*/false);
-        cls_->rotate_rois(dimgs, all, stream_);
-      }
-      std::vector<std::vector<std::string>> texts;
-      std::vector<std::vector<float>> scores;
-      rec_->run(dimgs, calls, &texts, &scores, stream_);
-      for (int i = 0; i < nb; ++i) {
-        std::vector<WordOut>& w = words[b0 + i];
-        // words[i] = (rec_texts[i], rec_scores[i], det_boxes[i])  (src/ocr_worker.cpp:293-300)
-        for (size_t k = 0; k < texts[i].size(); ++k) w.push_back(WordOut{texts[i][k], scores[i][k], boxes[i][k]});
-      }
+      std::vector<std::vector<WordOut>> w;
+      run_device(batch_.images(), &w);
+      for (int i = 0; i < nb; ++i) words[b0 + i] = std::move(w[i]);
     }
   } catch (const std::exception& e) {
     for (auto& s : errors) s = e.what();

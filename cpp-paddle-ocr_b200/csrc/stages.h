@@ -131,6 +131,8 @@ class RecStage {
   DevBuf h_items_{true}, h_cidx_{true}, h_clen_{true}, h_cscore_{true};
 };
 
+struct WordOut { std::string text; float confidence; Box box; };
+
 struct WorkerOptions {
   bool enable_cls = false;
   int max_batch = 64;  // images processed together by process_batch
@@ -143,6 +145,10 @@ class Worker {
   ~Worker();
   // One result JSON per image (reference schema, src/ocr_worker.cpp:155-190).
   void process_batch(const int* request_ids, const HostImage* imgs, int n, std::vector<std::string>* json);
+  // Same, for images that already live in device memory (`resident` is not modified: when the classifier is
+  // enabled its in-place ROI rotations happen on a device-side copy, like the reference's cloned request image).
+  void process_resident(const int* request_ids, const std::vector<DevImg>& resident, std::vector<std::string>* json);
+  cudaStream_t stream() const { return stream_; }
   int worker_id() const { return worker_id_; }
   int device() const { return device_; }
   long launches() const;
@@ -156,13 +162,15 @@ class Worker {
   std::unique_ptr<DetStage> det_;
   std::unique_ptr<ClsStage> cls_;
   std::unique_ptr<RecStage> rec_;
+  void run_device(const std::vector<DevImg>& dimgs, std::vector<std::vector<WordOut>>* words);
   ImageBatch batch_;
+  DevBuf copy_;
 };
 
 // jsoncpp-compatible compact writer pieces (StreamWriterBuilder, indentation "", emitUTF8 true)
 std::string json_quote(const std::string& s);
 std::string json_double(double v);
-struct WordOut { std::string text; float confidence; Box box; };
+
 std::string result_json(int request_id, int worker_id, bool success, int width, int height, double ms,
                         const std::vector<WordOut>& words, const std::string& error);
 

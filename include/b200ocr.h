@@ -143,6 +143,14 @@ int b200ocr_worker_process(b200ocr_worker_t w, int request_id, const b200ocr_ima
 /* Throughput form: n requests through the GPU together (results are per image, identical to n process() calls). */
 int b200ocr_worker_process_batch(b200ocr_worker_t w, const int* request_ids, const b200ocr_image* imgs, int n,
                                  char** jsons);
+/* Device-resident inputs: upload once, process many times (what a caller that already has its frames in HBM uses;
+ * bench.py's device-resident throughput figure).  The batch is not modified by processing. */
+typedef struct b200ocr_batch* b200ocr_batch_t;
+int b200ocr_batch_upload(int device, const b200ocr_image* imgs, int n, b200ocr_batch_t* out);
+void b200ocr_batch_destroy(b200ocr_batch_t batch);
+int b200ocr_worker_process_resident(b200ocr_worker_t w, b200ocr_batch_t batch, const int* request_ids, char** jsons);
+/* The worker's CUDA stream (a cudaStream_t), so that a caller can bracket its work with CUDA events. */
+void* b200ocr_worker_stream(b200ocr_worker_t w);
 /* kernels launched by this worker so far */
 long long b200ocr_worker_launches(b200ocr_worker_t w);
 
@@ -197,6 +205,12 @@ int b200ocr_net_output(b200ocr_net_t net, float* out_f32, uint8_t* out_bitmap, i
 /* Copies an intermediate tensor (Paddle variable name) of the last forward to host as fp32 NCHW.
  * Needs B200OCR_NET_KEEP_ALL.  out may be NULL to query dims. */
 int b200ocr_net_fetch(b200ocr_net_t net, const char* var, float* out, size_t cap_elems, int dims[4]);
+/* Per-fused-layer device time (CUDA events around every launch, averaged over `reps` after `warmup` passes) of the last
+ * forward's shape, as JSON [{"name","kind","ms","flops","bytes","tensor_core"}...]; free with b200ocr_free. */
+int b200ocr_net_profile(b200ocr_net_t net, int warmup, int reps, char** json);
+/* Same for the three networks of a worker at the shapes of its last process call:
+ * {"det":[...],"cls":[...],"rec":[...]} . */
+int b200ocr_worker_profile(b200ocr_worker_t w, int warmup, int reps, char** json);
 /* Number of kernels one forward pass launches for the last shape. */
 int b200ocr_net_launches(b200ocr_net_t net);
 

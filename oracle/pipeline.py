@@ -119,13 +119,13 @@ class OracleWorker:
         self.rec = OracleRecognizer(os.path.join(model_dir, "rec"), os.path.join(model_dir, "rec", "ppocr_keys_v1.txt"),
                                     16, 28, 192)
 
-    def process_words(self, img, det_boxes=None):
+    def process_words(self, img, det_boxes=None, want_raw=False):
         """processRequest (src/ocr_worker.cpp:213-311) -> [(text, score, box)].  `det_boxes` overrides the detector
         (parity tests feed the GPU's boxes so that the later stages see identical upstream data)."""
         image = img.copy()  # OCRRequest deep-copies (ocr_worker.h:28-29); rotations below mutate that copy
         boxes = self.det.run(image) if det_boxes is None else [list(map(list, b)) for b in det_boxes]
         if not boxes:
-            return []
+            return ([], []) if want_raw else []
         crops = []
         for b in boxes:
             r = ops.bounding_rect_crop(b, image.shape[0], image.shape[1])
@@ -133,14 +133,15 @@ class OracleWorker:
                 x, y, w, h = r
                 crops.append(image[y:y + h, x:x + w])  # ROI view, not a copy (ocr_worker.cpp:257)
         if not crops:
-            return []
+            return ([], []) if want_raw else []
         if self.cls is not None:
             labels, _ = self.cls.run(crops)
             for i, lab in enumerate(labels):
                 if lab == 1:
                     crops[i][:] = cv2.rotate(crops[i], cv2.ROTATE_180)  # in place on the shared image
-        texts, scores = self.rec.run(crops)
-        return [(texts[i], scores[i], boxes[i]) for i in range(len(texts))]
+        texts, scores, raw = self.rec.run(crops, want_raw=True)
+        words = [(texts[i], scores[i], boxes[i]) for i in range(len(texts))]
+        return (words, raw) if want_raw else words
 
     def process(self, request_id, img):
         t0 = time.perf_counter()

@@ -76,19 +76,29 @@ def rec_crops(n: int, height=48, width=320, seed=0):
 
 
 def prob_map(seed: int, height=320, width=512, n_boxes=12, rings=2, lines=2):
-    """S-prob: synthetic DB probability map: blurred rotated rectangles, rings (hole contours), 1-px lines."""
+    """S-prob: synthetic DB probability map: blurred rotated rectangles laid out on a jittered grid (so that most
+    stay separate blobs; a few touch and merge), rings (hole contours), 1-px lines, low-amplitude noise."""
     rng = np.random.default_rng(seed)
     p = np.zeros((height, width), np.float32)
-    for _ in range(n_boxes):
-        c = (float(rng.uniform(20, width - 20)), float(rng.uniform(10, height - 10)))
-        sz = (float(rng.uniform(20, 160)), float(rng.uniform(6, 28)))
-        ang = float(rng.uniform(-20, 20)) if rng.random() < 0.7 else float(rng.uniform(-90, 90))
-        pts = cv2.boxPoints((c, sz, ang)).astype(np.int32)
-        cv2.fillPoly(p, [pts], float(rng.uniform(0.5, 0.98)))
+    cols = max(1, width // 150)
+    rows = max(1, -(-n_boxes // cols))
+    ch, cw = height / rows, width / cols
+    k = 0
+    for r in range(rows):
+        for c in range(cols):
+            if k >= n_boxes:
+                break
+            k += 1
+            cx = (c + 0.5) * cw + float(rng.uniform(-0.1, 0.1)) * cw
+            cy = (r + 0.5) * ch + float(rng.uniform(-0.15, 0.15)) * ch
+            sz = (float(rng.uniform(0.35, 0.95)) * cw, float(rng.uniform(0.25, 0.7)) * min(ch, 40.0))
+            ang = float(rng.uniform(-8, 8)) if rng.random() < 0.8 else float(rng.uniform(-35, 35))
+            pts = cv2.boxPoints(((cx, cy), sz, ang)).astype(np.int32)
+            cv2.fillPoly(p, [pts], float(rng.uniform(0.45, 0.98)))
     for _ in range(rings):
-        c = (int(rng.uniform(40, width - 40)), int(rng.uniform(30, height - 30)))
-        cv2.ellipse(p, c, (int(rng.uniform(15, 40)), int(rng.uniform(10, 25))), float(rng.uniform(0, 180)), 0, 360,
-                    float(rng.uniform(0.6, 0.95)), int(rng.integers(2, 6)))
+        c = (int(rng.uniform(40, max(41, width - 40))), int(rng.uniform(20, max(21, height - 20))))
+        cv2.ellipse(p, c, (int(rng.uniform(12, 40)), int(rng.uniform(8, 22))), float(rng.uniform(0, 180)), 0, 360,
+                    float(rng.uniform(0.6, 0.95)), int(rng.integers(2, 5)))
     for _ in range(lines):
         a = (int(rng.uniform(0, width)), int(rng.uniform(0, height)))
         b = (int(rng.uniform(0, width)), int(rng.uniform(0, height)))
