@@ -155,6 +155,7 @@ def run_ours(args):
     import torch
     import b200ocr
     import make_synth_weights
+    from b200ocr import sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -177,7 +178,7 @@ def run_ours(args):
     worker = b200ocr.Worker(rank, models, gpu_id=local, enable_cls=True)
     n_sets = min(K, 4) if K > 0 else 1
     # distinct images per rank and per set; each set is B x 1.97 MB (>= L2 at B = 64), sets rotate between steps
-    host_sets = [make_cards(B, 1_000_000 * rank + 10_000 * s, pinned=True) for s in range(n_sets)]
+    host_sets = [make_cards(B, sharding.card_seed(rank, s, 0), pinned=True) for s in range(n_sets)]
     dev_sets = [b200ocr.DeviceBatch(list(h), device=local) for h in host_sets]
     ids = list(range(B))
     stream = torch.cuda.ExternalStream(worker.stream, device=torch.device("cuda", local))
@@ -203,12 +204,7 @@ def run_ours(args):
         barrier()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms, wall * 1e3], device="cuda", dtype=torch.float64)
-        cnt = torch.tensor([float(worker.launches - l0), float(words)], device="cuda", dtype=torch.float64)
-        if dist:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        return float(t[0]), float(t[1]), int(cnt[0]), float(cnt[1])
+        return sharding.reduce_run(dist, "cuda", ms, wall * 1e3, worker.launches - l0, words)
 
     def step_resident(s):
         out = worker.process_resident(ids, dev_sets[s % n_sets])

@@ -41,6 +41,7 @@ _sig("b200ocr_net_destroy", None, C.c_void_p)
 _sig("b200ocr_net_kind", C.c_int, C.c_void_p, C.c_char_p, C.c_int)
 _sig("b200ocr_net_plan_dump", C.c_int, C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int))
 _sig("b200ocr_net_forward", C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int)
+_sig("b200ocr_net_forward_ragged", C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p)
 _sig("b200ocr_net_out_shape", C.c_int, C.c_void_p, C.POINTER(C.c_int))
 _sig("b200ocr_net_output", C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
 _sig("b200ocr_net_fetch", C.c_int, C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int))
@@ -104,11 +105,16 @@ class Net:
         check(lib.b200ocr_net_plan_dump(self._h, buf, need.value, None))
         return buf.value.decode()
 
-    def forward(self, x: np.ndarray, thresh_u8: int = -1):
+    def forward(self, x: np.ndarray, thresh_u8: int = -1, widths=None):
         x = np.ascontiguousarray(x, dtype=np.float32)
         n, c, h, w = x.shape
         assert c == 3
-        check(lib.b200ocr_net_forward(self._h, x.ctypes.data, n, h, w, thresh_u8))
+        if widths is not None:
+            wd = np.ascontiguousarray(widths, np.int32)
+            assert wd.shape == (n,)
+            check(lib.b200ocr_net_forward_ragged(self._h, x.ctypes.data, n, h, w, wd.ctypes.data))
+        else:
+            check(lib.b200ocr_net_forward(self._h, x.ctypes.data, n, h, w, thresh_u8))
         shp = (C.c_int * 3)()
         check(lib.b200ocr_net_out_shape(self._h, shp))
         n, oh, ow = shp[0], shp[1], shp[2]

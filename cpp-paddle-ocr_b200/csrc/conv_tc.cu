@@ -114,6 +114,9 @@ struct ConvTcArgs {
   int out_pitch;
   const float* bias;
   Epi epi;
+  // ragged batches: valid output width per image; pixel -> (image, x) through the un-flattened dims
+  const int* vw;
+  int mask_w, mask_hw;
 };
 
 __global__ void __launch_bounds__(192)
@@ -207,6 +210,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int x = x0 + tw_, y = y0 + th_, n = n0 + tn_;
     const bool valid = r < rows && x < a.ow && y < a.oh && n < a.on;
     const long pix = (long(n) * a.oh + y) * a.ow + x;
+    const bool masked = valid && a.vw && int(pix % a.mask_w) >= a.vw[pix / a.mask_hw];
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int c8lim = (a.cout + 7) & ~7;
@@ -238,7 +242,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        if (c0 + i >= a.cout) f[i] = 0.f;
+        if (c0 + i >= a.cout || masked) f[i] = 0.f;
       __half* op = a.out + pix * a.out_pitch + c0;
       uint4 o0, o1;
       __half2* h0 = reinterpret_cast<__half2*>(&o0);
@@ -350,6 +354,9 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
   a.cout = out.c;
   a.out = out.p;
   a.out_pitch = out.pitch;
+  a.vw = nullptr;
+  a.mask_w = out_.w;
+  a.mask_hw = out_.h * out_.w;
 
   auto* impl = new ConvTcPlanImpl();
   const int c8 = (in.c + 7) & ~7;
@@ -378,10 +385,11 @@ void free_conv_tc_plan(ConvTcPlan* p) {
   p->impl = nullptr;
 }
 
-void launch_conv_tc(const ConvTcPlan& p, const float* bias, const Epi& e, cudaStream_t s) {
+void launch_conv_tc(const ConvTcPlan& p, const float* bias, const Epi& e, cudaStream_t s, const int* vw) {
   ConvTcArgs a = p.impl->args;
   a.bias = bias;
   a.epi = e;
+  a.vw = vw;
   conv_tc_kernel<<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a);
 }
 

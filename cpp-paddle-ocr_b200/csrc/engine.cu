@@ -16,6 +16,7 @@ struct Net::Inst {
   int n = 0, h = 0, w = 0;
   std::vector<Shape3> ts;            // per tensor
   std::vector<int> splits, hw;       // per tensor (Gap outputs): partial-sum layout
+  std::vector<int> gap_src;          // per tensor (Gap outputs): the pooled tensor
   std::vector<size_t> boff, bbytes;  // per buffer
   std::vector<ConvTcPlan> tc;        // per layer (impl == nullptr -> CUDA-core kernel)
   size_t need = 0;
@@ -52,29 +53,32 @@ Net::~Net() {
   cudaFree(d_wh_);
   cudaFree(d_wf_);
   cudaFree(arena_);
+  cudaFree(vw_dev_);
+  if (vw_pin_) cudaFreeHost(vw_pin_);
 }
 
 namespace {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 }  // namespace
 
-Net::Inst* Net::instantiate(int n, int h, int w) {
-  auto I = std::make_unique<Inst>();
-  I->n = n; I->h = h; I->w = w;
-  const int nt = int(plan_.tensors.size()), nb = int(plan_.buffers.size()), nl = int(plan_.layers.size());
-  I->ts.assign(nt, Shape3());
-  I->splits.assign(nt, 0);
-  I->hw.assign(nt, 0);
-  I->ts[plan_.input] = Shape3{n, h, w};
+void Net::infer(int n, int h, int w, std::vector<Shape3>* ts_, std::vector<int>* splits, std::vector<int>* hwv,
+                std::vector<int>* gap_src) const {
+  const int nt = int(plan_.tensors.size());
+  std::vector<Shape3>& ts = *ts_;
+  ts.assign(nt, Shape3());
+  if (splits) splits->assign(nt, 0);
+  if (hwv) hwv->assign(nt, 0);
+  if (gap_src) gap_src->assign(nt, -1);
+  ts[plan_.input] = Shape3{n, h, w};
   auto fail = [&](const Layer& L, const char* why) {
     throw std::runtime_error("shape error at layer " + L.name + ": " + why);
   };
   // ---- shape inference (concat views made by re-homing have no producer: they take a member's shape)
   auto resolve = [&](int t) {
-    if (I->ts[t].n == 0)
+    if (ts[t].n == 0)
       for (int u = 0; u < nt; ++u)
-        if (u != t && plan_.tensors[u].buf == plan_.tensors[t].buf && I->ts[u].n) { I->ts[t] = I->ts[u]; break; }
-    return I->ts[t];
+        if (u != t && plan_.tensors[u].buf == plan_.tensors[t].buf && ts[u].n) { ts[t] = ts[u]; break; }
+    return ts[t];
   };
   for (const Layer& L : plan_.layers) {
     const Shape3 in = resolve(L.in);
@@ -95,22 +99,23 @@ Net::Inst* Net::instantiate(int n, int h, int w) {
         break;
       case LKind::Gap:
         o = Shape3{in.n, 1, 1};
-        I->splits[L.out] = gap_splits(in.h * in.w);
-        I->hw[L.out] = in.h * in.w;
+        if (splits) (*splits)[L.out] = gap_splits(in.h);
+        if (hwv) (*hwv)[L.out] = in.h * in.w;
+        if (gap_src) (*gap_src)[L.out] = L.in;
         break;
       case LKind::SeFc:
       case LKind::FcSoftmax:
         o = Shape3{in.n, 1, 1};
         break;
       case LKind::UpAdd: {
-        const Shape3 b = I->ts[L.in2];
+        const Shape3 b = ts[L.in2];
         if (b.h * 2 != in.h || b.w * 2 != in.w) fail(L, "FPN levels are not 2x apart (input not a multiple of 32?)");
         break;
       }
       case LKind::UpCat: {
         const int sh[4] = {L.kh, L.kw, L.sh, L.sw};
         for (int k = 0; k < 4 && L.ins[k] >= 0; ++k) {
-          const Shape3 s = I->ts[L.ins[k]];
+          const Shape3 s = ts[L.ins[k]];
           if ((s.h << sh[k]) != in.h || (s.w << sh[k]) != in.w) fail(L, "concat inputs do not upsample to one size");
         }
         break;
@@ -126,9 +131,16 @@ Net::Inst* Net::instantiate(int n, int h, int w) {
         break;
       default: break;
     }
-    I->ts[L.out] = o;
+    ts[L.out] = o;
   }
   for (int t = 0; t < nt; ++t) resolve(t);
+}
+
+Net::Inst* Net::instantiate(int n, int h, int w) {
+  auto I = std::make_unique<Inst>();
+  I->n = n; I->h = h; I->w = w;
+  const int nt = int(plan_.tensors.size()), nb = int(plan_.buffers.size()), nl = int(plan_.layers.size());
+  infer(n, h, w, &I->ts, &I->splits, &I->hw, &I->gap_src);
   // ---- buffer sizes
   I->boff.assign(nb, 0);
   I->bbytes.assign(nb, 0);
@@ -203,8 +215,42 @@ static TV make_tv(uint8_t* arena, const Plan& plan, const std::vector<size_t>& b
   return v;
 }
 
-__half* Net::prepare(int n, int h, int w) {
+__half* Net::prepare(int n, int h, int w, const int* widths) {
   if (n < 1 || h < 1 || w < 1) throw std::runtime_error("Net::prepare: empty input");
+  ragged_ = false;
+  if (widths) {
+    bool all_full = true;
+    for (int i = 0; i < n; ++i) {
+      if (widths[i] < 1 || widths[i] > w) throw std::runtime_error("Net::prepare: row width out of range");
+      all_full &= widths[i] == w;
+    }
+    if (!all_full) {
+      for (const Layer& L : plan_.layers)
+        if (L.kind == LKind::UpAdd || L.kind == LKind::UpCat || L.kind == LKind::DbHead || L.kind == LKind::FcSoftmax)
+          throw std::runtime_error("ragged batches are only supported for sequence (rec) graphs");
+      const size_t nt = plan_.tensors.size(), need = nt * size_t(n);
+      cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+      if (need > vw_cap_) {
+        cuda_check(cudaDeviceSynchronize(), "sync before table growth");
+        cudaFree(vw_dev_);
+        if (vw_pin_) cudaFreeHost(vw_pin_);
+        vw_cap_ = need + need / 2;
+        cuda_check(cudaMalloc(&vw_dev_, vw_cap_ * sizeof(int)), "cudaMalloc width table");
+        cuda_check(cudaMallocHost(&vw_pin_, vw_cap_ * sizeof(int)), "cudaMallocHost width table");
+      }
+      std::map<int, std::vector<Shape3>> per_width;  // per distinct row width: every tensor's shape
+      for (int i = 0; i < n; ++i) {
+        auto it = per_width.find(widths[i]);
+        if (it == per_width.end()) {
+          std::vector<Shape3> ts;
+          infer(1, h, widths[i], &ts, nullptr, nullptr, nullptr);
+          it = per_width.emplace(widths[i], std::move(ts)).first;
+        }
+        for (size_t t = 0; t < nt; ++t) vw_pin_[t * n + i] = it->second[t].w;
+      }
+      ragged_ = true;
+    }
+  }
   cuda_check(cudaSetDevice(device_), "cudaSetDevice");
   auto key = std::make_tuple(n, h, w);
   auto it = cache_.find(key);
@@ -231,6 +277,7 @@ __half* Net::prepare(int n, int h, int w) {
 
 void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<void(int, bool)>* hook) {
   auto tv = [&](int t) { return make_tv(arena_, plan_, I.boff, I.ts, t); };
+  auto vwp = [&](int t) -> const int* { return ragged_ ? vw_dev_ + size_t(t) * I.n : nullptr; };
   auto vecp = [&](int t) { return reinterpret_cast<float*>(arena_ + I.boff[plan_.tensors[t].buf]); };
   int launches = 0;
   for (size_t li = 0; li < plan_.layers.size(); ++li) {
@@ -253,17 +300,17 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
         const float* bias = d_wf_ + L.bias_off;
         if (!opt_.force_simt && conv_tc_eligible(in, out, g)) {
           if (!I.tc[li].impl) I.tc[li] = make_conv_tc_plan(in, out, w, g);
-          launch_conv_tc(I.tc[li], bias, e, s);
+          launch_conv_tc(I.tc[li], bias, e, s, vwp(L.out));
         } else {
-          launch_conv_simt(in, out, w, bias, g, e, s);
+          launch_conv_simt(in, out, w, bias, g, e, s, vwp(L.out));
         }
         break;
       }
-      case LKind::DwConv: launch_dwconv(tv(L.in), tv(L.out), d_wf_ + L.wf_off, g, e, s); break;
+      case LKind::DwConv: launch_dwconv(tv(L.in), tv(L.out), d_wf_ + L.wf_off, g, e, s, vwp(L.out)); break;
       case LKind::Gap: launch_gap_partial(tv(L.in), vecp(L.out), I.splits[L.out], s); break;
       case LKind::SeFc:
         launch_se_fc(vecp(L.in), I.splits[L.in], I.hw[L.in], I.ts[L.in].n, L.cin, L.cmid, d_wf_ + L.wf_off,
-                     L.act_a, L.act_b, vecp(L.out), s);
+                     L.act_a, L.act_b, vecp(L.out), s, vwp(I.gap_src[L.in]), I.ts[I.gap_src[L.in]].h);
         break;
       case LKind::Scale: launch_scale(tv(L.in), vecp(L.in2), L.scale_residual, tv(L.out), s); break;
       case LKind::UpAdd: launch_upadd(tv(L.in), tv(L.in2), tv(L.out), s); break;
@@ -274,10 +321,10 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
         launch_upcat(ins, sh, nin, tv(L.out), s);
         break;
       }
-      case LKind::Pool: launch_pool(tv(L.in), tv(L.out), L.kh, L.kw, L.sh, L.sw, L.pool_max, s); break;
+      case LKind::Pool: launch_pool(tv(L.in), tv(L.out), L.kh, L.kw, L.sh, L.sw, L.pool_max, s, vwp(L.out)); break;
       case LKind::Add: launch_add(tv(L.in), tv(L.in2), tv(L.out), s); break;
-      case LKind::LayerNorm: launch_layernorm(tv(L.in), tv(L.out), d_wf_ + L.wf_off, L.eps, s); break;
-      case LKind::Attn: launch_attention(tv(L.in), tv(L.out), L.heads, L.head_dim, L.attn_scale, s); break;
+      case LKind::LayerNorm: launch_layernorm(tv(L.in), tv(L.out), d_wf_ + L.wf_off, L.eps, s, vwp(L.out)); break;
+      case LKind::Attn: launch_attention(tv(L.in), tv(L.out), L.heads, L.head_dim, L.attn_scale, s, vwp(L.out)); break;
       case LKind::DbHead: {
         TV in = tv(L.in);
         float* prob = vecp(L.out);
@@ -296,7 +343,8 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
         if (!opt_.force_simt && ctc_tc_eligible(in, L.cin_pad))
           launch_ctc_head_tc(in, d_wh_ + L.wh_off, d_wf_ + L.bias_off, L.cin_pad, L.cout, L.cout_pad, idx, prob, s);
         else
-          launch_ctc_head_simt(in, d_wh_ + L.wh_off, d_wf_ + L.bias_off, L.cin_pad, L.cout, L.cout_pad, idx, prob, s);
+          launch_ctc_head_simt(in, d_wh_ + L.wh_off, d_wf_ + L.bias_off, L.cin_pad, L.cout, L.cout_pad, idx, prob, s,
+                               vwp(L.in));
         break;
       }
     }
@@ -375,7 +423,10 @@ void Net::run(cudaStream_t stream, int thresh_u8) {
   if (!cur_) throw std::runtime_error("Net::run before prepare");
   Inst& I = *cur_;
   ++I.runs;
-  if (!opt_.use_graph || I.runs == 1) {
+  if (ragged_)
+    cuda_check(cudaMemcpyAsync(vw_dev_, vw_pin_, plan_.tensors.size() * size_t(I.n) * sizeof(int), cudaMemcpyHostToDevice,
+                               stream), "width table upload");
+  if (!opt_.use_graph || I.runs == 1 || ragged_) {  // ragged shapes rarely repeat: always eager
     // first run of a shape is eager: encodes tensor maps, sets function attributes
     record(I, stream, thresh_u8);
     cuda_check(cudaGetLastError(), "forward launch");

@@ -42,7 +42,11 @@ class Net {
 
   // Prepare buffers (and the CUDA graph) for an input of n x h x w.  The returned pointer is the
   // network input: NHWC fp16 with channel pitch 8 (channels 3..7 must be written as zero).
-  __half* prepare(int n, int h, int w);
+  // `widths` (optional, host int[n]): ragged batch -- row i is only widths[i] <= w columns wide; every layer then
+  // treats the columns beyond a row's (layer-scaled) width as the zero padding it would see at the edge of a
+  // tensor of that width, so each row's result is bit-identical to running it in a dense batch of its own
+  // width.  The caller must write zeros into the input beyond widths[i].  Sequence graphs (rec) only.
+  __half* prepare(int n, int h, int w, const int* widths = nullptr);
   // Execute the forward pass for the last prepared shape on `stream`.
   //   det: `thresh_u8` >= 0 also writes the thresholded bitmap.
   void run(cudaStream_t stream, int thresh_u8 = -1);
@@ -68,6 +72,8 @@ class Net {
  private:
   struct Inst;
   Inst* instantiate(int n, int h, int w);
+  void infer(int n, int h, int w, std::vector<Shape3>* ts, std::vector<int>* splits, std::vector<int>* hw,
+             std::vector<int>* gap_src) const;
   void record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<void(int, bool)>* hook = nullptr);
 
   Plan plan_;
@@ -79,6 +85,11 @@ class Net {
   size_t arena_bytes_ = 0;
   std::map<std::tuple<int, int, int>, std::unique_ptr<Inst>> cache_;
   Inst* cur_ = nullptr;
+  // ragged batches: per tensor, per row valid widths (int[nt][n]), staged in pinned memory
+  bool ragged_ = false;
+  int* vw_pin_ = nullptr;
+  int* vw_dev_ = nullptr;
+  size_t vw_cap_ = 0;
 };
 
 void cuda_check(cudaError_t e, const char* what);

@@ -21,6 +21,10 @@ struct Epi {
   int res_pitch = 0;
 };
 
+// Ragged batches: row n of a [N,h,w] tensor may only be `vw[n]` columns wide (the recognizer's text lines have
+// different padded widths).  A kernel that is given `vw` (device int[N], valid width of its OUTPUT tensor) writes
+// zeros at x >= vw[n], so that the next convolution sees exactly the zero padding it would see at the edge of a
+// tensor that is vw[n] wide.  nullptr = dense batch.
 struct ConvGeom {
   int kh = 1, kw = 1, sh = 1, sw = 1, ph = 0, pw = 0;
   int cin_pad = 0;  // weight row stride per tap
@@ -30,7 +34,7 @@ struct ConvGeom {
 // ---- convolution family -----------------------------------------------------
 // CUDA-core direct convolution (stems with C_in=3 and shapes the tensor-core path does not take).
 void launch_conv_simt(const TV& in, const TV& out, const __half* w, const float* bias,
-                      const ConvGeom& g, const Epi& e, cudaStream_t s);
+                      const ConvGeom& g, const Epi& e, cudaStream_t s, const int* vw = nullptr);
 // tcgen05 implicit-GEMM convolution (stride 1; 1x1, 1x3, 3x3): TMA -> smem -> UMMA -> TMEM -> epilogue.
 // Returns false if the shape is not eligible (caller then uses the CUDA-core kernel).
 // Tensor maps are encoded once per (layer, shape) by make_conv_tc_plan.
@@ -39,26 +43,31 @@ struct ConvTcPlan { ConvTcPlanImpl* impl = nullptr; };
 bool conv_tc_eligible(const TV& in, const TV& out, const ConvGeom& g);
 ConvTcPlan make_conv_tc_plan(const TV& in, const TV& out, const __half* w, const ConvGeom& g);
 void free_conv_tc_plan(ConvTcPlan* p);
-void launch_conv_tc(const ConvTcPlan& p, const float* bias, const Epi& e, cudaStream_t s);
+void launch_conv_tc(const ConvTcPlan& p, const float* bias, const Epi& e, cudaStream_t s, const int* vw = nullptr);
 void launch_dwconv(const TV& in, const TV& out, const float* w_bias, const ConvGeom& g,
-                   const Epi& e, cudaStream_t s);
+                   const Epi& e, cudaStream_t s, const int* vw = nullptr);
 
 // ---- SE block ---------------------------------------------------------------
-int gap_splits(int hw);
+int gap_splits(int h);
 void launch_gap_partial(const TV& in, float* partial, int splits, cudaStream_t s);
+// vw_in: valid width of the pooled tensor per row (mean over h * vw_in[n] pixels), h its height
 void launch_se_fc(const float* partial, int splits, int hw, int n, int c, int cmid, const float* blk,
-                  float slope, float offset, float* gate, cudaStream_t s);
+                  float slope, float offset, float* gate, cudaStream_t s, const int* vw_in = nullptr, int h = 0);
 void launch_scale(const TV& in, const float* gate, bool add_x, const TV& out, cudaStream_t s);
 
 // ---- glue ---------------------------------------------------------------------
 void launch_upadd(const TV& a, const TV& b_half_res, const TV& out, cudaStream_t s);
 void launch_upcat(const TV in[4], const int shift[4], int nin, const TV& out, cudaStream_t s);
 void launch_add(const TV& a, const TV& b, const TV& out, cudaStream_t s);
-void launch_pool(const TV& in, const TV& out, int kh, int kw, int sh, int sw, bool is_max, cudaStream_t s);
+void launch_pool(const TV& in, const TV& out, int kh, int kw, int sh, int sw, bool is_max, cudaStream_t s,
+                 const int* vw = nullptr);
 
 // ---- SVTR neck ----------------------------------------------------------------
-void launch_layernorm(const TV& in, const TV& out, const float* gamma_beta, float eps, cudaStream_t s);
-void launch_attention(const TV& qkv, const TV& out, int heads, int head_dim, float scale, cudaStream_t s);
+void launch_layernorm(const TV& in, const TV& out, const float* gamma_beta, float eps, cudaStream_t s,
+                      const int* vw = nullptr);
+// vw: number of valid tokens per sequence (keys beyond it are ignored, queries beyond it produce zeros)
+void launch_attention(const TV& qkv, const TV& out, int heads, int head_dim, float scale, cudaStream_t s,
+                      const int* vw = nullptr);
 
 // ---- heads ----------------------------------------------------------------------
 // DB head tail: deconv2x2+BN+relu -> deconv2x2 -> sigmoid, plus cbuf=(u8)(p*255) > thresh bitmap.
@@ -68,7 +77,7 @@ void launch_fc_softmax(const float* partial, int splits, int hw, int n, int cin,
                        const float* blk, float* out, cudaStream_t s);
 // CTC head: logits = feat . W^T + b; per (n,t): argmax index and softmax probability of the max.
 void launch_ctc_head_simt(const TV& feat, const __half* w, const float* bias, int cin_pad, int ncls,
-                          int ncls_pad, int* idx, float* prob, cudaStream_t s);
+                          int ncls_pad, int* idx, float* prob, cudaStream_t s, const int* vw = nullptr);
 bool ctc_tc_eligible(const TV& feat, int cin_pad);
 void launch_ctc_head_tc(const TV& feat, const __half* w, const float* bias, int cin_pad, int ncls,
                         int ncls_pad, int* idx, float* prob, cudaStream_t s);
@@ -77,7 +86,8 @@ void launch_ctc_head_tc(const TV& feat, const __half* w, const float* bias, int 
 struct NormParams { float scale[3], shift[3]; };  // y = (u8 * (1/255.f)) * scale + shift, per BGR channel
 NormParams make_norm(const float mean[3], const float scale[3]);
 struct DetPreItem { const uint8_t* src; int w, h; long stride; };          // one source image (device memory)
-struct CropItem { const uint8_t* img; long stride; int x, y, w, h, resize_w; };  // ROI of a device image
+// ROI of a device image; columns [resize_w, pad_w) hold the pad value, columns >= pad_w (ragged batches) zero
+struct CropItem { const uint8_t* img; long stride; int x, y, w, h, resize_w, pad_w; };
 // [n] images -> [n, dh, dw] network input; every image is resized to the same dh x dw
 void launch_det_preprocess(const DetPreItem* items_dev, int n, int dh, int dw, const NormParams& np, __half* out,
                            cudaStream_t s);

@@ -50,7 +50,13 @@ __device__ __forceinline__ void st8(__half* p, const H8& v) { *reinterpret_cast<
 
 // Shared epilogue for 8 consecutive channels starting at c0 of pixel `pix`.
 __device__ __forceinline__ void epilogue8(float* acc, const float* bias, int c0, int cout, const Epi& e,
-                                          const TV& out, long pix) {
+                                          const TV& out, long pix, bool masked = false) {
+  if (masked) {  // ragged batch: beyond this row's valid width the tensor is zero
+    H8 z;
+    z.u = make_uint4(0, 0, 0, 0);
+    st8(out.p + pix * out.pitch + c0, z);
+    return;
+  }
   float r[8];
   if (e.res) ld8(e.res + pix * e.res_pitch + c0).to_float(r);
 #pragma unroll
@@ -68,7 +74,7 @@ __device__ __forceinline__ void epilogue8(float* acc, const float* bias, int c0,
 // ---------------------------------------------------------------- direct conv
 __global__ void __launch_bounds__(kThreads)
 conv_simt_kernel(TV in, TV out, const __half* __restrict__ w, const float* __restrict__ bias,
-                 ConvGeom g, Epi e) {
+                 ConvGeom g, Epi e, const int* __restrict__ vw) {
   const int cgs = (out.c + 7) >> 3;
   const long npix = long(out.n) * out.h * out.w;
   const long total = npix * cgs;
@@ -81,6 +87,7 @@ conv_simt_kernel(TV in, TV out, const __half* __restrict__ w, const float* __res
     const int ox = int(pix % out.w);
     const int oy = int((pix / out.w) % out.h);
     const int n = int(pix / (long(out.w) * out.h));
+    if (vw && ox >= vw[n]) { epilogue8(nullptr, bias, cg * 8, out.c, e, out, pix, true); continue; }
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int ky = 0; ky < g.kh; ++ky) {
       const int iy = oy * g.sh - g.ph + ky;
@@ -110,7 +117,7 @@ conv_simt_kernel(TV in, TV out, const __half* __restrict__ w, const float* __res
 // ---------------------------------------------------------------- depthwise conv
 template <int KH, int KW>
 __global__ void __launch_bounds__(kThreads)
-dwconv_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi e) {
+dwconv_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi e, const int* __restrict__ vw) {
   const int cgs = (out.c + 7) >> 3;
   const int cp = g.cout_pad;
   const long total = long(out.n) * out.h * out.w * cgs;
@@ -121,6 +128,7 @@ dwconv_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi e) {
     const int ox = int(pix % out.w);
     const int oy = int((pix / out.w) % out.h);
     const int n = int(pix / (long(out.w) * out.h));
+    if (vw && ox >= vw[n]) { epilogue8(nullptr, bias, cg * 8, out.c, e, out, pix, true); continue; }
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int ky = 0; ky < KH; ++ky) {
@@ -154,18 +162,22 @@ gap_partial_kernel(TV in, float* __restrict__ partial, int splits) {
   const int lanes = max(1, kThreads / cgs);
   const int split = blockIdx.x, n = blockIdx.y;
   const int hw = in.h * in.w;
-  const int chunk = (hw + splits - 1) / splits;
-  const int p0 = split * chunk, p1 = min(hw, p0 + chunk);
+  // A split owns a range of ROWS and a lane owns the columns x == lane (mod lanes): the order in which one
+  // accumulator sees the valid pixels of a text line does not depend on how wide the surrounding tensor is
+  // (zero columns of a ragged batch add exactly 0), so pooled values are bit-identical to a dense run.
+  const int rows_per = (in.h + splits - 1) / splits;
+  const int y0 = split * rows_per, y1 = min(in.h, y0 + rows_per);
   const int cg = threadIdx.x % cgs, lane = threadIdx.x / cgs;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (lane < lanes) {
     const __half* base = in.p + long(n) * hw * in.pitch + cg * 8;
-    for (int p = p0 + lane; p < p1; p += lanes) {
-      float x[8];
-      ld8(base + long(p) * in.pitch).to_float(x);
+    for (int y = y0; y < y1; ++y)
+      for (int xx = lane; xx < in.w; xx += lanes) {
+        float x[8];
+        ld8(base + (long(y) * in.w + xx) * in.pitch).to_float(x);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += x[i];
-    }
+        for (int i = 0; i < 8; ++i) acc[i] += x[i];
+      }
 #pragma unroll
     for (int i = 0; i < 8; ++i) sm[lane * cp + cg * 8 + i] = acc[i];
   }
@@ -180,12 +192,14 @@ gap_partial_kernel(TV in, float* __restrict__ partial, int splits) {
 // blk: w1[cmid][c], b1[cmid], w2[c][cmid], b2[c]
 __global__ void __launch_bounds__(kThreads)
 se_fc_kernel(const float* __restrict__ partial, int splits, float inv_hw, int c, int cmid,
-             const float* __restrict__ blk, float slope, float offset, float* __restrict__ gate) {
+             const float* __restrict__ blk, float slope, float offset, float* __restrict__ gate,
+             const int* __restrict__ vw_in, int h) {
   extern __shared__ float sm[];
   const int cp = (c + 7) / 8 * 8;
   float* pooled = sm;        // [cp]
   float* hidden = sm + cp;   // [cmid]
   const int n = blockIdx.x;
+  if (vw_in) inv_hw = 1.f / float(h * vw_in[n]);
   for (int i = threadIdx.x; i < cp; i += blockDim.x) {
     float s = 0.f;
     for (int k = 0; k < splits; ++k) s += partial[(long(n) * splits + k) * cp + i];
@@ -303,7 +317,7 @@ __global__ void __launch_bounds__(kThreads) add_kernel(TV a, TV b, TV out) {
 
 // windows are clipped to the input; avg divides by the clipped size (Paddle exclusive=true)
 __global__ void __launch_bounds__(kThreads)
-pool_kernel(TV in, TV out, int kh, int kw, int sh, int sw, int is_max) {
+pool_kernel(TV in, TV out, int kh, int kw, int sh, int sw, int is_max, const int* __restrict__ vw) {
   const int cgs = (in.c + 7) >> 3;
   const long total = long(out.n) * out.h * out.w * cgs;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
@@ -311,6 +325,12 @@ pool_kernel(TV in, TV out, int kh, int kw, int sh, int sw, int is_max) {
     const long pix = t / cgs;
     const int ox = int(pix % out.w), oy = int((pix / out.w) % out.h), n = int(pix / (long(out.w) * out.h));
     const int y0 = oy * sh, y1 = min(y0 + kh, in.h), x0 = ox * sw, x1 = min(x0 + kw, in.w);
+    if (vw && ox >= vw[n]) {
+      H8 z;
+      z.u = make_uint4(0, 0, 0, 0);
+      st8(out.p + pix * out.pitch + cg * 8, z);
+      continue;
+    }
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = is_max ? -FLT_MAX : 0.f;
@@ -338,13 +358,17 @@ pool_kernel(TV in, TV out, int kh, int kw, int sh, int sw, int is_max) {
 // ---------------------------------------------------------------- SVTR neck
 // one warp per token; C <= 256
 __global__ void __launch_bounds__(kThreads)
-layernorm_kernel(TV in, TV out, const float* __restrict__ gb, float eps) {
+layernorm_kernel(TV in, TV out, const float* __restrict__ gb, float eps, const int* __restrict__ vw) {
   const long rows = long(in.n) * in.h * in.w;
   const int lane = threadIdx.x & 31;
   const long row = (blockIdx.x * long(blockDim.x) + threadIdx.x) >> 5;
   if (row >= rows) return;
   const int c0 = lane * 8;
   const bool have = c0 < in.c;
+  if (vw && int(row % in.w) >= vw[row / (long(in.h) * in.w)]) {
+    if (have) { H8 z; z.u = make_uint4(0, 0, 0, 0); st8(out.p + row * out.pitch + c0, z); }
+    return;
+  }
   float x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (have) ld8(in.p + row * in.pitch + c0).to_float(x);
   float s = 0.f;
@@ -377,15 +401,18 @@ layernorm_kernel(TV in, TV out, const float* __restrict__ gb, float eps) {
 // qkv row layout (Paddle reshape [N,T,3,heads,d]): [which(3)][head][d].  One block per (n, head).
 // smem: K[T][d], V[T][d], P[warps][T]
 __global__ void __launch_bounds__(128)
-attention_kernel(TV qkv, TV out, int heads, int hd, float scale) {
+attention_kernel(TV qkv, TV out, int heads, int hd, float scale, const int* __restrict__ vw) {
   extern __shared__ float sm[];
-  const int T = qkv.h * qkv.w;
+  const int Tfull = qkv.h * qkv.w;
   const int n = blockIdx.x / heads, head = blockIdx.x % heads;
+  const int T = vw ? vw[n] : Tfull;  // valid tokens of this sequence
   float* K = sm;
-  float* V = K + T * hd;
-  float* P = V + T * hd;
-  const __half* base = qkv.p + long(n) * T * qkv.pitch;
+  float* V = K + Tfull * hd;
+  float* P = V + Tfull * hd;
+  const __half* base = qkv.p + long(n) * Tfull * qkv.pitch;
   const int C = heads * hd;
+  for (int i = T * hd + threadIdx.x; i < Tfull * hd; i += blockDim.x)  // queries beyond the valid length -> zeros
+    out.p[(long(n) * Tfull + i / hd) * out.pitch + head * hd + i % hd] = __float2half_rn(0.f);
   for (int i = threadIdx.x; i < T * hd; i += blockDim.x) {
     const int t = i / hd, d = i % hd;
     K[i] = __half2float(base[long(t) * qkv.pitch + C + head * hd + d]);
@@ -424,7 +451,7 @@ attention_kernel(TV qkv, TV out, int heads, int hd, float scale) {
     if (lane < hd)
       for (int j = 0; j < T; ++j) acc = fmaf(p[j], V[j * hd + lane], acc);
     if (lane < hd)
-      out.p[(long(n) * T + tq) * out.pitch + head * hd + lane] = __float2half_rn(acc / sum);
+      out.p[(long(n) * Tfull + tq) * out.pitch + head * hd + lane] = __float2half_rn(acc / sum);
     __syncwarp();
   }
 }
@@ -520,7 +547,7 @@ __global__ void fc_softmax_kernel(const float* __restrict__ partial, int splits,
 // CUDA-core CTC head: 8 tokens per block share each weight row; per token running (max, argmax, sum).
 __global__ void __launch_bounds__(kThreads)
 ctc_head_simt_kernel(TV feat, const __half* __restrict__ w, const float* __restrict__ bias, int cin_pad,
-                     int ncls_pad, int* __restrict__ idx, float* __restrict__ prob) {
+                     int ncls_pad, int* __restrict__ idx, float* __restrict__ prob, const int* __restrict__ vw) {
   constexpr int ROWS = 8;
   extern __shared__ float sm[];  // feat[ROWS][cin_pad]
   const long rows = long(feat.n) * feat.h * feat.w;
@@ -588,8 +615,10 @@ ctc_head_simt_kernel(TV feat, const __half* __restrict__ w, const float* __restr
       if (m2 > m || (m2 == m && a2 < a)) a = a2;
       m = nm;
     }
-    idx[r0 + r] = a;
-    prob[r0 + r] = 1.f / s;
+    const long row = r0 + r;
+    const bool pad = vw && int(row % feat.w) >= vw[row / (long(feat.h) * feat.w)];
+    idx[row] = pad ? 0 : a;  // beyond the valid length: blank, which the CTC collapse skips
+    prob[row] = pad ? 0.f : 1.f / s;
   }
 }
 
@@ -626,23 +655,24 @@ inline int grid_for(long total, int threads = kThreads) {
 }  // namespace
 
 void launch_conv_simt(const TV& in, const TV& out, const __half* w, const float* bias,
-                      const ConvGeom& g, const Epi& e, cudaStream_t s) {
+                      const ConvGeom& g, const Epi& e, cudaStream_t s, const int* vw) {
   const long total = long(out.n) * out.h * out.w * ((out.c + 7) / 8);
-  conv_simt_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, w, bias, g, e);
+  conv_simt_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, w, bias, g, e, vw);
 }
 
 void launch_dwconv(const TV& in, const TV& out, const float* wb, const ConvGeom& g, const Epi& e,
-                   cudaStream_t s) {
+                   cudaStream_t s, const int* vw) {
   const long total = long(out.n) * out.h * out.w * ((out.c + 7) / 8);
   const int grid = grid_for(total);
-  if (g.kh == 3 && g.kw == 3) dwconv_kernel<3, 3><<<grid, kThreads, 0, s>>>(in, out, wb, g, e);
-  else if (g.kh == 5 && g.kw == 5) dwconv_kernel<5, 5><<<grid, kThreads, 0, s>>>(in, out, wb, g, e);
+  if (g.kh == 3 && g.kw == 3) dwconv_kernel<3, 3><<<grid, kThreads, 0, s>>>(in, out, wb, g, e, vw);
+  else if (g.kh == 5 && g.kw == 5) dwconv_kernel<5, 5><<<grid, kThreads, 0, s>>>(in, out, wb, g, e, vw);
   else abort();
 }
 
-int gap_splits(int hw) {
-  int s = (hw + 2047) / 2048;
-  return s < 1 ? 1 : (s > 64 ? 64 : s);
+int gap_splits(int h) {
+  // splits divide the ROWS (see gap_partial_kernel) and depend on the height only, so that a ragged batch
+  // reduces every text line in the same order as a dense batch of its own width would
+  return h < 1 ? 1 : (h > 8 ? 8 : h);
 }
 
 void launch_gap_partial(const TV& in, float* partial, int splits, cudaStream_t s) {
@@ -653,10 +683,10 @@ void launch_gap_partial(const TV& in, float* partial, int splits, cudaStream_t s
 }
 
 void launch_se_fc(const float* partial, int splits, int hw, int n, int c, int cmid, const float* blk,
-                  float slope, float offset, float* gate, cudaStream_t s) {
+                  float slope, float offset, float* gate, cudaStream_t s, const int* vw_in, int h) {
   const int cp = (c + 7) / 8 * 8;
   se_fc_kernel<<<n, kThreads, (cp + cmid) * sizeof(float), s>>>(partial, splits, 1.f / float(hw), c, cmid,
-                                                                 blk, slope, offset, gate);
+                                                                 blk, slope, offset, gate, vw_in, h);
 }
 
 void launch_scale(const TV& in, const float* gate, bool add_x, const TV& out, cudaStream_t s) {
@@ -688,18 +718,19 @@ void launch_add(const TV& a, const TV& b, const TV& out, cudaStream_t s) {
   add_kernel<<<grid_for(total), kThreads, 0, s>>>(a, b, out);
 }
 
-void launch_pool(const TV& in, const TV& out, int kh, int kw, int sh, int sw, bool is_max, cudaStream_t s) {
+void launch_pool(const TV& in, const TV& out, int kh, int kw, int sh, int sw, bool is_max, cudaStream_t s,
+                 const int* vw) {
   const long total = long(out.n) * out.h * out.w * ((out.c + 7) / 8);
-  pool_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, kh, kw, sh, sw, is_max ? 1 : 0);
+  pool_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, kh, kw, sh, sw, is_max ? 1 : 0, vw);
 }
 
-void launch_layernorm(const TV& in, const TV& out, const float* gb, float eps, cudaStream_t s) {
+void launch_layernorm(const TV& in, const TV& out, const float* gb, float eps, cudaStream_t s, const int* vw) {
   const long rows = long(in.n) * in.h * in.w;
   const long blocks = (rows * 32 + kThreads - 1) / kThreads;
-  layernorm_kernel<<<int(blocks), kThreads, 0, s>>>(in, out, gb, eps);
+  layernorm_kernel<<<int(blocks), kThreads, 0, s>>>(in, out, gb, eps, vw);
 }
 
-void launch_attention(const TV& qkv, const TV& out, int heads, int hd, float scale, cudaStream_t s) {
+void launch_attention(const TV& qkv, const TV& out, int heads, int hd, float scale, cudaStream_t s, const int* vw) {
   const int T = qkv.h * qkv.w;
   const size_t smem = (size_t(2) * T * hd + size_t(4) * T) * sizeof(float);
   static size_t configured = 0;
@@ -707,7 +738,7 @@ void launch_attention(const TV& qkv, const TV& out, int heads, int hd, float sca
     cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     configured = smem;
   }
-  attention_kernel<<<qkv.n * heads, 128, smem, s>>>(qkv, out, heads, hd, scale);
+  attention_kernel<<<qkv.n * heads, 128, smem, s>>>(qkv, out, heads, hd, scale, vw);
 }
 
 void launch_dbhead(const TV& in, const float* blk, int cmid, float* prob, uint8_t* bitmap, int thresh_u8,
@@ -724,11 +755,11 @@ void launch_fc_softmax(const float* partial, int splits, int hw, int n, int cin,
 }
 
 void launch_ctc_head_simt(const TV& feat, const __half* w, const float* bias, int cin_pad, int ncls,
-                          int ncls_pad, int* idx, float* prob, cudaStream_t s) {
+                          int ncls_pad, int* idx, float* prob, cudaStream_t s, const int* vw) {
   (void)ncls;
   const long rows = long(feat.n) * feat.h * feat.w;
   ctc_head_simt_kernel<<<int((rows + 7) / 8), kThreads, size_t(8) * cin_pad * sizeof(float), s>>>(
-      feat, w, bias, cin_pad, ncls_pad, idx, prob);
+      feat, w, bias, cin_pad, ncls_pad, idx, prob, vw);
 }
 
 void launch_nchw3_to_input(const float* in, int n, int h, int w, __half* out, cudaStream_t s) {

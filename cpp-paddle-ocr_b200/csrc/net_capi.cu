@@ -80,11 +80,12 @@ int b200ocr_net_plan_dump(b200ocr_net_t h, char* buf, int cap, int* needed) {
   });
 }
 
-int b200ocr_net_forward(b200ocr_net_t h, const float* nchw, int n, int height, int width, int thresh_u8) {
+static int net_forward_impl(b200ocr_net_t h, const float* nchw, int n, int height, int width, int thresh_u8,
+                            const int* widths) {
   return capi_guard([&] {
     if (!h || !nchw) throw std::invalid_argument("null argument");
     Net& net = *h->net;
-    __half* in = net.prepare(n, height, width);
+    __half* in = net.prepare(n, height, width, widths);
     const size_t bytes = size_t(n) * 3 * height * width * sizeof(float);
     if (bytes > h->d_in_bytes) {
       cudaFree(h->d_in);
@@ -97,6 +98,14 @@ int b200ocr_net_forward(b200ocr_net_t h, const float* nchw, int n, int height, i
     net.run(h->stream, thresh_u8);
     cuda_check(cudaStreamSynchronize(h->stream), "forward");
   });
+}
+
+int b200ocr_net_forward(b200ocr_net_t h, const float* nchw, int n, int height, int width, int thresh_u8) {
+  return net_forward_impl(h, nchw, n, height, width, thresh_u8, nullptr);
+}
+int b200ocr_net_forward_ragged(b200ocr_net_t h, const float* nchw, int n, int height, int width, const int* widths) {
+  if (!widths) { b200ocr::set_last_error("null widths"); return 1; }
+  return net_forward_impl(h, nchw, n, height, width, -1, widths);
 }
 
 int b200ocr_net_out_shape(b200ocr_net_t h, int shape[3]) {

@@ -502,7 +502,7 @@ int b200ocr_crop_preprocess(int device, const b200ocr_image* crops, int n, int k
     for (int i = 0; i < n; ++i) {
       const float ratio = float(dev[i].cols) / float(dev[i].rows);
       int rw = std::ceil(float(img_h) * ratio) > float(img_w) ? img_w : int(std::ceil(float(img_h) * ratio));
-      items[i] = CropItem{dev[i].p, dev[i].stride, 0, 0, dev[i].cols, dev[i].rows, rw};
+      items[i] = CropItem{dev[i].p, dev[i].stride, 0, 0, dev[i].cols, dev[i].rows, rw, img_w};
     }
     DevBuf di, in, out;
     di.ensure(sizeof(CropItem) * n);

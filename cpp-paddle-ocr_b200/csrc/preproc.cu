@@ -131,7 +131,8 @@ crop_preprocess_kernel(const CropItem* __restrict__ items, int n, int dh, int dw
     const int dy = r / dw, dx = r - dy * dw;
     const CropItem it = items[b];
     if (dx >= it.resize_w) {
-      store_px(out, t, pad_value, pad_value, pad_value);
+      const float v = dx < it.pad_w ? pad_value : 0.f;  // beyond this row's own batch width: ragged filler
+      store_px(out, t, v, v, v);
       continue;
     }
     Src s{it.img + long(it.y) * it.stride + long(it.x) * 3, it.w, it.h, it.stride};

@@ -251,7 +251,7 @@ void ClsStage::run(const std::vector<DevImg>& imgs, const std::vector<Roi>& rois
     for (int k = 0; k < nb; ++k) {
       const Roi& r = rois[b0 + k];
       const DevImg& im = imgs[r.img];
-      h_items_.as<CropItem>()[k] = CropItem{im.p, im.stride, r.x, r.y, r.w, r.h, resize_width(48, 192, r.w, r.h)};
+      h_items_.as<CropItem>()[k] = CropItem{im.p, im.stride, r.x, r.y, r.w, r.h, resize_width(48, 192, r.w, r.h), 192};
     }
     __half* in = net_.prepare(nb, 48, 192);
     cuda_check(cudaMemcpyAsync(items_.p, h_items_.p, sizeof(CropItem) * nb, cudaMemcpyHostToDevice, s), "cls items");
@@ -340,8 +340,8 @@ void RecStage::run(const std::vector<DevImg>& imgs, const std::vector<std::vecto
   auto t0 = Clock::now();
   texts->assign(calls.size(), {});
   scores->assign(calls.size(), {});
-  struct Row { int call, roi; CropItem item; };
-  std::map<int, std::vector<Row>> by_width;  // padded batch width -> rows
+  struct Row { int call, roi, width; CropItem item; };
+  std::vector<Row> rows;
   for (size_t c = 0; c < calls.size(); ++c) {
     const std::vector<Roi>& rois = calls[c];
     const size_t m = rois.size();
@@ -362,64 +362,90 @@ void RecStage::run(const std::vector<DevImg>& imgs, const std::vector<std::vecto
       }
       const int img_w = int(float(img_h_) * max_wh_ratio);  // CrnnResizeImg: imgW = int(imgH * wh_ratio)
       const int batch_width = std::max(img_w_, img_w);
+      // a batch narrower than rec_img_w would be padded by PermuteBatch's zero-filled tensor with 0.0 instead of
+      // -1.0; int(imgH * (imgW/imgH)) equals imgW for the shipped settings, so that case is rejected, not emulated
+      if (img_w < batch_width) throw std::runtime_error("rec_img_w/rec_img_h combination pads with two different values");
       for (size_t k = beg; k < end; ++k) {
         const Roi& r = rois[order[k]];
         const DevImg& im = imgs[r.img];
         Row row;
-        row.call = int(c); row.roi = int(order[k]);
-        row.item = CropItem{im.p, im.stride, r.x, r.y, r.w, r.h, resize_width(img_h_, img_w, r.w, r.h)};
-        // a batch narrower than rec_img_w is padded by PermuteBatch's zero-filled tensor: value 0.0, not -1.0;
-        // int(imgH * (imgW/imgH)) equals imgW for the shipped settings, so that case is rejected, not emulated
-        if (img_w < batch_width) throw std::runtime_error("rec_img_w/rec_img_h combination pads with two different values");
-        by_width[batch_width].push_back(row);
+        row.call = int(c); row.roi = int(order[k]); row.width = batch_width;
+        row.item = CropItem{im.p, im.stride, r.x, r.y, r.w, r.h, resize_width(img_h_, img_w, r.w, r.h), batch_width};
+        rows.push_back(row);
       }
     }
+  }
+  // Rows of every reference batch keep the padded width of THEIR batch; rows of different widths share one launch
+  // as a ragged batch (Net::prepare with per-row widths), which leaves every row's values unchanged.  Sorting by
+  // width and cutting chunks where padding would exceed ~25% bounds the wasted columns.
+  std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.width < b.width; });
+  struct Chunk { size_t b0; int nb, wmax, T; size_t off; };
+  std::vector<Chunk> chunks;
+  size_t total_ids = 0;
+  for (size_t b0 = 0; b0 < rows.size();) {
+    size_t e = b0;
+    long sum_w = 0;
+    while (e < rows.size() && int(e - b0) < max_rows) {
+      const long w_new = rows[e].width;
+      if (e > b0 && (sum_w + w_new) * 4 < 3 * long(e - b0 + 1) * w_new) break;  // fill ratio would drop below 75 %
+      if (e > b0 && long(e - b0 + 1) * w_new > max_cols) break;
+      sum_w += w_new;
+      ++e;
+    }
+    Chunk ch;
+    ch.b0 = b0; ch.nb = int(e - b0); ch.wmax = rows[e - 1].width; ch.T = 0; ch.off = 0;
+    chunks.push_back(ch);
+    b0 = e;
   }
   t[0] += ms_since(t0);
-  for (auto& g : by_width) {
-    const int W = g.first;
-    std::vector<Row>& rows = g.second;
-    for (size_t b0 = 0; b0 < rows.size(); b0 += size_t(max_rows)) {
-      t0 = Clock::now();
-      const int nb = int(std::min(rows.size() - b0, size_t(max_rows)));
-      h_items_.ensure(sizeof(CropItem) * nb);
-      items_.ensure(sizeof(CropItem) * nb);
-      for (int k = 0; k < nb; ++k) h_items_.as<CropItem>()[k] = rows[b0 + k].item;
-      __half* in = net_.prepare(nb, img_h_, W);
-      cuda_check(cudaMemcpyAsync(items_.p, h_items_.p, sizeof(CropItem) * nb, cudaMemcpyHostToDevice, s), "rec items");
-      // pad value -1.0: CrnnResizeImg pads with u8 zeros BEFORE normalisation (src/preprocess_op.cpp:115-117)
-      launch_crop_preprocess(items_.as<CropItem>(), nb, img_h_, W, make_norm(kMean05, kScale2), -1.f, in, s);
-      t[0] += ms_since(t0);
-      t0 = Clock::now();
-      net_.run(s);
-      const int T = net_.out_shape().w;
-      cidx_.ensure(sizeof(int) * size_t(nb) * T);
-      clen_.ensure(sizeof(int) * nb);
-      cscore_.ensure(sizeof(float) * nb);
-      launch_ctc_collapse(net_.out_idx(), net_.out_f32(), nb, T, cidx_.as<int>(), clen_.as<int>(), cscore_.as<float>(), s);
-      launches += net_.launches_per_run() + 2;
-      h_cidx_.ensure(sizeof(int) * size_t(nb) * T);
-      h_clen_.ensure(sizeof(int) * nb);
-      h_cscore_.ensure(sizeof(float) * nb);
-      cuda_check(cudaMemcpyAsync(h_cidx_.p, cidx_.p, sizeof(int) * size_t(nb) * T, cudaMemcpyDeviceToHost, s), "rec ids");
-      cuda_check(cudaMemcpyAsync(h_clen_.p, clen_.p, sizeof(int) * nb, cudaMemcpyDeviceToHost, s), "rec len");
-      cuda_check(cudaMemcpyAsync(h_cscore_.p, cscore_.p, sizeof(float) * nb, cudaMemcpyDeviceToHost, s), "rec score");
-      cuda_check(cudaStreamSynchronize(s), "rec");
-      t[1] += ms_since(t0);
-      t0 = Clock::now();
-      for (int k = 0; k < nb; ++k) {
-        const int len = h_clen_.as<int>()[k];
-        if (len == 0) continue;  // score is NaN in the reference -> the caller's "" / 0 stay (src/ocr_rec.cpp:122-125)
-        std::string str;
-        const int* ids = h_cidx_.as<int>() + size_t(k) * T;
-        for (int j = 0; j < len; ++j) str += label_list_[ids[j]];
-        const Row& r = rows[b0 + k];
-        (*texts)[r.call][r.roi] = std::move(str);
-        (*scores)[r.call][r.roi] = h_cscore_.as<float>()[k];
-      }
-      t[2] += ms_since(t0);
-    }
+  t0 = Clock::now();
+  h_items_.ensure(sizeof(CropItem) * std::max<size_t>(rows.size(), 1));
+  items_.ensure(sizeof(CropItem) * std::max<size_t>(rows.size(), 1));
+  for (size_t k = 0; k < rows.size(); ++k) h_items_.as<CropItem>()[k] = rows[k].item;
+  if (!rows.empty())
+    cuda_check(cudaMemcpyAsync(items_.p, h_items_.p, sizeof(CropItem) * rows.size(), cudaMemcpyHostToDevice, s), "rec items");
+  // worst-case output size: T <= wmax / 8 + 1
+  for (Chunk& ch : chunks) { ch.off = total_ids; total_ids += size_t(ch.nb) * (ch.wmax / 8 + 2); }
+  cidx_.ensure(sizeof(int) * std::max<size_t>(total_ids, 1));
+  clen_.ensure(sizeof(int) * std::max<size_t>(rows.size(), 1));
+  cscore_.ensure(sizeof(float) * std::max<size_t>(rows.size(), 1));
+  h_cidx_.ensure(sizeof(int) * std::max<size_t>(total_ids, 1));
+  h_clen_.ensure(sizeof(int) * std::max<size_t>(rows.size(), 1));
+  h_cscore_.ensure(sizeof(float) * std::max<size_t>(rows.size(), 1));
+  std::vector<int> widths;
+  for (Chunk& ch : chunks) {
+    widths.resize(ch.nb);
+    for (int k = 0; k < ch.nb; ++k) widths[k] = rows[ch.b0 + k].width;
+    __half* in = net_.prepare(ch.nb, img_h_, ch.wmax, widths.data());
+    // pad value -1.0: CrnnResizeImg pads with u8 zeros BEFORE normalisation (src/preprocess_op.cpp:115-117)
+    launch_crop_preprocess(items_.as<CropItem>() + ch.b0, ch.nb, img_h_, ch.wmax, make_norm(kMean05, kScale2), -1.f, in, s);
+    net_.run(s);
+    ch.T = net_.out_shape().w;
+    if (size_t(ch.nb) * ch.T > size_t(ch.nb) * (ch.wmax / 8 + 2)) throw std::runtime_error("rec: unexpected sequence length");
+    launch_ctc_collapse(net_.out_idx(), net_.out_f32(), ch.nb, ch.T, cidx_.as<int>() + ch.off, clen_.as<int>() + ch.b0,
+                        cscore_.as<float>() + ch.b0, s);
+    launches += net_.launches_per_run() + 2;
   }
+  if (!rows.empty()) {
+    cuda_check(cudaMemcpyAsync(h_cidx_.p, cidx_.p, sizeof(int) * total_ids, cudaMemcpyDeviceToHost, s), "rec ids");
+    cuda_check(cudaMemcpyAsync(h_clen_.p, clen_.p, sizeof(int) * rows.size(), cudaMemcpyDeviceToHost, s), "rec len");
+    cuda_check(cudaMemcpyAsync(h_cscore_.p, cscore_.p, sizeof(float) * rows.size(), cudaMemcpyDeviceToHost, s), "rec score");
+    cuda_check(cudaStreamSynchronize(s), "rec");
+  }
+  t[1] += ms_since(t0);
+  t0 = Clock::now();
+  for (const Chunk& ch : chunks)
+    for (int k = 0; k < ch.nb; ++k) {
+      const int len = h_clen_.as<int>()[ch.b0 + k];
+      if (len == 0) continue;  // score is NaN in the reference -> the caller's "" / 0 stay (src/ocr_rec.cpp:122-125)
+      std::string str;
+      const int* ids = h_cidx_.as<int>() + ch.off + size_t(k) * ch.T;
+      for (int j = 0; j < len; ++j) str += label_list_[ids[j]];
+      const Row& r = rows[ch.b0 + k];
+      (*texts)[r.call][r.roi] = std::move(str);
+      (*scores)[r.call][r.roi] = h_cscore_.as<float>()[ch.b0 + k];
+    }
+  t[2] += ms_since(t0);
   if (times) times->insert(times->end(), t, t + 3);
 }
 

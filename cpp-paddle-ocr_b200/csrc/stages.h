@@ -121,7 +121,8 @@ class RecStage {
            std::vector<double>* times = nullptr);
   const std::vector<std::string>& labels() const { return label_list_; }
   Net& net() { return net_; }
-  int max_rows = 1024;  // rows per forward pass
+  int max_rows = 1024;       // rows per forward pass
+  long max_cols = 400000;    // rows x padded width per forward pass (bounds the activation arena)
   long launches = 0;
  private:
   Net net_;

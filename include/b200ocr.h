@@ -195,6 +195,9 @@ int b200ocr_net_plan_dump(b200ocr_net_t net, char* buf, int cap, int* needed);
 /* Forward pass on a host fp32 NCHW tensor [n,3,height,width] (already normalised).
  * det: thresh_u8 >= 0 additionally produces the bitmap `(uchar)(p*255) > thresh_u8` (src/ocr_det.cpp:143-154). */
 int b200ocr_net_forward(b200ocr_net_t net, const float* nchw, int n, int height, int width, int thresh_u8);
+/* Ragged batch (sequence graphs): row i is widths[i] <= width columns wide and must be zero beyond that; every row's
+ * result is bit-identical to running it in a dense batch of its own width (tests/test_net_parity_gpu.py). */
+int b200ocr_net_forward_ragged(b200ocr_net_t net, const float* nchw, int n, int height, int width, const int* widths);
 /* det: (n, H, W)   cls: (n, 1, 1)   rec: (n, 1, T) */
 int b200ocr_net_out_shape(b200ocr_net_t net, int shape[3]);
 /* det: out_f32 = probability map [n,H,W], out_bitmap = [n,H,W] (0/255)

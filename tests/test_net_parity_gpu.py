@@ -115,3 +115,30 @@ def test_graph_replay_and_buffer_reuse_equal_eager(models_dir, kind):
         if u is not None:
             assert np.array_equal(u, v)
     assert b.launches > 0
+
+
+@pytest.mark.parametrize("simt", [True, False], ids=["cuda-core", "tcgen05"])
+@pytest.mark.parametrize("h", [28, 48])
+def test_ragged_rec_batch_is_bit_identical_to_dense_batches(models_dir, h, simt):
+    """Rows of different padded widths share one launch (Net::prepare with per-row widths); every row must come out
+    exactly as in a dense batch of its own width -- that is what lets the recognizer merge the reference's
+    per-image batches without changing a single value."""
+    import b200ocr
+    rng = np.random.default_rng(7)
+    widths = [192, 200, 231, 320, 323, 408, 200, 514]
+    wmax = max(widths)
+    rows = [rng.standard_normal((3, h, w)).astype(np.float32) for w in widths]
+    x = np.zeros((len(widths), 3, h, wmax), np.float32)
+    for i, r in enumerate(rows):
+        x[i, :, :, :widths[i]] = r
+    flags = b200ocr.NET_NO_GRAPH | (b200ocr.NET_FORCE_SIMT if simt else 0)
+    net = b200ocr.Net(f"{models_dir}/rec", 0, flags)
+    prob_r, idx_r = net.forward(x, widths=widths)
+    for w in sorted(set(widths)):
+        sel = [i for i, v in enumerate(widths) if v == w]
+        prob_d, idx_d = net.forward(np.stack([rows[i] for i in sel]))
+        T = prob_d.shape[1]
+        for k, i in enumerate(sel):
+            assert np.array_equal(idx_r[i, :T], idx_d[k]), (w, i)
+            assert np.array_equal(prob_r[i, :T], prob_d[k]), (w, i)
+            assert not idx_r[i, T:].any() and not prob_r[i, T:].any()   # beyond a row's length: blanks

@@ -81,7 +81,7 @@ def prob_map(seed: int, height=320, width=512, n_boxes=12, rings=2, lines=2):
     rng = np.random.default_rng(seed)
     p = np.zeros((height, width), np.float32)
     cols = max(1, width // 150)
-    rows = max(1, -(-n_boxes // cols))
+    rows = max(1, min(-(-n_boxes // cols), height // 20))
     ch, cw = height / rows, width / cols
     k = 0
     for r in range(rows):
