@@ -80,7 +80,7 @@ void launch_ctc_head_simt(const TV& feat, const __half* w, const float* bias, in
                           int ncls_pad, int* idx, float* prob, cudaStream_t s, const int* vw = nullptr);
 bool ctc_tc_eligible(const TV& feat, int cin_pad);
 void launch_ctc_head_tc(const TV& feat, const __half* w, const float* bias, int cin_pad, int ncls,
-                        int ncls_pad, int* idx, float* prob, cudaStream_t s);
+                        int ncls_pad, int* idx, float* prob, cudaStream_t s, const int* vw = nullptr);
 
 // ---- pre-processing (preproc.cu) ---------------------------------------------------
 struct NormParams { float scale[3], shift[3]; };  // y = (u8 * (1/255.f)) * scale + shift, per BGR channel
