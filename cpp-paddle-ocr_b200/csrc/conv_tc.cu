@@ -351,6 +351,9 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
   while (a.tmem_cols < a.bn) a.tmem_cols <<= 1;
   const int k_iters = g.kh * g.kw * ((in.c + 63) / 64);
   a.stages = k_iters < kStagesMax ? k_iters : kStagesMax;
+  // Two CTAs per SM (one loads / multiplies while the other drains its accumulator) beat one CTA with a deep
+  // ring: keep the ring at what fits twice into shared memory (and twice 256 TMEM columns always fit).
+  while (a.stages > 2 && size_t(a.stages) * (kATileBytes + a.bn * 128) + 1024 + 128 > 110 * 1024) --a.stages;
   a.cout = out.c;
   a.out = out.p;
   a.out_pitch = out.pitch;

@@ -161,18 +161,34 @@ ctc_head_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tmem_ld16(trow + col, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const float4* bp = reinterpret_cast<const float4*>(a.bias + cbase + col);
+        float f[16];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const float4 b = __ldg(bp + g);
-          const float f[4] = {__uint_as_float(v[4 * g]) + b.x, __uint_as_float(v[4 * g + 1]) + b.y,
-                              __uint_as_float(v[4 * g + 2]) + b.z, __uint_as_float(v[4 * g + 3]) + b.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float x = f[i];
-            if (x > mx) { sum = sum * __expf(mx - x) + 1.f; mx = x; am = cbase + col + 4 * g + i; }
-            else sum += __expf(x - mx);
-          }
+          f[4 * g] = __uint_as_float(v[4 * g]) + b.x;
+          f[4 * g + 1] = __uint_as_float(v[4 * g + 1]) + b.y;
+          f[4 * g + 2] = __uint_as_float(v[4 * g + 2]) + b.z;
+          f[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + b.w;
         }
+        // group maximum first (no transcendental), one rescale when the running maximum moves (rare), then 16
+        // independent exponentials
+        float m16 = f[0];
+#pragma unroll
+        for (int i = 1; i < 16; ++i) m16 = fmaxf(m16, f[i]);
+        if (m16 > mx) {
+          sum *= __expf(mx - m16);
+          mx = m16;
+          int first = 15;
+#pragma unroll
+          for (int i = 14; i >= 0; --i) first = (f[i] == m16) ? i : first;  // first maximum wins (Utility::argmax)
+          am = cbase + col + first;
+        }
+        float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          e0 += __expf(f[i] - mx); e1 += __expf(f[i + 1] - mx); e2 += __expf(f[i + 2] - mx); e3 += __expf(f[i + 3] - mx);
+        }
+        sum += (e0 + e1) + (e2 + e3);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&t_empty[buf]);

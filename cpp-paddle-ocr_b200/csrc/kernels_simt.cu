@@ -152,6 +152,117 @@ dwconv_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi e, co
   }
 }
 
+// Depthwise conv, register-blocked along x: one thread owns S consecutive output pixels of one 8-channel group.
+// Per filter row it loads the KW weight vectors once and every input column once (a (S-1)*SW+KW wide window),
+// instead of KH*KW input + weight loads per output pixel.
+template <int KH, int KW, int SW, int S>
+__global__ void __launch_bounds__(kThreads)
+dwconv_strip_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi e, const int* __restrict__ vw) {
+  const int cgs = (out.c + 7) >> 3;
+  const int cp = g.cout_pad;
+  const int strips = (out.w + S - 1) / S;
+  const long total = long(out.n) * out.h * strips * cgs;
+  const float* bias = wb + long(KH * KW) * cp;
+  constexpr int WIN = (S - 1) * SW + KW;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const int cg = int(t % cgs);
+    long r = t / cgs;
+    const int sx = int(r % strips); r /= strips;
+    const int oy = int(r % out.h);
+    const int n = int(r / out.h);
+    const int ox0 = sx * S;
+    float acc[S][8];
+#pragma unroll
+    for (int s_ = 0; s_ < S; ++s_)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[s_][i] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < KH; ++ky) {
+      const int iy = oy * g.sh - g.ph + ky;
+      if (iy < 0 || iy >= in.h) continue;
+      float w[KW][8];
+#pragma unroll
+      for (int kx = 0; kx < KW; ++kx) {
+        const float4* wp = reinterpret_cast<const float4*>(wb + long(ky * KW + kx) * cp + cg * 8);
+        const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+        w[kx][0] = w0.x; w[kx][1] = w0.y; w[kx][2] = w0.z; w[kx][3] = w0.w;
+        w[kx][4] = w1.x; w[kx][5] = w1.y; w[kx][6] = w1.z; w[kx][7] = w1.w;
+      }
+      const __half* row = in.p + (long(n) * in.h + iy) * in.w * in.pitch + cg * 8;
+      const int ix0 = ox0 * SW - g.pw;
+#pragma unroll
+      for (int j = 0; j < WIN; ++j) {
+        const int ix = ix0 + j;
+        if (ix < 0 || ix >= in.w) continue;
+        float x[8];
+        ld8(row + long(ix) * in.pitch).to_float(x);
+#pragma unroll
+        for (int s_ = 0; s_ < S; ++s_) {
+          const int kx = j - s_ * SW;  // compile-time after unrolling
+          if (kx >= 0 && kx < KW) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[s_][i] = fmaf(x[i], w[kx][i], acc[s_][i]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int s_ = 0; s_ < S; ++s_) {
+      const int ox = ox0 + s_;
+      if (ox >= out.w) break;
+      const long pix = (long(n) * out.h + oy) * out.w + ox;
+      epilogue8(acc[s_], bias, cg * 8, out.c, e, out, pix, vw && ox >= vw[n]);
+    }
+  }
+}
+
+// First layer: 3 input channels (pitch 8), 3x3, any stride; all COUT channels of one output pixel per thread,
+// filter in shared memory as fp32 [tap][ci][co].
+template <int COUT>
+__global__ void __launch_bounds__(kThreads)
+stem_conv_kernel(TV in, TV out, const __half* __restrict__ w, const float* __restrict__ bias, ConvGeom g, Epi e,
+                 const int* __restrict__ vw) {
+  __shared__ float sw[9 * 3 * COUT];
+  __shared__ float sb[COUT];
+  for (int i = threadIdx.x; i < 9 * 3 * COUT; i += blockDim.x) {
+    const int co = i % COUT, ci = (i / COUT) % 3, tap = i / (3 * COUT);
+    sw[i] = __half2float(w[(long(co) * 9 + tap) * g.cin_pad + ci]);
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
+  __syncthreads();
+  const long npix = long(out.n) * out.h * out.w;
+  for (long pix = blockIdx.x * long(blockDim.x) + threadIdx.x; pix < npix; pix += long(gridDim.x) * blockDim.x) {
+    const int ox = int(pix % out.w);
+    const int oy = int((pix / out.w) % out.h);
+    const int n = int(pix / (long(out.w) * out.h));
+    float acc[COUT];
+#pragma unroll
+    for (int i = 0; i < COUT; ++i) acc[i] = 0.f;
+    const bool masked = vw && ox >= vw[n];
+    if (!masked) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * g.sh - g.ph + ky;
+        if (iy < 0 || iy >= in.h) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = ox * g.sw - g.pw + kx;
+          if (ix < 0 || ix >= in.w) continue;
+          const uint2 raw = *reinterpret_cast<const uint2*>(in.p + ((long(n) * in.h + iy) * in.w + ix) * in.pitch);
+          const float2 ab = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+          const float c = __half2float(*reinterpret_cast<const __half*>(&raw.y));
+          const float* wp = sw + (ky * 3 + kx) * 3 * COUT;
+#pragma unroll
+          for (int co = 0; co < COUT; ++co)
+            acc[co] = fmaf(ab.x, wp[co], fmaf(ab.y, wp[COUT + co], fmaf(c, wp[2 * COUT + co], acc[co])));
+        }
+      }
+    }
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += 8) epilogue8(acc + c0, sb, c0, out.c, e, out, pix, masked);
+  }
+}
+
 // ---------------------------------------------------------------- SE block
 // partial[n][split][cp] = sum over the split's pixels (fp32, fixed order -> deterministic)
 __global__ void __launch_bounds__(kThreads)
@@ -656,12 +767,30 @@ inline int grid_for(long total, int threads = kThreads) {
 
 void launch_conv_simt(const TV& in, const TV& out, const __half* w, const float* bias,
                       const ConvGeom& g, const Epi& e, cudaStream_t s, const int* vw) {
+  if (in.c == 3 && in.pitch == 8 && g.kh == 3 && g.kw == 3 && e.res == nullptr && (out.c == 8 || out.c == 16)) {
+    const int grid = grid_for(long(out.n) * out.h * out.w);
+    if (out.c == 16) stem_conv_kernel<16><<<grid, kThreads, 0, s>>>(in, out, w, bias, g, e, vw);
+    else stem_conv_kernel<8><<<grid, kThreads, 0, s>>>(in, out, w, bias, g, e, vw);
+    return;
+  }
   const long total = long(out.n) * out.h * out.w * ((out.c + 7) / 8);
   conv_simt_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, w, bias, g, e, vw);
 }
 
 void launch_dwconv(const TV& in, const TV& out, const float* wb, const ConvGeom& g, const Epi& e,
                    cudaStream_t s, const int* vw) {
+  {
+    // register-blocked strips along x whenever the row is long enough to fill them
+    constexpr int S = 4;
+    const long st = long(out.n) * out.h * ((out.w + S - 1) / S) * ((out.c + 7) / 8);
+    const int sg = grid_for(st);
+    if (out.w >= 2 * S && e.res == nullptr) {
+      if (g.kh == 3 && g.kw == 3 && g.sw == 1) { dwconv_strip_kernel<3, 3, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
+      if (g.kh == 3 && g.kw == 3 && g.sw == 2) { dwconv_strip_kernel<3, 3, 2, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
+      if (g.kh == 5 && g.kw == 5 && g.sw == 1) { dwconv_strip_kernel<5, 5, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
+      if (g.kh == 5 && g.kw == 5 && g.sw == 2) { dwconv_strip_kernel<5, 5, 2, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
+    }
+  }
   const long total = long(out.n) * out.h * out.w * ((out.c + 7) / 8);
   const int grid = grid_for(total);
   if (g.kh == 3 && g.kw == 3) dwconv_kernel<3, 3><<<grid, kThreads, 0, s>>>(in, out, wb, g, e, vw);
