@@ -77,6 +77,47 @@ ccl_merge_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int n, int
   }
 }
 
+// Run-based variant for w % 32 == 0 (every detection map: its sides are multiples of 32): a warp owns 32
+// consecutive pixels of one row, a ballot finds the horizontal runs, and every pixel starts out pointing at the first
+// pixel of its run inside the warp's segment -- no atomics.  Unions are then only issued where runs meet: at segment
+// boundaries, at the first pixel of every vertical overlap with a run of the row above, and for the two diagonal
+// contacts of the 8-connected foreground that are not already implied by a horizontal or vertical contact.
+__global__ void __launch_bounds__(256)
+ccl_runs_init_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int* __restrict__ aux, long total) {
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned mask = __ballot_sync(0xffffffffu, bm[t] != 0);
+    const unsigned diff = (mask ^ (mask << 1)) | 1u;       // bit i: pixel i starts a run inside this segment
+    const unsigned upto = diff & (0xffffffffu >> (31 - lane));
+    const int start = 31 - __clz(upto);
+    L[t] = int(t - lane + start);
+    aux[t] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ccl_runs_merge_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int n, int h, int w) {
+  const long per = long(h) * w, total = per * n;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const int r = int(t % per);
+    const int y = r / w, x = r - y * w;
+    const bool fg = bm[t] != 0;
+    const bool left_same = x > 0 && (bm[t - 1] != 0) == fg;
+    if ((x & 31) == 0 && left_same) uf_union(L, int(t), int(t - 1));  // runs continue across the segment boundary
+    if (y == 0) continue;
+    const bool up_same = (bm[t - w] != 0) == fg;
+    if (up_same) {
+      // first pixel of this overlap: the pair (left, up-left) does not already carry the same contact
+      const bool carried = left_same && (bm[t - w - 1] != 0) == fg;
+      if (!carried) uf_union(L, int(t), int(t - w));
+    } else if (fg) {
+      // 8-connectivity: diagonal contacts that no horizontal / vertical contact implies
+      if (x > 0 && bm[t - w - 1] != 0 && bm[t - 1] == 0) uf_union(L, int(t), int(t - w - 1));
+      if (x + 1 < w && bm[t - w + 1] != 0 && bm[t + 1] == 0) uf_union(L, int(t), int(t - w + 1));
+    }
+  }
+}
+
 // flatten + flag background components that touch the image frame (they are the "outside")
 __global__ void __launch_bounds__(256)
 ccl_flatten_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int* __restrict__ touch, int n, int h, int w) {
@@ -420,9 +461,11 @@ void launch_dbpost(const DbPostParams& p, const float* prob, const uint8_t* bitm
   s.y1 = reinterpret_cast<int*>(ws + 6 * al(px * 4));
   int* list = reinterpret_cast<int*>(ws + 7 * al(px * 4));
   const int g = grid_for(long(px));
-  ccl_init_kernel<<<g, 256, 0, st>>>(L, touch, long(px));
+  if (p.w % 32 == 0) ccl_runs_init_kernel<<<g, 256, 0, st>>>(bitmap, L, touch, long(px));
+  else ccl_init_kernel<<<g, 256, 0, st>>>(L, touch, long(px));
   slot_init_kernel<<<g, 256, 0, st>>>(s, long(px));
-  ccl_merge_kernel<<<g, 256, 0, st>>>(bitmap, L, p.n, p.h, p.w);
+  if (p.w % 32 == 0) ccl_runs_merge_kernel<<<g, 256, 0, st>>>(bitmap, L, p.n, p.h, p.w);
+  else ccl_merge_kernel<<<g, 256, 0, st>>>(bitmap, L, p.n, p.h, p.w);
   ccl_flatten_kernel<<<g, 256, 0, st>>>(bitmap, L, touch, p.n, p.h, p.w);
   mark_kernel<<<g, 256, 0, st>>>(bitmap, L, touch, s, p.n, p.h, p.w);
   list_kernel<<<p.n, 1024, 0, st>>>(s.flag, p.h, p.w, p.max_candidates, counts_dev, list);
