@@ -88,15 +88,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
-__device__ __forceinline__ float act_fn(float v, int act, float a, float b) {
-  switch (act) {
-    case 1: return fmaxf(v, 0.f);
-    case 2: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
-    case 3: return v / (1.f + __expf(-v));
-    case 4: return fminf(fmaxf(v * a + b, 0.f), 1.f);
-    case 5: return 1.f / (1.f + __expf(-v));
-    default: return v;
-  }
+template <int ACT>
+__device__ __forceinline__ float act_fn(float v, float a, float b) {
+  if (ACT == 1) return fmaxf(v, 0.f);
+  if (ACT == 2) return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  if (ACT == 3) return v / (1.f + __expf(-v));
+  if (ACT == 4) return fminf(fmaxf(v * a + b, 0.f), 1.f);
+  if (ACT == 5) return 1.f / (1.f + __expf(-v));
+  return v;
 }
 
 struct ConvTcArgs {
@@ -119,6 +118,7 @@ struct ConvTcArgs {
   int mask_w, mask_hw;
 };
 
+template <int ACT>
 __global__ void __launch_bounds__(192)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcArgs a) {
@@ -222,10 +222,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int c0 = nblk * a.bn + col;
       if (!valid || c0 >= c8lim) continue;
       float f[16];
+      {
+        const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);  // bias is padded to a multiple of 16
 #pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + a.bias[c0 + i];
+        for (int g = 0; g < 4; ++g) {
+          const float4 b = __ldg(bp + g);
+          f[4 * g] = __uint_as_float(v[4 * g]) + b.x;
+          f[4 * g + 1] = __uint_as_float(v[4 * g + 1]) + b.y;
+          f[4 * g + 2] = __uint_as_float(v[4 * g + 2]) + b.z;
+          f[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + b.w;
+        }
+      }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] = a.epi.s2 * act_fn(f[i], a.epi.act, a.epi.a, a.epi.b) + a.epi.t2;
+      for (int i = 0; i < 16; ++i) f[i] = a.epi.s2 * act_fn<ACT>(f[i], a.epi.a, a.epi.b) + a.epi.t2;
       const bool second = c0 + 8 < c8lim;
       if (a.epi.res) {
         const __half* rp = a.epi.res + pix * a.epi.res_pitch + c0;
@@ -240,9 +249,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 4; ++i) { float2 p = __half22float2(g[i]); f[8 + 2 * i] += p.x; f[8 + 2 * i + 1] += p.y; }
         }
       }
+      if (masked) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (c0 + i >= a.cout || masked) f[i] = 0.f;
+        for (int i = 0; i < 16; ++i) f[i] = 0.f;
+      } else if (c0 + 16 > a.cout) {  // only the last channel group of a layer can be partial
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i >= a.cout) f[i] = 0.f;
+      }
       __half* op = a.out + pix * a.out_pitch + c0;
       uint4 o0, o1;
       __half2* h0 = reinterpret_cast<__half2*>(&o0);
@@ -377,7 +391,12 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
   impl->grid = dim3(unsigned(a.tiles_x * a.tiles_y * tiles_n), unsigned(n_tiles));
   impl->smem = size_t(a.stages) * (kATileBytes + a.bn * 128) + 1024 + 128;
   // per device (function attributes live in the context): cheap, done once per (layer, shape)
-  cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(conv_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   ConvTcPlan p;
   p.impl = impl;
   return p;
@@ -393,7 +412,14 @@ void launch_conv_tc(const ConvTcPlan& p, const float* bias, const Epi& e, cudaSt
   a.bias = bias;
   a.epi = e;
   a.vw = vw;
-  conv_tc_kernel<<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a);
+  switch (e.act) {
+    case 1: conv_tc_kernel<1><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
+    case 2: conv_tc_kernel<2><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
+    case 3: conv_tc_kernel<3><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
+    case 4: conv_tc_kernel<4><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
+    case 5: conv_tc_kernel<5><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
+    default: conv_tc_kernel<0><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
+  }
 }
 
 }  // namespace b200ocr

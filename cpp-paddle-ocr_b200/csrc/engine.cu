@@ -54,7 +54,7 @@ Net::~Net() {
   cudaFree(d_wf_);
   cudaFree(arena_);
   cudaFree(vw_dev_);
-  if (vw_pin_) cudaFreeHost(vw_pin_);
+  free(vw_pin_);
 }
 
 namespace {
@@ -233,10 +233,13 @@ __half* Net::prepare(int n, int h, int w, const int* widths) {
       if (need > vw_cap_) {
         cuda_check(cudaDeviceSynchronize(), "sync before table growth");
         cudaFree(vw_dev_);
-        if (vw_pin_) cudaFreeHost(vw_pin_);
+        free(vw_pin_);
         vw_cap_ = need + need / 2;
         cuda_check(cudaMalloc(&vw_dev_, vw_cap_ * sizeof(int)), "cudaMalloc width table");
-        cuda_check(cudaMallocHost(&vw_pin_, vw_cap_ * sizeof(int)), "cudaMallocHost width table");
+        // PAGEABLE on purpose: cudaMemcpyAsync from pageable memory snapshots the source before it returns, so the
+        // next prepare() may overwrite this table while earlier launches are still queued
+        vw_pin_ = static_cast<int*>(malloc(vw_cap_ * sizeof(int)));
+        if (!vw_pin_) throw std::bad_alloc();
       }
       std::map<int, std::vector<Shape3>> per_width;  // per distinct row width: every tensor's shape
       for (int i = 0; i < n; ++i) {

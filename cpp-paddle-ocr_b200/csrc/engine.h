@@ -85,7 +85,7 @@ class Net {
   size_t arena_bytes_ = 0;
   std::map<std::tuple<int, int, int>, std::unique_ptr<Inst>> cache_;
   Inst* cur_ = nullptr;
-  // ragged batches: per tensor, per row valid widths (int[nt][n]), staged in pinned memory
+  // ragged batches: per tensor, per row valid widths (int[nt][n]); host copy is pageable (see prepare)
   bool ragged_ = false;
   int* vw_pin_ = nullptr;
   int* vw_dev_ = nullptr;

@@ -154,7 +154,8 @@ dwconv_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi e, co
 
 // Depthwise conv, register-blocked along x: one thread owns S consecutive output pixels of one 8-channel group.
 // Per filter row it loads the KW weight vectors once and every input column once (a (S-1)*SW+KW wide window),
-// instead of KH*KW input + weight loads per output pixel.
+// instead of KH*KW input + weight loads per output pixel.  All loads of a filter row are unconditional (clamped
+// address, zeroed afterwards when out of range) so that they are issued back to back instead of one per branch.
 template <int KH, int KW, int SW, int S>
 __global__ void __launch_bounds__(kThreads)
 dwconv_strip_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi e, const int* __restrict__ vw) {
@@ -171,15 +172,21 @@ dwconv_strip_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi
     const int oy = int(r % out.h);
     const int n = int(r / out.h);
     const int ox0 = sx * S;
+    const int ix0 = ox0 * SW - g.pw;
     float acc[S][8];
 #pragma unroll
     for (int s_ = 0; s_ < S; ++s_)
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[s_][i] = 0.f;
+    const __half* img = in.p + long(n) * in.h * in.w * in.pitch + cg * 8;
 #pragma unroll
     for (int ky = 0; ky < KH; ++ky) {
       const int iy = oy * g.sh - g.ph + ky;
-      if (iy < 0 || iy >= in.h) continue;
+      const bool yok = iy >= 0 && iy < in.h;
+      const __half* row = img + long(min(max(iy, 0), in.h - 1)) * in.w * in.pitch;
+      H8 raw[WIN];
+#pragma unroll
+      for (int j = 0; j < WIN; ++j) raw[j] = ld8(row + long(min(max(ix0 + j, 0), in.w - 1)) * in.pitch);
       float w[KW][8];
 #pragma unroll
       for (int kx = 0; kx < KW; ++kx) {
@@ -188,14 +195,14 @@ dwconv_strip_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi
         w[kx][0] = w0.x; w[kx][1] = w0.y; w[kx][2] = w0.z; w[kx][3] = w0.w;
         w[kx][4] = w1.x; w[kx][5] = w1.y; w[kx][6] = w1.z; w[kx][7] = w1.w;
       }
-      const __half* row = in.p + (long(n) * in.h + iy) * in.w * in.pitch + cg * 8;
-      const int ix0 = ox0 * SW - g.pw;
 #pragma unroll
       for (int j = 0; j < WIN; ++j) {
         const int ix = ix0 + j;
-        if (ix < 0 || ix >= in.w) continue;
+        const bool ok = yok && ix >= 0 && ix < in.w;
         float x[8];
-        ld8(row + long(ix) * in.pitch).to_float(x);
+        raw[j].to_float(x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = ok ? x[i] : 0.f;
 #pragma unroll
         for (int s_ = 0; s_ < S; ++s_) {
           const int kx = j - s_ * SW;  // compile-time after unrolling

@@ -243,20 +243,21 @@ void ClsStage::run(const std::vector<DevImg>& imgs, const std::vector<Roi>& rois
   probs_.ensure(sizeof(float) * std::max(n, 1));
   // Every row is resized/padded to the fixed 48x192 input on its own, so the reference's batches of
   // cls_batch_num (src/ocr_cls.cpp:35-62) can be merged into larger launches without changing any value.
+  // all items are staged once: the pinned buffer must not be rewritten while an earlier async copy may still read it
+  h_items_.ensure(sizeof(CropItem) * std::max(n, 1));
+  items_.ensure(sizeof(CropItem) * std::max(n, 1));
+  for (int k = 0; k < n; ++k) {
+    const Roi& r = rois[k];
+    const DevImg& im = imgs[r.img];
+    h_items_.as<CropItem>()[k] = CropItem{im.p, im.stride, r.x, r.y, r.w, r.h, resize_width(48, 192, r.w, r.h), 192};
+  }
+  if (n > 0) cuda_check(cudaMemcpyAsync(items_.p, h_items_.p, sizeof(CropItem) * n, cudaMemcpyHostToDevice, s), "cls items");
   for (int b0 = 0; b0 < n; b0 += max_batch) {
     const int nb = std::min(max_batch, n - b0);
     auto t0 = Clock::now();
-    h_items_.ensure(sizeof(CropItem) * nb);
-    items_.ensure(sizeof(CropItem) * nb);
-    for (int k = 0; k < nb; ++k) {
-      const Roi& r = rois[b0 + k];
-      const DevImg& im = imgs[r.img];
-      h_items_.as<CropItem>()[k] = CropItem{im.p, im.stride, r.x, r.y, r.w, r.h, resize_width(48, 192, r.w, r.h), 192};
-    }
     __half* in = net_.prepare(nb, 48, 192);
-    cuda_check(cudaMemcpyAsync(items_.p, h_items_.p, sizeof(CropItem) * nb, cudaMemcpyHostToDevice, s), "cls items");
     // pad value 0.0: the classifier pads AFTER normalisation (src/ocr_cls.cpp:52-56)
-    launch_crop_preprocess(items_.as<CropItem>(), nb, 48, 192, make_norm(kMean05, kScale2), 0.f, in, s);
+    launch_crop_preprocess(items_.as<CropItem>() + b0, nb, 48, 192, make_norm(kMean05, kScale2), 0.f, in, s);
     t[0] += ms_since(t0);
     t0 = Clock::now();
     net_.run(s);
@@ -289,9 +290,9 @@ void ClsStage::rotate_rois(const std::vector<DevImg>& imgs, const std::vector<Ro
   // rois arrive grouped by image in ROI order; first[i] = index of image i's first ROI
   const int nimg = int(imgs.size());
   const size_t bytes = sizeof(RotItem) * n + sizeof(int) * (nimg + 1);
-  h_items_.ensure(bytes);
-  items_.ensure(bytes);
-  RotItem* it = h_items_.as<RotItem>();
+  h_rot_.ensure(bytes);
+  rot_.ensure(bytes);
+  RotItem* it = h_rot_.as<RotItem>();
   int* first = reinterpret_cast<int*>(it + n);
   int k = 0;
   for (int i = 0; i < nimg; ++i) {
@@ -303,8 +304,8 @@ void ClsStage::rotate_rois(const std::vector<DevImg>& imgs, const std::vector<Ro
   }
   first[nimg] = k;
   if (k != n) throw std::runtime_error("rotate_rois: ROIs must be grouped by ascending image index");
-  cuda_check(cudaMemcpyAsync(items_.p, h_items_.p, bytes, cudaMemcpyHostToDevice, s), "rotate items");
-  rotate_seq_kernel<<<nimg, 1024, 0, s>>>(items_.as<RotItem>(), reinterpret_cast<const int*>(items_.as<RotItem>() + n),
+  cuda_check(cudaMemcpyAsync(rot_.p, h_rot_.p, bytes, cudaMemcpyHostToDevice, s), "rotate items");
+  rotate_seq_kernel<<<nimg, 1024, 0, s>>>(rot_.as<RotItem>(), reinterpret_cast<const int*>(rot_.as<RotItem>() + n),
                                           labels_.as<int>());
   ++launches;
 }

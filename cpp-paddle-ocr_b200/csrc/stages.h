@@ -105,8 +105,8 @@ class ClsStage {
   Net net_;
   int batch_num_;
   float thresh_;
-  DevBuf items_, labels_, probs_;
-  DevBuf h_items_{true}, h_out_{true};
+  DevBuf items_, labels_, probs_, rot_;
+  DevBuf h_items_{true}, h_out_{true}, h_rot_{true};
 };
 
 class RecStage {
