@@ -447,3 +447,17 @@ def _net_profile(self, warmup=2, reps=5):
 
 
 Net.profile = _net_profile
+
+
+_sig("b200ocr_rotate_crop", C.c_int, C.c_int, _P(Image), C.c_void_p, _P(C.c_int), _P(C.c_int), C.c_void_p)
+
+
+def rotate_crop(img, box, device=0):
+    """Utility::GetRotateCropImage (reference src/utility.cpp:137-190) on the GPU."""
+    arr, keep = _images([img])
+    b = np.ascontiguousarray(np.asarray(box, np.int32).reshape(8))
+    r, c = C.c_int(), C.c_int()
+    check(lib.b200ocr_rotate_crop(device, arr, b.ctypes.data, C.byref(r), C.byref(c), None))
+    out = np.empty((r.value, c.value, 3), np.uint8)
+    check(lib.b200ocr_rotate_crop(device, arr, b.ctypes.data, C.byref(r), C.byref(c), out.ctypes.data))
+    return out

