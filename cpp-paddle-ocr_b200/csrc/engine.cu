@@ -309,7 +309,9 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
         }
         break;
       }
-      case LKind::DwConv: launch_dwconv(tv(L.in), tv(L.out), d_wf_ + L.wf_off, g, e, s, vwp(L.out)); break;
+      case LKind::DwConv:
+        launch_dwconv(tv(L.in), tv(L.out), d_wf_ + L.wf_off, d_wh_ + L.wh_off, g, e, s, vwp(L.out));
+        break;
       case LKind::Gap: launch_gap_partial(tv(L.in), vecp(L.out), I.splits[L.out], s); break;
       case LKind::SeFc:
         launch_se_fc(vecp(L.in), I.splits[L.in], I.hw[L.in], I.ts[L.in].n, L.cin, L.cmid, d_wf_ + L.wf_off,

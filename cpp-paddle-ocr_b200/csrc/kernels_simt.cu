@@ -152,13 +152,30 @@ dwconv_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi e, co
   }
 }
 
+// fp16 x fp16 + fp32 -> fp32 in one instruction (sm_100 FHFMA): the product of two halves is exact in fp32, so this
+// equals converting both operands and issuing an FFMA -- without the conversions.
+__device__ __forceinline__ float fhfma(unsigned short a, unsigned short b, float c) {
+  asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(c) : "h"(a), "h"(b));
+  return c;
+}
+__device__ __forceinline__ void fhfma8(const uint4& x, const uint4& w, float* acc) {
+  const unsigned xs[4] = {x.x, x.y, x.z, x.w}, ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    acc[2 * i] = fhfma((unsigned short)(xs[i] & 0xffffu), (unsigned short)(ws[i] & 0xffffu), acc[2 * i]);
+    acc[2 * i + 1] = fhfma((unsigned short)(xs[i] >> 16), (unsigned short)(ws[i] >> 16), acc[2 * i + 1]);
+  }
+}
+
 // Depthwise conv, register-blocked along x: one thread owns S consecutive output pixels of one 8-channel group.
-// Per filter row it loads the KW weight vectors once and every input column once (a (S-1)*SW+KW wide window),
-// instead of KH*KW input + weight loads per output pixel.  All loads of a filter row are unconditional (clamped
-// address, zeroed afterwards when out of range) so that they are issued back to back instead of one per branch.
+// Per filter row it loads the KW weight vectors (fp16, 16 B each) once and every input column once (a
+// (S-1)*SW+KW wide window) instead of KH*KW input + weight loads per output pixel; all loads of a filter row are
+// unconditional (clamped address, zeroed afterwards when out of range) so that they issue back to back, and the
+// multiply-accumulates take the fp16 operands directly (FHFMA), fp32 accumulation.
 template <int KH, int KW, int SW, int S>
 __global__ void __launch_bounds__(kThreads)
-dwconv_strip_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi e, const int* __restrict__ vw) {
+dwconv_strip_kernel(TV in, TV out, const float* __restrict__ wb, const __half* __restrict__ wh, ConvGeom g, Epi e,
+                    const int* __restrict__ vw) {
   const int cgs = (out.c + 7) >> 3;
   const int cp = g.cout_pad;
   const int strips = (out.w + S - 1) / S;
@@ -173,6 +190,7 @@ dwconv_strip_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi
     const int n = int(r / out.h);
     const int ox0 = sx * S;
     const int ix0 = ox0 * SW - g.pw;
+    const bool interior = ix0 >= 0 && ix0 + WIN <= in.w;
     float acc[S][8];
 #pragma unroll
     for (int s_ = 0; s_ < S; ++s_)
@@ -182,34 +200,29 @@ dwconv_strip_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi
 #pragma unroll
     for (int ky = 0; ky < KH; ++ky) {
       const int iy = oy * g.sh - g.ph + ky;
-      const bool yok = iy >= 0 && iy < in.h;
-      const __half* row = img + long(min(max(iy, 0), in.h - 1)) * in.w * in.pitch;
-      H8 raw[WIN];
+      if (iy < 0 || iy >= in.h) continue;
+      const __half* row = img + long(iy) * in.w * in.pitch;
+      uint4 raw[WIN];
+      if (interior) {
 #pragma unroll
-      for (int j = 0; j < WIN; ++j) raw[j] = ld8(row + long(min(max(ix0 + j, 0), in.w - 1)) * in.pitch);
-      float w[KW][8];
+        for (int j = 0; j < WIN; ++j) raw[j] = *reinterpret_cast<const uint4*>(row + long(ix0 + j) * in.pitch);
+      } else {
 #pragma unroll
-      for (int kx = 0; kx < KW; ++kx) {
-        const float4* wp = reinterpret_cast<const float4*>(wb + long(ky * KW + kx) * cp + cg * 8);
-        const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
-        w[kx][0] = w0.x; w[kx][1] = w0.y; w[kx][2] = w0.z; w[kx][3] = w0.w;
-        w[kx][4] = w1.x; w[kx][5] = w1.y; w[kx][6] = w1.z; w[kx][7] = w1.w;
+        for (int j = 0; j < WIN; ++j) {
+          const int ix = ix0 + j;
+          raw[j] = *reinterpret_cast<const uint4*>(row + long(min(max(ix, 0), in.w - 1)) * in.pitch);
+          if (ix < 0 || ix >= in.w) raw[j] = make_uint4(0, 0, 0, 0);
+        }
       }
+      uint4 w[KW];
+#pragma unroll
+      for (int kx = 0; kx < KW; ++kx) w[kx] = __ldg(reinterpret_cast<const uint4*>(wh + long(ky * KW + kx) * cp + cg * 8));
 #pragma unroll
       for (int j = 0; j < WIN; ++j) {
-        const int ix = ix0 + j;
-        const bool ok = yok && ix >= 0 && ix < in.w;
-        float x[8];
-        raw[j].to_float(x);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = ok ? x[i] : 0.f;
 #pragma unroll
         for (int s_ = 0; s_ < S; ++s_) {
           const int kx = j - s_ * SW;  // compile-time after unrolling
-          if (kx >= 0 && kx < KW) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[s_][i] = fmaf(x[i], w[kx][i], acc[s_][i]);
-          }
+          if (kx >= 0 && kx < KW) fhfma8(raw[j], w[kx], acc[s_]);
         }
       }
     }
@@ -784,7 +797,7 @@ void launch_conv_simt(const TV& in, const TV& out, const __half* w, const float*
   conv_simt_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, w, bias, g, e, vw);
 }
 
-void launch_dwconv(const TV& in, const TV& out, const float* wb, const ConvGeom& g, const Epi& e,
+void launch_dwconv(const TV& in, const TV& out, const float* wb, const __half* wh, const ConvGeom& g, const Epi& e,
                    cudaStream_t s, const int* vw) {
   {
     // register-blocked strips along x whenever the row is long enough to fill them
@@ -792,10 +805,10 @@ void launch_dwconv(const TV& in, const TV& out, const float* wb, const ConvGeom&
     const long st = long(out.n) * out.h * ((out.w + S - 1) / S) * ((out.c + 7) / 8);
     const int sg = grid_for(st);
     if (out.w >= 2 * S && e.res == nullptr) {
-      if (g.kh == 3 && g.kw == 3 && g.sw == 1) { dwconv_strip_kernel<3, 3, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
-      if (g.kh == 3 && g.kw == 3 && g.sw == 2) { dwconv_strip_kernel<3, 3, 2, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
-      if (g.kh == 5 && g.kw == 5 && g.sw == 1) { dwconv_strip_kernel<5, 5, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
-      if (g.kh == 5 && g.kw == 5 && g.sw == 2) { dwconv_strip_kernel<5, 5, 2, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
+      if (g.kh == 3 && g.kw == 3 && g.sw == 1) { dwconv_strip_kernel<3, 3, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, wh, g, e, vw); return; }
+      if (g.kh == 3 && g.kw == 3 && g.sw == 2) { dwconv_strip_kernel<3, 3, 2, S><<<sg, kThreads, 0, s>>>(in, out, wb, wh, g, e, vw); return; }
+      if (g.kh == 5 && g.kw == 5 && g.sw == 1) { dwconv_strip_kernel<5, 5, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, wh, g, e, vw); return; }
+      if (g.kh == 5 && g.kw == 5 && g.sw == 2) { dwconv_strip_kernel<5, 5, 2, S><<<sg, kThreads, 0, s>>>(in, out, wb, wh, g, e, vw); return; }
     }
   }
   const long total = long(out.n) * out.h * out.w * ((out.c + 7) / 8);

@@ -299,6 +299,11 @@ struct Builder {
       }
       L.wf_off = push_f(blk);
       L.cin_pad = L.cout_pad = cp;
+      // fp16 copy [tap][cp] for the mixed-precision (fp16 x fp16 + fp32) kernel; the fp32 block keeps the bias
+      while (plan.wh.size() % 8) plan.wh.push_back(0);
+      L.wh_off = int64_t(plan.wh.size());
+      for (int t = 0; t < taps; ++t)
+        for (int c = 0; c < cp; ++c) plan.wh.push_back(f32_to_f16_bits(blk[size_t(t) * cp + c]));
     } else {
       if (groups != 1) fail(i, "grouped conv unsupported");
       L.kind = LKind::Conv;
