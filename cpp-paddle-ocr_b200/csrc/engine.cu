@@ -310,7 +310,10 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
         break;
       }
       case LKind::DwConv:
-        launch_dwconv(tv(L.in), tv(L.out), d_wf_ + L.wf_off, d_wh_ + L.wh_off, g, e, s, vwp(L.out));
+        // the detector keeps fp32 depthwise weights: its output is thresholded pixel by pixel and has to stay
+        // within 1e-2 of the fp32 reference; rec / cls take the FHFMA kernel (fp16 weights), ~1.5x faster
+        launch_dwconv(tv(L.in), tv(L.out), d_wf_ + L.wf_off, plan_.kind == "det" ? nullptr : d_wh_ + L.wh_off, g, e, s,
+                      vwp(L.out));
         break;
       case LKind::Gap: launch_gap_partial(tv(L.in), vecp(L.out), I.splits[L.out], s); break;
       case LKind::SeFc:

@@ -44,7 +44,8 @@ bool conv_tc_eligible(const TV& in, const TV& out, const ConvGeom& g);
 ConvTcPlan make_conv_tc_plan(const TV& in, const TV& out, const __half* w, const ConvGeom& g);
 void free_conv_tc_plan(ConvTcPlan* p);
 void launch_conv_tc(const ConvTcPlan& p, const float* bias, const Epi& e, cudaStream_t s, const int* vw = nullptr);
-// w_bias: fp32 [taps][cp] weights + [cp] bias; w_half: the same weights as fp16 [taps][cp]
+// w_bias: fp32 [taps][cp] weights + [cp] bias; w_half: the same weights as fp16 [taps][cp] (FHFMA kernel), or
+// nullptr to multiply with the fp32 weights (conversion + FFMA: slower, one rounding less)
 void launch_dwconv(const TV& in, const TV& out, const float* w_bias, const __half* w_half, const ConvGeom& g,
                    const Epi& e, cudaStream_t s, const int* vw = nullptr);
 

@@ -236,6 +236,78 @@ dwconv_strip_kernel(TV in, TV out, const float* __restrict__ wb, const __half* _
   }
 }
 
+// fp32-weight variant (used by the detector, whose thresholded output is the most precision-sensitive):
+// Depthwise conv, register-blocked along x: one thread owns S consecutive output pixels of one 8-channel group.
+// Per filter row it loads the KW weight vectors once and every input column once (a (S-1)*SW+KW wide window),
+// instead of KH*KW input + weight loads per output pixel.  All loads of a filter row are unconditional (clamped
+// address, zeroed afterwards when out of range) so that they are issued back to back instead of one per branch.
+template <int KH, int KW, int SW, int S>
+__global__ void __launch_bounds__(kThreads)
+dwconv_strip_f32w_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi e, const int* __restrict__ vw) {
+  const int cgs = (out.c + 7) >> 3;
+  const int cp = g.cout_pad;
+  const int strips = (out.w + S - 1) / S;
+  const long total = long(out.n) * out.h * strips * cgs;
+  const float* bias = wb + long(KH * KW) * cp;
+  constexpr int WIN = (S - 1) * SW + KW;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const int cg = int(t % cgs);
+    long r = t / cgs;
+    const int sx = int(r % strips); r /= strips;
+    const int oy = int(r % out.h);
+    const int n = int(r / out.h);
+    const int ox0 = sx * S;
+    const int ix0 = ox0 * SW - g.pw;
+    float acc[S][8];
+#pragma unroll
+    for (int s_ = 0; s_ < S; ++s_)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[s_][i] = 0.f;
+    const __half* img = in.p + long(n) * in.h * in.w * in.pitch + cg * 8;
+#pragma unroll
+    for (int ky = 0; ky < KH; ++ky) {
+      const int iy = oy * g.sh - g.ph + ky;
+      const bool yok = iy >= 0 && iy < in.h;
+      const __half* row = img + long(min(max(iy, 0), in.h - 1)) * in.w * in.pitch;
+      H8 raw[WIN];
+#pragma unroll
+      for (int j = 0; j < WIN; ++j) raw[j] = ld8(row + long(min(max(ix0 + j, 0), in.w - 1)) * in.pitch);
+      float w[KW][8];
+#pragma unroll
+      for (int kx = 0; kx < KW; ++kx) {
+        const float4* wp = reinterpret_cast<const float4*>(wb + long(ky * KW + kx) * cp + cg * 8);
+        const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+        w[kx][0] = w0.x; w[kx][1] = w0.y; w[kx][2] = w0.z; w[kx][3] = w0.w;
+        w[kx][4] = w1.x; w[kx][5] = w1.y; w[kx][6] = w1.z; w[kx][7] = w1.w;
+      }
+#pragma unroll
+      for (int j = 0; j < WIN; ++j) {
+        const int ix = ix0 + j;
+        const bool ok = yok && ix >= 0 && ix < in.w;
+        float x[8];
+        raw[j].to_float(x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = ok ? x[i] : 0.f;
+#pragma unroll
+        for (int s_ = 0; s_ < S; ++s_) {
+          const int kx = j - s_ * SW;  // compile-time after unrolling
+          if (kx >= 0 && kx < KW) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[s_][i] = fmaf(x[i], w[kx][i], acc[s_][i]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int s_ = 0; s_ < S; ++s_) {
+      const int ox = ox0 + s_;
+      if (ox >= out.w) break;
+      const long pix = (long(n) * out.h + oy) * out.w + ox;
+      epilogue8(acc[s_], bias, cg * 8, out.c, e, out, pix, vw && ox >= vw[n]);
+    }
+  }
+}
+
 // First layer: 3 input channels (pitch 8), 3x3, any stride; all COUT channels of one output pixel per thread,
 // filter in shared memory as fp32 [tap][ci][co].
 template <int COUT>
@@ -804,7 +876,13 @@ void launch_dwconv(const TV& in, const TV& out, const float* wb, const __half* w
     constexpr int S = 4;
     const long st = long(out.n) * out.h * ((out.w + S - 1) / S) * ((out.c + 7) / 8);
     const int sg = grid_for(st);
-    if (out.w >= 2 * S && e.res == nullptr) {
+    if (out.w >= 2 * S && e.res == nullptr && wh == nullptr) {
+      if (g.kh == 3 && g.kw == 3 && g.sw == 1) { dwconv_strip_f32w_kernel<3, 3, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
+      if (g.kh == 3 && g.kw == 3 && g.sw == 2) { dwconv_strip_f32w_kernel<3, 3, 2, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
+      if (g.kh == 5 && g.kw == 5 && g.sw == 1) { dwconv_strip_f32w_kernel<5, 5, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
+      if (g.kh == 5 && g.kw == 5 && g.sw == 2) { dwconv_strip_f32w_kernel<5, 5, 2, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
+    }
+    if (out.w >= 2 * S && e.res == nullptr && wh != nullptr) {
       if (g.kh == 3 && g.kw == 3 && g.sw == 1) { dwconv_strip_kernel<3, 3, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, wh, g, e, vw); return; }
       if (g.kh == 3 && g.kw == 3 && g.sw == 2) { dwconv_strip_kernel<3, 3, 2, S><<<sg, kThreads, 0, s>>>(in, out, wb, wh, g, e, vw); return; }
       if (g.kh == 5 && g.kw == 5 && g.sw == 1) { dwconv_strip_kernel<5, 5, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, wh, g, e, vw); return; }
