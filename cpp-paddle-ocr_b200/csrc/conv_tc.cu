@@ -13,6 +13,7 @@
 
 #include <cuda.h>
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 
@@ -32,6 +33,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -118,6 +122,76 @@ struct ConvTcArgs {
   int mask_w, mask_hw;
 };
 
+// Drain one accumulator tile: the calling warp owns TMEM lanes 32*(warp%4) .. +31 (row r of the tile = lane of D).
+template <int ACT>
+__device__ __forceinline__ void epilogue_tile(const ConvTcArgs& a, uint32_t tmem_base, int x0, int y0, int n0, int nblk,
+                                              int warp, int lane) {
+  const int q = warp & 3;
+  const int r = q * 32 + lane;
+  const int rows = a.tw * a.th * a.tn;
+  const int tw_ = r % a.tw, th_ = (r / a.tw) % a.th, tn_ = r / (a.tw * a.th);
+  const int x = x0 + tw_, y = y0 + th_, n = n0 + tn_;
+  const bool valid = r < rows && x < a.ow && y < a.oh && n < a.on;
+  const long pix = (long(n) * a.oh + y) * a.ow + x;
+  const bool masked = valid && a.vw && int(pix % a.mask_w) >= a.vw[pix / a.mask_hw];
+  const int c8lim = (a.cout + 7) & ~7;
+  const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
+  for (int col = 0; col < a.bn; col += 16) {
+    uint32_t v[16];
+    tmem_ld16(trow + col, v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const int c0 = nblk * a.bn + col;
+    if (!valid || c0 >= c8lim) continue;
+    float f[16];
+    {
+      const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);  // bias is padded to a multiple of 16
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float4 b = __ldg(bp + g);
+        f[4 * g] = __uint_as_float(v[4 * g]) + b.x;
+        f[4 * g + 1] = __uint_as_float(v[4 * g + 1]) + b.y;
+        f[4 * g + 2] = __uint_as_float(v[4 * g + 2]) + b.z;
+        f[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + b.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = a.epi.s2 * act_fn<ACT>(f[i], a.epi.a, a.epi.b) + a.epi.t2;
+    const bool second = c0 + 8 < c8lim;
+    if (a.epi.res) {
+      const __half* rp = a.epi.res + pix * a.epi.res_pitch + c0;
+      uint4 r0 = *reinterpret_cast<const uint4*>(rp);
+      const __half2* h = reinterpret_cast<const __half2*>(&r0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { float2 p = __half22float2(h[i]); f[2 * i] += p.x; f[2 * i + 1] += p.y; }
+      if (second) {
+        uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
+        const __half2* g = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 p = __half22float2(g[i]); f[8 + 2 * i] += p.x; f[8 + 2 * i + 1] += p.y; }
+      }
+    }
+    if (masked) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = 0.f;
+    } else if (c0 + 16 > a.cout) {  // only the last channel group of a layer can be partial
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (c0 + i >= a.cout) f[i] = 0.f;
+    }
+    __half* op = a.out + pix * a.out_pitch + c0;
+    uint4 o0, o1;
+    __half2* h0 = reinterpret_cast<__half2*>(&o0);
+    __half2* h1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h0[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      h1[i] = __floats2half2_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
+    }
+    *reinterpret_cast<uint4*>(op) = o0;
+    if (second) *reinterpret_cast<uint4*>(op + 8) = o1;
+  }
+}
+
 template <int ACT>
 __global__ void __launch_bounds__(192)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -202,79 +276,130 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(tmem_full);
     }
   } else {
-    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; row == lane of D
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int rows = a.tw * a.th * a.tn;
-    const int tw_ = r % a.tw, th_ = (r / a.tw) % a.th, tn_ = r / (a.tw * a.th);
-    const int x = x0 + tw_, y = y0 + th_, n = n0 + tn_;
-    const bool valid = r < rows && x < a.ow && y < a.oh && n < a.on;
-    const long pix = (long(n) * a.oh + y) * a.ow + x;
-    const bool masked = valid && a.vw && int(pix % a.mask_w) >= a.vw[pix / a.mask_hw];
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int c8lim = (a.cout + 7) & ~7;
-    const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
-    for (int col = 0; col < a.bn; col += 16) {
-      uint32_t v[16];
-      tmem_ld16(trow + col, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int c0 = nblk * a.bn + col;
-      if (!valid || c0 >= c8lim) continue;
-      float f[16];
-      {
-        const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);  // bias is padded to a multiple of 16
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float4 b = __ldg(bp + g);
-          f[4 * g] = __uint_as_float(v[4 * g]) + b.x;
-          f[4 * g + 1] = __uint_as_float(v[4 * g + 1]) + b.y;
-          f[4 * g + 2] = __uint_as_float(v[4 * g + 2]) + b.z;
-          f[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + b.w;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] = a.epi.s2 * act_fn<ACT>(f[i], a.epi.a, a.epi.b) + a.epi.t2;
-      const bool second = c0 + 8 < c8lim;
-      if (a.epi.res) {
-        const __half* rp = a.epi.res + pix * a.epi.res_pitch + c0;
-        uint4 r0 = *reinterpret_cast<const uint4*>(rp);
-        const __half2* h = reinterpret_cast<const __half2*>(&r0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { float2 p = __half22float2(h[i]); f[2 * i] += p.x; f[2 * i + 1] += p.y; }
-        if (second) {
-          uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
-          const __half2* g = reinterpret_cast<const __half2*>(&r1);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { float2 p = __half22float2(g[i]); f[8 + 2 * i] += p.x; f[8 + 2 * i + 1] += p.y; }
-        }
-      }
-      if (masked) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = 0.f;
-      } else if (c0 + 16 > a.cout) {  // only the last channel group of a layer can be partial
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c0 + i >= a.cout) f[i] = 0.f;
-      }
-      __half* op = a.out + pix * a.out_pitch + c0;
-      uint4 o0, o1;
-      __half2* h0 = reinterpret_cast<__half2*>(&o0);
-      __half2* h1 = reinterpret_cast<__half2*>(&o1);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        h0[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-        h1[i] = __floats2half2_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
-      }
-      *reinterpret_cast<uint4*>(op) = o0;
-      if (second) *reinterpret_cast<uint4*>(op + 8) = o1;
-    }
+    epilogue_tile<ACT>(a, tmem_base, x0, y0, n0, nblk, warp, lane);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(uint32_t(a.tmem_cols))
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- persistent variant
+// For layers whose whole filter block (all taps x all K chunks of one N tile) fits in shared memory next to the A
+// ring: one CTA per SM slot keeps the filter resident, walks over its share of the pixel tiles and double-buffers
+// the accumulator in TMEM, so the TMA loads of tile i+1, the MMAs of tile i+1 and the epilogue of tile i overlap
+// and the per-CTA set-up (barriers, TMEM allocation, descriptor fetch, filter load) is paid once.
+template <int ACT>
+__global__ void __launch_bounds__(192)
+conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const ConvTcArgs a, const int n_mtiles, const int kt /* taps * K chunks */) {
+  extern __shared__ uint8_t smem_raw[];
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* a_full = b_full + 1;
+  uint64_t* a_empty = a_full + kStagesMax;
+  uint64_t* t_full = a_empty + kStagesMax;  // [2]
+  uint64_t* t_empty = t_full + 2;           // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
+  const uint32_t tiles_base = (smem_u32(smem_raw) + 256 + 1023) & ~1023u;
+  uint8_t* tiles = smem_raw + (tiles_base - smem_u32(smem_raw));
+  const int b_chunk = a.bn * 128;
+  const uint32_t a_ring = uint32_t(kt) * b_chunk;  // offset of the A ring behind the resident filter
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblk = blockIdx.y;
+  const int kchunks = (a.cin + 63) >> 6;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    mbar_init(b_full, 1);
+    for (int s = 0; s < a.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(uint32_t(2 * a.tmem_cols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(b_full, uint32_t(kt) * b_chunk);
+      for (int tap = 0, it = 0; tap < a.kh * a.kw; ++tap)
+        for (int kc = 0; kc < kchunks; ++kc, ++it)
+          tma_load_2d(&tmB, b_full, tiles + size_t(it) * b_chunk, tap * a.cin_pad + kc * 64, nblk * a.bn);
+      const uint32_t a_bytes = uint32_t(a.tw * a.th * a.tn * 128);
+      int g = 0;
+      for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x) {
+        int t = tile;
+        const int tx = t % a.tiles_x; t /= a.tiles_x;
+        const int ty = t % a.tiles_y; t /= a.tiles_y;
+        const int x0 = tx * a.tw, y0 = ty * a.th, n0 = t * a.tn;
+        for (int ky = 0; ky < a.kh; ++ky)
+          for (int kx = 0; kx < a.kw; ++kx)
+            for (int kc = 0; kc < kchunks; ++kc, ++g) {
+              const int s = g % a.stages;
+              mbar_wait(&a_empty[s], (uint32_t(g / a.stages) & 1u) ^ 1u);
+              mbar_expect_tx(&a_full[s], a_bytes);
+              tma_load_4d(&tmA, &a_full[s], tiles + a_ring + size_t(s) * kATileBytes, kc * 64, x0 + kx - a.pw,
+                          y0 + ky - a.ph, n0);
+            }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (uint32_t(a.bn >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+      mbar_wait(b_full, 0);
+      int g = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&t_empty[buf], (uint32_t(lt >> 1) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t dst = tmem_base + uint32_t(buf * a.tmem_cols);
+        for (int tap = 0, it = 0; tap < a.kh * a.kw; ++tap)
+          for (int kc = 0; kc < kchunks; ++kc, ++it, ++g) {
+            const int s = g % a.stages;
+            mbar_wait(&a_full[s], uint32_t(g / a.stages) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = tiles_base + a_ring + uint32_t(s) * kATileBytes;
+            const uint32_t sb = tiles_base + uint32_t(it) * b_chunk;
+            const int rem = a.cin - kc * 64;
+            const int k16 = rem >= 64 ? 4 : (rem + 15) >> 4;
+            for (int k = 0; k < k16; ++k) umma_f16(dst, umma_desc(sa + k * 32), umma_desc(sb + k * 32), idesc, (it | k) != 0);
+            umma_commit(&a_empty[s]);
+          }
+        umma_commit(&t_full[buf]);
+      }
+    }
+  } else {
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x, ++lt) {
+      int t = tile;
+      const int tx = t % a.tiles_x; t /= a.tiles_x;
+      const int ty = t % a.tiles_y; t /= a.tiles_y;
+      const int buf = lt & 1;
+      mbar_wait(&t_full[buf], uint32_t(lt >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      epilogue_tile<ACT>(a, tmem_base + uint32_t(buf * a.tmem_cols), tx * a.tw, ty * a.th, t * a.tn, nblk, warp, lane);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&t_empty[buf]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(uint32_t(2 * a.tmem_cols))
                  : "memory");
   }
 }
@@ -321,6 +446,8 @@ struct ConvTcPlanImpl {
   ConvTcArgs args;
   dim3 grid;
   size_t smem;
+  bool persistent = false;
+  int n_mtiles = 0, kt = 0;
 };
 
 bool conv_tc_eligible(const TV& in, const TV& out, const ConvGeom& g) {
@@ -387,9 +514,31 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
   cuuint64_t sB[1] = {cuuint64_t(taps) * g.cin_pad * 2};
   cuuint32_t bB[2] = {64, cuuint32_t(a.bn)};
   encode(&impl->tmB, const_cast<__half*>(w), 2, dB, sB, bB);
-  impl->args = a;
   impl->grid = dim3(unsigned(a.tiles_x * a.tiles_y * tiles_n), unsigned(n_tiles));
   impl->smem = size_t(a.stages) * (kATileBytes + a.bn * 128) + 1024 + 128;
+  // persistent variant: filter block resident + A ring + double-buffered accumulator
+  {
+    const int m_tiles = a.tiles_x * a.tiles_y * tiles_n;
+    const size_t b_bytes = size_t(k_iters) * a.bn * 128;
+    const int st = k_iters < kStagesMax ? (k_iters < 2 ? 2 : k_iters) : kStagesMax;
+    const size_t need = b_bytes + size_t(st) * kATileBytes + 1024 + 256;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (2 * a.tmem_cols <= 512 && need <= 220 * 1024 && m_tiles >= 2 * sms / 3 && !getenv("B200OCR_NO_PERSISTENT_CONV")) {
+      int per_sm = int((227 * 1024) / need);
+      per_sm = std::min(per_sm, 512 / (2 * a.tmem_cols));
+      per_sm = std::max(1, std::min(per_sm, 4));
+      const int ctas = std::min(m_tiles, sms * per_sm);
+      impl->persistent = true;
+      impl->n_mtiles = m_tiles;
+      impl->kt = k_iters;
+      a.stages = st;
+      impl->grid = dim3(unsigned(ctas), unsigned(n_tiles));
+      impl->smem = need;
+    }
+  }
+  impl->args = a;
   // per device (function attributes live in the context): cheap, done once per (layer, shape)
   cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -397,6 +546,12 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
   cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(conv_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   ConvTcPlan p;
   p.impl = impl;
   return p;
@@ -412,6 +567,18 @@ void launch_conv_tc(const ConvTcPlan& p, const float* bias, const Epi& e, cudaSt
   a.bias = bias;
   a.epi = e;
   a.vw = vw;
+  if (p.impl->persistent) {
+    const int nm = p.impl->n_mtiles, kt = p.impl->kt;
+    switch (e.act) {
+      case 1: conv_tc_persist_kernel<1><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
+      case 2: conv_tc_persist_kernel<2><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
+      case 3: conv_tc_persist_kernel<3><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
+      case 4: conv_tc_persist_kernel<4><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
+      case 5: conv_tc_persist_kernel<5><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
+      default: conv_tc_persist_kernel<0><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
+    }
+    return;
+  }
   switch (e.act) {
     case 1: conv_tc_kernel<1><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
     case 2: conv_tc_kernel<2><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
