@@ -22,6 +22,11 @@ namespace b200ocr {
 namespace {
 
 constexpr int kStagesMax = 4;
+// The epilogue is a chain of dependent instructions per 16-column group; with one warp per scheduler every latency
+// is exposed.  16 epilogue warps (4 per TMEM lane quadrant, each taking every 4th column group) keep all four
+// schedulers busy.  Block = 2 control warps + kEpiWarps.
+constexpr int kEpiWarps = 16;
+constexpr int kThreadsTc = 64 + 32 * kEpiWarps;
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 fp16
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -126,7 +131,8 @@ struct ConvTcArgs {
 template <int ACT>
 __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& a, uint32_t tmem_base, int x0, int y0, int n0, int nblk,
                                               int warp, int lane) {
-  const int q = warp & 3;
+  const int q = warp & 3;               // TMEM lane quadrant this warp may read (hardware rule: warp id % 4)
+  const int cgrp = (warp - 2) >> 2;     // which share of the 16-column groups
   const int r = q * 32 + lane;
   const int rows = a.tw * a.th * a.tn;
   const int tw_ = r % a.tw, th_ = (r / a.tw) % a.th, tn_ = r / (a.tw * a.th);
@@ -136,7 +142,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& a, uint32_t tmem
   const bool masked = valid && a.vw && int(pix % a.mask_w) >= a.vw[pix / a.mask_hw];
   const int c8lim = (a.cout + 7) & ~7;
   const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
-  for (int col = 0; col < a.bn; col += 16) {
+  for (int col = cgrp * 16; col < a.bn; col += 16 * (kEpiWarps / 4)) {
     uint32_t v[16];
     tmem_ld16(trow + col, v);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -193,7 +199,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& a, uint32_t tmem
 }
 
 template <int ACT>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(kThreadsTc)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -295,7 +301,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // the accumulator in TMEM, so the TMA loads of tile i+1, the MMAs of tile i+1 and the epilogue of tile i overlap
 // and the per-CTA set-up (barriers, TMEM allocation, descriptor fetch, filter load) is paid once.
 template <int ACT>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(kThreadsTc)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const ConvTcArgs a, const int n_mtiles, const int kt /* taps * K chunks */) {
   extern __shared__ uint8_t smem_raw[];
@@ -318,7 +324,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     mbar_init(b_full, 1);
     for (int s = 0; s < a.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 32 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -570,22 +576,22 @@ void launch_conv_tc(const ConvTcPlan& p, const float* bias, const Epi& e, cudaSt
   if (p.impl->persistent) {
     const int nm = p.impl->n_mtiles, kt = p.impl->kt;
     switch (e.act) {
-      case 1: conv_tc_persist_kernel<1><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
-      case 2: conv_tc_persist_kernel<2><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
-      case 3: conv_tc_persist_kernel<3><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
-      case 4: conv_tc_persist_kernel<4><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
-      case 5: conv_tc_persist_kernel<5><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
-      default: conv_tc_persist_kernel<0><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
+      case 1: conv_tc_persist_kernel<1><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
+      case 2: conv_tc_persist_kernel<2><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
+      case 3: conv_tc_persist_kernel<3><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
+      case 4: conv_tc_persist_kernel<4><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
+      case 5: conv_tc_persist_kernel<5><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
+      default: conv_tc_persist_kernel<0><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
     }
     return;
   }
   switch (e.act) {
-    case 1: conv_tc_kernel<1><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
-    case 2: conv_tc_kernel<2><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
-    case 3: conv_tc_kernel<3><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
-    case 4: conv_tc_kernel<4><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
-    case 5: conv_tc_kernel<5><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
-    default: conv_tc_kernel<0><<<p.impl->grid, 192, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
+    case 1: conv_tc_kernel<1><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
+    case 2: conv_tc_kernel<2><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
+    case 3: conv_tc_kernel<3><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
+    case 4: conv_tc_kernel<4><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
+    case 5: conv_tc_kernel<5><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
+    default: conv_tc_kernel<0><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
   }
 }
 

@@ -173,5 +173,10 @@ def test_pool_dispatch_and_results(models_dir, images):
         assert d["request_id"] == i and d["success"] and d["words"] == want[i]
         seen_workers.add(d["worker_id"])
     assert len(seen_workers) >= 1
+    import time
+    for _ in range(100):  # a worker clears its busy flag right after publishing its results
+        if pool.idle_count == pool.worker_count:
+            break
+        time.sleep(0.01)
     assert pool.idle_count == pool.worker_count
     pool.close()
