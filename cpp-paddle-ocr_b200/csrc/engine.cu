@@ -278,12 +278,13 @@ __half* Net::prepare(int n, int h, int w, const int* widths) {
   return reinterpret_cast<__half*>(arena_ + I->boff[plan_.tensors[plan_.input].buf]);
 }
 
-void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<void(int, bool)>* hook) {
+void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<void(int, bool)>* hook, int only) {
   auto tv = [&](int t) { return make_tv(arena_, plan_, I.boff, I.ts, t); };
   auto vwp = [&](int t) -> const int* { return ragged_ ? vw_dev_ + size_t(t) * I.n : nullptr; };
   auto vecp = [&](int t) { return reinterpret_cast<float*>(arena_ + I.boff[plan_.tensors[t].buf]); };
   int launches = 0;
   for (size_t li = 0; li < plan_.layers.size(); ++li) {
+    if (only >= 0 && int(li) != only) continue;
     const Layer& L = plan_.layers[li];
     if (hook) (*hook)(int(li), true);
     Epi e;
@@ -360,7 +361,7 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
     ++launches;
     if (hook) (*hook)(int(li), false);
   }
-  I.launches = launches;
+  if (only < 0) I.launches = launches;
 }
 
 std::vector<Net::LayerProfile> Net::profile(cudaStream_t stream, int warmup, int reps, int thresh_u8) {
@@ -368,22 +369,31 @@ std::vector<Net::LayerProfile> Net::profile(cudaStream_t stream, int warmup, int
   Inst& I = *cur_;
   const int nl = int(plan_.layers.size());
   for (int k = 0; k < warmup; ++k) record(I, stream, thresh_u8);
-  std::vector<cudaEvent_t> ev(size_t(nl) * 2);
+  // Every launch is timed on its own between two CUDA events on `stream`, after a write of a buffer larger than
+  // L2 (so a layer never finds its input in cache only because the previous repetition left it there).  All work
+  // is enqueued without host synchronisation: the GPU never waits for the host inside a timed window.
+  const size_t flush_bytes = size_t(256) << 20;
+  void* flush = nullptr;
+  cuda_check(cudaMalloc(&flush, flush_bytes), "cudaMalloc L2 flush buffer");
+  std::vector<cudaEvent_t> ev(size_t(nl) * reps * 2);
   for (auto& e : ev) cuda_check(cudaEventCreate(&e), "cudaEventCreate");
+  for (int li = 0; li < nl; ++li)
+    for (int r = 0; r < reps; ++r) {
+      cudaMemsetAsync(flush, r, flush_bytes, stream);
+      cudaEventRecord(ev[(size_t(li) * reps + r) * 2], stream);
+      record(I, stream, thresh_u8, nullptr, li);
+      cudaEventRecord(ev[(size_t(li) * reps + r) * 2 + 1], stream);
+    }
+  cuda_check(cudaStreamSynchronize(stream), "profile pass");
   std::vector<double> ms(nl, 0.0);
-  std::function<void(int, bool)> hook = [&](int li, bool before) {
-    cudaEventRecord(ev[size_t(li) * 2 + (before ? 0 : 1)], stream);
-  };
-  for (int r = 0; r < reps; ++r) {
-    record(I, stream, thresh_u8, &hook);
-    cuda_check(cudaStreamSynchronize(stream), "profile pass");
-    for (int li = 0; li < nl; ++li) {
+  for (int li = 0; li < nl; ++li)
+    for (int r = 0; r < reps; ++r) {
       float t = 0.f;
-      cudaEventElapsedTime(&t, ev[size_t(li) * 2], ev[size_t(li) * 2 + 1]);
+      cudaEventElapsedTime(&t, ev[(size_t(li) * reps + r) * 2], ev[(size_t(li) * reps + r) * 2 + 1]);
       ms[li] += t;
     }
-  }
   for (auto& e : ev) cudaEventDestroy(e);
+  cudaFree(flush);
   static const char* kn[] = {"Conv", "DwConv", "Gap", "SeFc", "Scale", "UpAdd", "UpCat", "Pool",
                              "Add", "LayerNorm", "Attn", "DbHead", "FcSoftmax", "CtcHead"};
   std::vector<LayerProfile> out;

@@ -61,7 +61,8 @@ class Net {
   bool fetch(const std::string& var, std::vector<float>* out, int dims[4]);
 
   // Per-layer device time of the last prepared shape: every fused layer is launched on its own between two
-  // CUDA events on `stream` (after `warmup` untimed passes), averaged over `reps`.  Also reports the layer's
+  // CUDA events on `stream` (after `warmup` untimed passes, L2 flushed before every timed launch), averaged
+  // over `reps`.  Also reports the layer's
   // algorithmic FLOPs and HBM bytes (activations in + out + weights) so that a caller can place it on a roofline.
   struct LayerProfile { std::string name, kind; double ms, flops, bytes; int tensor_core; };
   std::vector<LayerProfile> profile(cudaStream_t stream, int warmup, int reps, int thresh_u8 = -1);
@@ -74,7 +75,8 @@ class Net {
   Inst* instantiate(int n, int h, int w);
   void infer(int n, int h, int w, std::vector<Shape3>* ts, std::vector<int>* splits, std::vector<int>* hw,
              std::vector<int>* gap_src) const;
-  void record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<void(int, bool)>* hook = nullptr);
+  void record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<void(int, bool)>* hook = nullptr,
+              int only = -1);
 
   Plan plan_;
   NetOptions opt_;

@@ -174,7 +174,7 @@ __device__ __forceinline__ void fhfma8(const uint4& x, const uint4& w, float* ac
 // unconditional (clamped address, zeroed afterwards when out of range) so that they issue back to back, and the
 // multiply-accumulates take the fp16 operands directly (FHFMA), fp32 accumulation.
 template <int KH, int KW, int SW, int S>
-__global__ void __launch_bounds__(kThreads, S >= 8 ? 2 : 1)
+__global__ void __launch_bounds__(kThreads)
 dwconv_strip_kernel(TV in, TV out, const float* __restrict__ wb, const __half* __restrict__ wh, ConvGeom g, Epi e,
                     const int* __restrict__ vw) {
   const int cgs = (out.c + 7) >> 3;
@@ -882,14 +882,6 @@ void launch_dwconv(const TV& in, const TV& out, const float* wb, const __half* w
       if (g.kh == 3 && g.kw == 3 && g.sw == 2) { dwconv_strip_f32w_kernel<3, 3, 2, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
       if (g.kh == 5 && g.kw == 5 && g.sw == 1) { dwconv_strip_f32w_kernel<5, 5, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
       if (g.kh == 5 && g.kw == 5 && g.sw == 2) { dwconv_strip_f32w_kernel<5, 5, 2, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
-    }
-    if (out.w >= 32 && e.res == nullptr && wh != nullptr && g.sw == 1 && !getenv("B200OCR_DW_S4")) {
-      // long rows: 8 outputs per thread (17 instead of 26 loads per 8 outputs and filter row for 5x5)
-      constexpr int S8 = 8;
-      const long st8 = long(out.n) * out.h * ((out.w + S8 - 1) / S8) * ((out.c + 7) / 8);
-      const int sg8 = grid_for(st8);
-      if (g.kh == 3 && g.kw == 3) { dwconv_strip_kernel<3, 3, 1, S8><<<sg8, kThreads, 0, s>>>(in, out, wb, wh, g, e, vw); return; }
-      if (g.kh == 5 && g.kw == 5) { dwconv_strip_kernel<5, 5, 1, S8><<<sg8, kThreads, 0, s>>>(in, out, wb, wh, g, e, vw); return; }
     }
     if (out.w >= 2 * S && e.res == nullptr && wh != nullptr) {
       if (g.kh == 3 && g.kw == 3 && g.sw == 1) { dwconv_strip_kernel<3, 3, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, wh, g, e, vw); return; }
