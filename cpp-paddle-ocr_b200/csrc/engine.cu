@@ -215,7 +215,7 @@ static TV make_tv(uint8_t* arena, const Plan& plan, const std::vector<size_t>& b
   return v;
 }
 
-__half* Net::prepare(int n, int h, int w, const int* widths) {
+__half* Net::prepare(int n, int h, int w, const int* widths, cudaStream_t stream) {
   if (n < 1 || h < 1 || w < 1) throw std::runtime_error("Net::prepare: empty input");
   ragged_ = false;
   if (widths) {
@@ -231,7 +231,7 @@ __half* Net::prepare(int n, int h, int w, const int* widths) {
       const size_t nt = plan_.tensors.size(), need = nt * size_t(n);
       cuda_check(cudaSetDevice(device_), "cudaSetDevice");
       if (need > vw_cap_) {
-        cuda_check(cudaDeviceSynchronize(), "sync before table growth");
+        cuda_check(cudaStreamSynchronize(stream), "sync before table growth");
         cudaFree(vw_dev_);
         free(vw_pin_);
         vw_cap_ = need + need / 2;
@@ -261,7 +261,7 @@ __half* Net::prepare(int n, int h, int w, const int* widths) {
   if (I->need > arena_bytes_) {
     // grow the shared arena; every cached instance holds pointers into the old one
     const size_t need = I->need;
-    cuda_check(cudaDeviceSynchronize(), "sync before arena growth");
+    cuda_check(cudaStreamSynchronize(stream), "sync before arena growth");
     cache_.clear();
     cudaFree(arena_);
     arena_ = nullptr;
@@ -311,9 +311,9 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
         break;
       }
       case LKind::DwConv:
-        // the detector keeps fp32 depthwise weights: its output is thresholded pixel by pixel and has to stay
-        // within 1e-2 of the fp32 reference; rec / cls take the FHFMA kernel (fp16 weights), ~1.5x faster
-        launch_dwconv(tv(L.in), tv(L.out), d_wf_ + L.wf_off, plan_.kind == "det" ? nullptr : d_wh_ + L.wh_off, g, e, s,
+        // the detector and the classifier keep fp32 depthwise weights: their outputs (thresholded probability map,
+        // soft-max score) have to stay within 1e-2 of the fp32 reference; rec takes the FHFMA kernel (fp16 weights)
+        launch_dwconv(tv(L.in), tv(L.out), d_wf_ + L.wf_off, plan_.kind == "rec" ? d_wh_ + L.wh_off : nullptr, g, e, s,
                       vwp(L.out));
         break;
       case LKind::Gap: launch_gap_partial(tv(L.in), vecp(L.out), I.splits[L.out], s); break;

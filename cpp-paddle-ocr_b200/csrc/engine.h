@@ -46,7 +46,9 @@ class Net {
   // treats the columns beyond a row's (layer-scaled) width as the zero padding it would see at the edge of a
   // tensor of that width, so each row's result is bit-identical to running it in a dense batch of its own
   // width.  The caller must write zeros into the input beyond widths[i].  Sequence graphs (rec) only.
-  __half* prepare(int n, int h, int w, const int* widths = nullptr);
+  // `stream`: the stream this net's work is queued on; it is synchronised (never the whole device: another worker may
+  // be capturing a CUDA graph) before memory that queued work may still use is released.
+  __half* prepare(int n, int h, int w, const int* widths = nullptr, cudaStream_t stream = nullptr);
   // Execute the forward pass for the last prepared shape on `stream`.
   //   det: `thresh_u8` >= 0 also writes the thresholded bitmap.
   void run(cudaStream_t stream, int thresh_u8 = -1);

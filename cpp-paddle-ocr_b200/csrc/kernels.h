@@ -48,6 +48,9 @@ void launch_conv_tc(const ConvTcPlan& p, const float* bias, const Epi& e, cudaSt
 // nullptr to multiply with the fp32 weights (conversion + FFMA: slower, one rounding less)
 void launch_dwconv(const TV& in, const TV& out, const float* w_bias, const __half* w_half, const ConvGeom& g,
                    const Epi& e, cudaStream_t s, const int* vw = nullptr);
+// shared-memory tiled variant (dwconv.cu): 3x3 / 5x5, strides 1|2; false = shape not covered, nothing launched
+bool launch_dwconv_tile(const TV& in, const TV& out, const float* w_bias, const __half* w_half, const ConvGeom& g,
+                        const Epi& e, cudaStream_t s, const int* vw);
 
 // ---- SE block ---------------------------------------------------------------
 int gap_splits(int h);

@@ -872,6 +872,7 @@ void launch_conv_simt(const TV& in, const TV& out, const __half* w, const float*
 
 void launch_dwconv(const TV& in, const TV& out, const float* wb, const __half* wh, const ConvGeom& g, const Epi& e,
                    cudaStream_t s, const int* vw) {
+  if (launch_dwconv_tile(in, out, wb, wh, g, e, s, vw)) return;
   {
     // register-blocked strips along x whenever the row is long enough to fill them
     constexpr int S = 4;

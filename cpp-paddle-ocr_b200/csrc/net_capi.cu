@@ -85,7 +85,7 @@ static int net_forward_impl(b200ocr_net_t h, const float* nchw, int n, int heigh
   return capi_guard([&] {
     if (!h || !nchw) throw std::invalid_argument("null argument");
     Net& net = *h->net;
-    __half* in = net.prepare(n, height, width, widths);
+    __half* in = net.prepare(n, height, width, widths, h->stream);
     const size_t bytes = size_t(n) * 3 * height * width * sizeof(float);
     if (bytes > h->d_in_bytes) {
       cudaFree(h->d_in);

@@ -374,8 +374,9 @@ int b200ocr_batch_upload(int device, const b200ocr_image* imgs, int n, b200ocr_b
       if (!imgs[i].data || imgs[i].rows <= 0 || imgs[i].cols <= 0) throw std::invalid_argument("empty image");
       hi[i] = to_host(imgs[i]);
     }
-    h->b.upload(hi.data(), n, nullptr);
-    cuda_check(cudaDeviceSynchronize(), "batch upload");
+    // per-thread stream: never a device-wide synchronisation (another worker may be capturing a CUDA graph)
+    h->b.upload(hi.data(), n, cudaStreamPerThread);
+    cuda_check(cudaStreamSynchronize(cudaStreamPerThread), "batch upload");
     *out = h.release();
   });
 }

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -18,17 +19,18 @@ double ms_since(Clock::time_point t0) { return std::chrono::duration<double, std
 
 // ------------------------------------------------------------------------------------------------ buffers
 DevBuf::~DevBuf() {
-  if (!p) return;
-  if (pinned) cudaFreeHost(p); else cudaFree(p);
+  if (p) retired_.push_back(p);
+  for (void* q : retired_) {
+    if (pinned) cudaFreeHost(q); else cudaFree(q);
+  }
 }
 void DevBuf::ensure(size_t bytes) {
   if (bytes <= cap) return;
   if (p) {
-    cuda_check(cudaDeviceSynchronize(), "sync before buffer growth");
-    if (pinned) cudaFreeHost(p); else cudaFree(p);
+    retired_.push_back(p);
     p = nullptr;
   }
-  size_t want = std::max(bytes + bytes / 2, size_t(4096));
+  size_t want = std::max(bytes * 2, size_t(4096));  // doubling keeps the retired allocations below the live one
   if (pinned) cuda_check(cudaMallocHost(&p, want), "cudaMallocHost");
   else cuda_check(cudaMalloc(&p, want), "cudaMalloc");
   cap = want;
@@ -125,7 +127,7 @@ void DetStage::run_group(const std::vector<DevImg>& imgs, const std::vector<int>
     inf.src_h = im.rows; inf.src_w = im.cols;
     h_info_.as<DbImageInfo>()[k] = inf;
   }
-  __half* in = net_.prepare(n, rh, rw);
+  __half* in = net_.prepare(n, rh, rw, nullptr, s);
   cuda_check(cudaMemcpyAsync(items_.p, h_items_.p, sizeof(DetPreItem) * n, cudaMemcpyHostToDevice, s), "det items");
   cuda_check(cudaMemcpyAsync(info_.p, h_info_.p, sizeof(DbImageInfo) * n, cudaMemcpyHostToDevice, s), "det info");
   static const float mean[3] = {0.485f, 0.456f, 0.406f};                     // reference ocr_det.h:121
@@ -255,7 +257,7 @@ void ClsStage::run(const std::vector<DevImg>& imgs, const std::vector<Roi>& rois
   for (int b0 = 0; b0 < n; b0 += max_batch) {
     const int nb = std::min(max_batch, n - b0);
     auto t0 = Clock::now();
-    __half* in = net_.prepare(nb, 48, 192);
+    __half* in = net_.prepare(nb, 48, 192, nullptr, s);
     // pad value 0.0: the classifier pads AFTER normalisation (src/ocr_cls.cpp:52-56)
     launch_crop_preprocess(items_.as<CropItem>() + b0, nb, 48, 192, make_norm(kMean05, kScale2), 0.f, in, s);
     t[0] += ms_since(t0);
@@ -388,7 +390,7 @@ void RecStage::run(const std::vector<DevImg>& imgs, const std::vector<std::vecto
     long sum_w = 0;
     while (e < rows.size() && int(e - b0) < max_rows) {
       const long w_new = rows[e].width;
-      if (e > b0 && (sum_w + w_new) * 4 < 3 * long(e - b0 + 1) * w_new) break;  // fill ratio would drop below 75 %
+      if (e > b0 && double(sum_w + w_new) < min_fill * double(long(e - b0 + 1) * w_new)) break;  // too much padding
       if (e > b0 && long(e - b0 + 1) * w_new > max_cols) break;
       sum_w += w_new;
       ++e;
@@ -398,6 +400,9 @@ void RecStage::run(const std::vector<DevImg>& imgs, const std::vector<std::vecto
     chunks.push_back(ch);
     b0 = e;
   }
+  last_chunks = int(chunks.size()); last_cols = 0; last_real_cols = 0;
+  for (const Chunk& ch : chunks) last_cols += long(ch.nb) * ch.wmax;
+  for (const Row& r : rows) last_real_cols += r.width;
   t[0] += ms_since(t0);
   t0 = Clock::now();
   h_items_.ensure(sizeof(CropItem) * std::max<size_t>(rows.size(), 1));
@@ -417,7 +422,7 @@ void RecStage::run(const std::vector<DevImg>& imgs, const std::vector<std::vecto
   for (Chunk& ch : chunks) {
     widths.resize(ch.nb);
     for (int k = 0; k < ch.nb; ++k) widths[k] = rows[ch.b0 + k].width;
-    __half* in = net_.prepare(ch.nb, img_h_, ch.wmax, widths.data());
+    __half* in = net_.prepare(ch.nb, img_h_, ch.wmax, widths.data(), s);
     // pad value -1.0: CrnnResizeImg pads with u8 zeros BEFORE normalisation (src/preprocess_op.cpp:115-117)
     launch_crop_preprocess(items_.as<CropItem>() + ch.b0, ch.nb, img_h_, ch.wmax, make_norm(kMean05, kScale2), -1.f, in, s);
     net_.run(s);
@@ -527,6 +532,12 @@ Worker::Worker(int worker_id, const std::string& model_dir, int device, const Wo
   det_ = std::make_unique<DetStage>(model_dir + "/det", device, dp);
   if (opt.enable_cls) cls_ = std::make_unique<ClsStage>(model_dir + "/cls", device, 8, 0.98f);
   rec_ = std::make_unique<RecStage>(model_dir + "/rec", device, model_dir + "/rec/ppocr_keys_v1.txt", 16, 28, 192);
+  // tuning knobs (launch granularity only; results do not depend on them)
+  if (const char* v = getenv("B200OCR_DET_MAX_BATCH")) det_->max_batch = std::max(1, atoi(v));
+  if (const char* v = getenv("B200OCR_CLS_MAX_BATCH")) { if (cls_) cls_->max_batch = std::max(1, atoi(v)); }
+  if (const char* v = getenv("B200OCR_REC_MAX_COLS")) rec_->max_cols = std::max(1000L, atol(v));
+  if (const char* v = getenv("B200OCR_REC_MAX_ROWS")) rec_->max_rows = std::max(1, atoi(v));
+  if (const char* v = getenv("B200OCR_REC_FILL")) rec_->min_fill = std::min(1.0, std::max(0.1, atof(v)));
 }
 
 Worker::~Worker() {
@@ -542,7 +553,11 @@ void Worker::run_device(const std::vector<DevImg>& dimgs, std::vector<std::vecto
   const int nb = int(dimgs.size());
   words->assign(nb, {});
   std::vector<std::vector<Box>> boxes;
-  det_->run(dimgs, &boxes, stream_);
+  static const bool trace = getenv("B200OCR_TRACE") != nullptr;  // host wall time per phase, to stderr
+  const auto t_begin = Clock::now();
+  std::vector<double> t_det, t_cls, t_rec;
+  det_->run(dimgs, &boxes, stream_, trace ? &t_det : nullptr);
+  const double ms_det = ms_since(t_begin);
   // ROI = cv::boundingRect(points) & image (src/ocr_worker.cpp:244-259); boundingRect of integer-valued
   // float points is (minx, miny, maxx - minx + 1, maxy - miny + 1)
   std::vector<std::vector<Roi>> calls(nb);
@@ -560,13 +575,23 @@ void Worker::run_device(const std::vector<DevImg>& dimgs, std::vector<std::vecto
       r.img = i; r.x = x0; r.y = y0; r.w = x1 - x0; r.h = y1 - y0;
       if (r.w > 0 && r.h > 0) { calls[i].push_back(r); all.push_back(r); }
     }
+  const double ms_roi = ms_since(t_begin);
   if (cls_ && !all.empty()) {
-    cls_->run(dimgs, all, nullptr, nullptr, stream_, /*fetch_to_host=*/false);
+    cls_->run(dimgs, all, nullptr, nullptr, stream_, /*fetch_to_host=*/false, trace ? &t_cls : nullptr);
     cls_->rotate_rois(dimgs, all, stream_);
   }
+  const double ms_cls = ms_since(t_begin);
   std::vector<std::vector<std::string>> texts;
   std::vector<std::vector<float>> scores;
-  rec_->run(dimgs, calls, &texts, &scores, stream_);
+  rec_->run(dimgs, calls, &texts, &scores, stream_, trace ? &t_rec : nullptr);
+  if (trace) {
+    auto v = [](const std::vector<double>& t, int i) { return int(t.size()) > i ? t[i] : 0.0; };
+    fprintf(stderr, "[b200ocr trace] worker %d: %d images, %zu rois | det %.2f (pre %.2f net %.2f post+sync %.2f) roi %.2f "
+            "cls-enqueue %.2f (pre %.2f net %.2f post %.2f) rec %.2f (plan %.2f run+sync %.2f decode %.2f) ms; rec chunks %d, cols %ld (real %ld)\n",
+            worker_id_, nb, all.size(), ms_det, v(t_det, 0), v(t_det, 1), v(t_det, 2), ms_roi - ms_det, ms_cls - ms_roi,
+            v(t_cls, 0), v(t_cls, 1), v(t_cls, 2), ms_since(t_begin) - ms_cls, v(t_rec, 0), v(t_rec, 1), v(t_rec, 2),
+            rec_->last_chunks, rec_->last_cols, rec_->last_real_cols);
+  }
   for (int i = 0; i < nb; ++i) {
     std::vector<WordOut>& w = (*words)[i];
     // words[i] = (rec_texts[i], rec_scores[i], det_boxes[i])  (src/ocr_worker.cpp:293-300)

@@ -28,8 +28,13 @@ struct DevBuf {
   ~DevBuf();
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
+  // Grows the buffer (contents are NOT kept).  The old allocation may still be read by work queued on the owner's
+  // stream, and a device-wide synchronisation is not allowed while another worker's stream is being captured into a
+  // CUDA graph, so it is only retired here and freed with the object.
   void ensure(size_t bytes);
   template <class T> T* as() const { return static_cast<T*>(p); }
+ private:
+  std::vector<void*> retired_;
 };
 
 struct HostImage {  // what cv::Mat::data / rows / cols / step describe (8-bit BGR)
@@ -123,6 +128,8 @@ class RecStage {
   Net& net() { return net_; }
   int max_rows = 1024;       // rows per forward pass
   long max_cols = 400000;    // rows x padded width per forward pass (bounds the activation arena)
+  int last_chunks = 0; long last_cols = 0, last_real_cols = 0;  // trace: ragged chunking of the last run()
+  double min_fill = 0.75;    // a ragged chunk is cut where its real columns / (rows x widest row) would drop below this
   long launches = 0;
  private:
   Net net_;
