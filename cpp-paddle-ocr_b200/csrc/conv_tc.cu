@@ -100,9 +100,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 template <int ACT>
 __device__ __forceinline__ float act_fn(float v, float a, float b) {
   if (ACT == 1) return fmaxf(v, 0.f);
-  if (ACT == 2) return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  if (ACT == 2) return v * __saturatef(fmaf(v, 1.f / 6.f, 0.5f));  // x * relu6(x + 3) / 6: one FFMA.SAT + one FMUL
   if (ACT == 3) return v / (1.f + __expf(-v));
-  if (ACT == 4) return fminf(fmaxf(v * a + b, 0.f), 1.f);
+  if (ACT == 4) return __saturatef(fmaf(v, a, b));
   if (ACT == 5) return 1.f / (1.f + __expf(-v));
   return v;
 }
@@ -129,8 +129,8 @@ struct ConvTcArgs {
 
 // Drain one accumulator tile: the calling warp owns TMEM lanes 32*(warp%4) .. +31 (row r of the tile = lane of D).
 template <int ACT>
-__device__ __forceinline__ void epilogue_tile(const ConvTcArgs& a, uint32_t tmem_base, int x0, int y0, int n0, int nblk,
-                                              int warp, int lane) {
+__device__ __forceinline__ void epilogue_tile(const ConvTcArgs& a, const float* __restrict__ bias_blk, uint32_t tmem_base,
+                                              int x0, int y0, int n0, int nblk, int warp, int lane) {
   const int q = warp & 3;               // TMEM lane quadrant this warp may read (hardware rule: warp id % 4)
   const int cgrp = (warp - 2) >> 2;     // which share of the 16-column groups
   const int r = q * 32 + lane;
@@ -150,10 +150,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& a, uint32_t tmem
     if (!valid || c0 >= c8lim) continue;
     float f[16];
     {
-      const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);  // bias is padded to a multiple of 16
+      const float4* bp = reinterpret_cast<const float4*>(bias_blk + col);  // bias is padded to a multiple of 16
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const float4 b = __ldg(bp + g);
+        const float4 b = bp[g];
         f[4 * g] = __uint_as_float(v[4 * g]) + b.x;
         f[4 * g + 1] = __uint_as_float(v[4 * g + 1]) + b.y;
         f[4 * g + 2] = __uint_as_float(v[4 * g + 2]) + b.z;
@@ -284,7 +284,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    epilogue_tile<ACT>(a, tmem_base, x0, y0, n0, nblk, warp, lane);
+    epilogue_tile<ACT>(a, a.bias + nblk * a.bn, tmem_base, x0, y0, n0, nblk, warp, lane);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -311,13 +311,16 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* t_full = a_empty + kStagesMax;  // [2]
   uint64_t* t_empty = t_full + 2;           // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
-  const uint32_t tiles_base = (smem_u32(smem_raw) + 256 + 1023) & ~1023u;
+  float* sbias = reinterpret_cast<float*>(smem_raw + 256);  // this N tile's folded bias (<= 256 floats), read by every tile
+  const uint32_t tiles_base = (smem_u32(smem_raw) + 256 + 1024 + 1023) & ~1023u;
   uint8_t* tiles = smem_raw + (tiles_base - smem_u32(smem_raw));
   const int b_chunk = a.bn * 128;
   const uint32_t a_ring = uint32_t(kt) * b_chunk;  // offset of the A ring behind the resident filter
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = blockIdx.y;
   const int kchunks = (a.cin + 63) >> 6;
+  for (int i = threadIdx.x; i < a.bn; i += blockDim.x)
+    sbias[i] = nblk * a.bn + i < ((a.cout + 15) & ~15) ? a.bias[nblk * a.bn + i] : 0.f;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -396,7 +399,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int buf = lt & 1;
       mbar_wait(&t_full[buf], uint32_t(lt >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      epilogue_tile<ACT>(a, tmem_base + uint32_t(buf * a.tmem_cols), tx * a.tw, ty * a.th, t * a.tn, nblk, warp, lane);
+      epilogue_tile<ACT>(a, sbias, tmem_base + uint32_t(buf * a.tmem_cols), tx * a.tw, ty * a.th, t * a.tn, nblk, warp, lane);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&t_empty[buf]);
     }
@@ -527,7 +530,7 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
     const int m_tiles = a.tiles_x * a.tiles_y * tiles_n;
     const size_t b_bytes = size_t(k_iters) * a.bn * 128;
     const int st = k_iters < kStagesMax ? (k_iters < 2 ? 2 : k_iters) : kStagesMax;
-    const size_t need = b_bytes + size_t(st) * kATileBytes + 1024 + 256;
+    const size_t need = b_bytes + size_t(st) * kATileBytes + 1024 + 1024 + 256;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -74,6 +74,10 @@ void launch_layernorm(const TV& in, const TV& out, const float* gamma_beta, floa
 void launch_attention(const TV& qkv, const TV& out, int heads, int head_dim, float scale, cudaStream_t s,
                       const int* vw = nullptr);
 
+// tensor-core variant (attention.cu); false = shape not covered, nothing launched
+bool launch_attention_mma(const TV& qkv, const TV& out, int heads, int head_dim, float scale, cudaStream_t s,
+                          const int* vw);
+
 // ---- heads ----------------------------------------------------------------------
 // DB head tail: deconv2x2+BN+relu -> deconv2x2 -> sigmoid, plus cbuf=(u8)(p*255) > thresh bitmap.
 void launch_dbhead(const TV& in, const float* blk, int cmid, float* prob, uint8_t* bitmap,

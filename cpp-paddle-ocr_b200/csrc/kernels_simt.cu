@@ -16,9 +16,9 @@ constexpr int kThreads = 256;
 __device__ __forceinline__ float apply_act(float v, int act, float a, float b) {
   switch (act) {
     case 1: return fmaxf(v, 0.f);
-    case 2: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    case 2: return v * __saturatef(fmaf(v, 1.f / 6.f, 0.5f));  // x * relu6(x + 3) / 6: one FFMA.SAT + one FMUL
     case 3: return v / (1.f + __expf(-v));
-    case 4: return fminf(fmaxf(v * a + b, 0.f), 1.f);
+    case 4: return __saturatef(fmaf(v, a, b));
     case 5: return 1.f / (1.f + __expf(-v));
     default: return v;
   }
@@ -49,7 +49,23 @@ __device__ __forceinline__ H8 ld8(const __half* p) {
 }
 __device__ __forceinline__ void st8(__half* p, const H8& v) { *reinterpret_cast<uint4*>(p) = v.u; }
 
-// Shared epilogue for 8 consecutive channels starting at c0 of pixel `pix`.
+template <int ACT>
+__device__ __forceinline__ float act_t(float v, float a, float b) {
+  if (ACT == 1) return fmaxf(v, 0.f);
+  if (ACT == 2) return v * __saturatef(fmaf(v, 1.f / 6.f, 0.5f));
+  if (ACT == 3) return v / (1.f + __expf(-v));
+  if (ACT == 4) return __saturatef(fmaf(v, a, b));
+  if (ACT == 5) return 1.f / (1.f + __expf(-v));
+  return v;
+}
+template <int ACT>
+__device__ __forceinline__ void epilogue8_act(float* acc, const float* bias, int c0, const Epi& e) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = fmaf(e.s2, act_t<ACT>(acc[i] + bias[c0 + i], e.a, e.b), e.t2);
+}
+
+// Shared epilogue for 8 consecutive channels starting at c0 of pixel `pix`.  The activation is selected ONCE per
+// call (a per-element switch compiles to an indirect branch per value).
 __device__ __forceinline__ void epilogue8(float* acc, const float* bias, int c0, int cout, const Epi& e,
                                           const TV& out, long pix, bool masked = false) {
   if (masked) {  // ragged batch: beyond this row's valid width the tensor is zero
@@ -58,14 +74,24 @@ __device__ __forceinline__ void epilogue8(float* acc, const float* bias, int c0,
     st8(out.p + pix * out.pitch + c0, z);
     return;
   }
-  float r[8];
-  if (e.res) ld8(e.res + pix * e.res_pitch + c0).to_float(r);
+  switch (e.act) {
+    case 1: epilogue8_act<1>(acc, bias, c0, e); break;
+    case 2: epilogue8_act<2>(acc, bias, c0, e); break;
+    case 3: epilogue8_act<3>(acc, bias, c0, e); break;
+    case 4: epilogue8_act<4>(acc, bias, c0, e); break;
+    case 5: epilogue8_act<5>(acc, bias, c0, e); break;
+    default: epilogue8_act<0>(acc, bias, c0, e); break;
+  }
+  if (e.res) {
+    float r[8];
+    ld8(e.res + pix * e.res_pitch + c0).to_float(r);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float v = acc[i] + bias[c0 + i];
-    v = e.s2 * apply_act(v, e.act, e.a, e.b) + e.t2;
-    if (e.res) v += r[i];
-    acc[i] = (c0 + i < cout) ? v : 0.f;
+    for (int i = 0; i < 8; ++i) acc[i] += r[i];
+  }
+  if (c0 + 8 > cout) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (c0 + i >= cout) acc[i] = 0.f;
   }
   H8 o;
   o.from_float(acc);
@@ -356,6 +382,114 @@ stem_conv_kernel(TV in, TV out, const __half* __restrict__ w, const float* __res
   }
 }
 
+template <int COUT, int ACT>
+__device__ __forceinline__ void stem_store(float (*acc)[COUT], const float* sb, const Epi& e, const TV& out, long pix0, int ox0,
+                                           int vwn) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int ox = ox0 + p;
+    if (ox >= out.w) break;
+    __half* op = out.p + (pix0 + p) * out.pitch;
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += 8) {
+      H8 o;
+      if (ox >= vwn) {
+        o.u = make_uint4(0, 0, 0, 0);
+      } else {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i] = fmaf(e.s2, act_t<ACT>(acc[p][c0 + i] + sb[c0 + i], e.a, e.b), e.t2);
+          if (c0 + i >= out.c) v[i] = 0.f;
+        }
+        o.from_float(v);
+      }
+      st8(op + c0, o);
+    }
+  }
+}
+
+// First layer, stride 2: one thread = 4 consecutive output pixels x all COUT channels.  Per filter row the thread
+// loads its 9 input pixels once (8 B each: 3 of the 8 channel slots are real) and every filter tap's COUT weights
+// come from shared memory as broadcast 16-byte loads shared by the 4 pixels: 27 * COUT / 4 shared loads per
+// 4 * 27 * COUT multiply-adds (the one-pixel kernel above issues one shared load per multiply-add).
+template <int COUT>
+__global__ void __launch_bounds__(128, 3)
+stem_conv_s2x4_kernel(TV in, TV out, const __half* __restrict__ w, const float* __restrict__ bias, ConvGeom g, Epi e,
+                      const int* __restrict__ vw) {
+  __shared__ __align__(16) float sw[9 * 3 * COUT];
+  __shared__ float sb[COUT];
+  for (int i = threadIdx.x; i < 9 * 3 * COUT; i += blockDim.x) {
+    const int co = i % COUT, ci = (i / COUT) % 3, tap = i / (3 * COUT);
+    sw[i] = __half2float(w[(long(co) * 9 + tap) * g.cin_pad + ci]);
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
+  __syncthreads();
+  const int strips = (out.w + 3) >> 2;
+  const long total = long(out.n) * out.h * strips;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const int sx = int(t % strips);
+    const int oy = int((t / strips) % out.h);
+    const int n = int(t / (long(strips) * out.h));
+    const int ox0 = sx * 4;
+    const int ix0 = ox0 * 2 - g.pw;
+    float acc[4][COUT];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int i = 0; i < COUT; ++i) acc[p][i] = 0.f;
+    // all 27 input pixels are requested before the first multiply-add (one round trip to memory per thread)
+    uint2 raw[3][9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - g.ph + ky;
+      const bool y_ok = iy >= 0 && iy < in.h;
+      const __half* row = in.p + (long(n) * in.h + (y_ok ? iy : 0)) * in.w * in.pitch;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const int ix = ix0 + j;
+        raw[ky][j] = make_uint2(0u, 0u);
+        if (y_ok && ix >= 0 && ix < in.w) raw[ky][j] = *reinterpret_cast<const uint2*>(row + long(ix) * in.pitch);
+      }
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      float x[9][3];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const float2 ab = __half22float2(*reinterpret_cast<const __half2*>(&raw[ky][j].x));
+        x[j][0] = ab.x; x[j][1] = ab.y;
+        x[j][2] = __half2float(*reinterpret_cast<const __half*>(&raw[ky][j].y));
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float4* wp = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * 3 + ci) * COUT);
+#pragma unroll
+          for (int q = 0; q < COUT / 4; ++q) {
+            const float4 wv = wp[q];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              const float xv = x[2 * p + kx][ci];
+              acc[p][4 * q] = fmaf(xv, wv.x, acc[p][4 * q]);
+              acc[p][4 * q + 1] = fmaf(xv, wv.y, acc[p][4 * q + 1]);
+              acc[p][4 * q + 2] = fmaf(xv, wv.z, acc[p][4 * q + 2]);
+              acc[p][4 * q + 3] = fmaf(xv, wv.w, acc[p][4 * q + 3]);
+            }
+          }
+        }
+    }
+    const int vwn = vw ? vw[n] : out.w;
+    const long pix0 = (long(n) * out.h + oy) * out.w + ox0;
+    switch (e.act) {  // one activation dispatch per thread, not per value
+      case 1: stem_store<COUT, 1>(acc, sb, e, out, pix0, ox0, vwn); break;
+      case 2: stem_store<COUT, 2>(acc, sb, e, out, pix0, ox0, vwn); break;
+      default: stem_store<COUT, 0>(acc, sb, e, out, pix0, ox0, vwn); break;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- SE block
 // partial[n][split][cp] = sum over the split's pixels (fp32, fixed order -> deterministic)
 __global__ void __launch_bounds__(kThreads)
@@ -394,43 +528,98 @@ gap_partial_kernel(TV in, float* __restrict__ partial, int splits) {
 }
 
 // blk: w1[cmid][c], b1[cmid], w2[c][cmid], b2[c]
+template <int kSeSamples>
 __global__ void __launch_bounds__(kThreads)
-se_fc_kernel(const float* __restrict__ partial, int splits, float inv_hw, int c, int cmid,
+se_fc_kernel(const float* __restrict__ partial, int splits, float inv_hw0, int n_total, int c, int cmid,
              const float* __restrict__ blk, float slope, float offset, float* __restrict__ gate,
              const int* __restrict__ vw_in, int h) {
+  // One block = kSeSamples consecutive samples: the two small matrices (c x cmid floats each) are read once per
+  // block instead of once per sample; one thread owns one output neuron of all its samples (no reductions).
+  // blk: w1t[c][cmid], b1[cmid], w2t[cmid][c], b2[c].
   extern __shared__ float sm[];
   const int cp = (c + 7) / 8 * 8;
-  float* pooled = sm;        // [cp]
-  float* hidden = sm + cp;   // [cmid]
-  const int n = blockIdx.x;
-  if (vw_in) inv_hw = 1.f / float(h * vw_in[n]);
-  for (int i = threadIdx.x; i < cp; i += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += partial[(long(n) * splits + k) * cp + i];
-    pooled[i] = s * inv_hw;
-  }
-  __syncthreads();
-  const float* w1 = blk;
-  const float* b1 = w1 + long(cmid) * c;
-  const float* w2 = b1 + cmid;
-  const float* b2 = w2 + long(c) * cmid;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int m = warp; m < cmid; m += nwarps) {
-    float s = 0.f;
-    for (int i = lane; i < c; i += 32) s = fmaf(w1[long(m) * c + i], pooled[i], s);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) hidden[m] = fmaxf(s + b1[m], 0.f);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < cp; i += blockDim.x) {
+  float* pooled = sm;                      // [kSeSamples][cp]
+  float* hidden = sm + kSeSamples * cp;    // [kSeSamples][cmid]
+  const int n0 = blockIdx.x * kSeSamples;
+  const int ns = min(kSeSamples, n_total - n0);
+  for (int t = threadIdx.x; t < kSeSamples * cp; t += blockDim.x) {
+    const int sidx = t / cp, i = t - sidx * cp;
     float v = 0.f;
-    if (i < c) {
-      float s = b2[i];
-      for (int m = 0; m < cmid; ++m) s = fmaf(w2[long(i) * cmid + m], hidden[m], s);
-      v = fminf(fmaxf(s * slope + offset, 0.f), 1.f);
+    if (sidx < ns) {
+      const int n = n0 + sidx;
+      const float inv_hw = vw_in ? 1.f / float(h * vw_in[n]) : inv_hw0;
+      float s = 0.f;
+      for (int k = 0; k < splits; ++k) s += partial[(long(n) * splits + k) * cp + i];
+      v = s * inv_hw;
     }
-    gate[long(n) * cp + i] = v;
+    pooled[t] = v;
+  }
+  __syncthreads();
+  const float* w1t = blk;
+  const float* b1 = w1t + long(cmid) * c;
+  const float* w2t = b1 + cmid;
+  const float* b2 = w2t + long(c) * cmid;
+  // fc1: thread = (half of the input channels, hidden neuron); 8 independent weight loads in flight per thread
+  float* part = hidden + kSeSamples * cmid;  // [2][kSeSamples][cmid] partial sums
+  for (int t = threadIdx.x; t < 2 * cmid; t += blockDim.x) {
+    const int half = t / cmid, m = t - half * cmid;
+    const int i0 = half * (c / 2), i1 = half ? c : c / 2;
+    float a[kSeSamples];
+#pragma unroll
+    for (int q = 0; q < kSeSamples; ++q) a[q] = 0.f;
+    int i = i0;
+    for (; i + 8 <= i1; i += 8) {
+      float w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = __ldg(w1t + long(i + u) * cmid + m);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int q = 0; q < kSeSamples; ++q) a[q] = fmaf(w[u], pooled[q * cp + i + u], a[q]);
+    }
+    for (; i < i1; ++i) {
+      const float w = __ldg(w1t + long(i) * cmid + m);
+#pragma unroll
+      for (int q = 0; q < kSeSamples; ++q) a[q] = fmaf(w, pooled[q * cp + i], a[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < kSeSamples; ++q) part[(half * kSeSamples + q) * cmid + m] = a[q];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < kSeSamples * cmid; t += blockDim.x) {
+    const int m = t % cmid;
+    hidden[t] = fmaxf(part[t] + part[kSeSamples * cmid + t] + b1[m], 0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cp; i += blockDim.x) {
+    float a[kSeSamples];
+#pragma unroll
+    for (int q = 0; q < kSeSamples; ++q) a[q] = 0.f;
+    if (i < c) {
+      const float bb = b2[i];
+#pragma unroll
+      for (int q = 0; q < kSeSamples; ++q) a[q] = bb;
+      int m = 0;
+      for (; m + 8 <= cmid; m += 8) {
+        float w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = __ldg(w2t + long(m + u) * c + i);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int q = 0; q < kSeSamples; ++q) a[q] = fmaf(w[u], hidden[q * cmid + m + u], a[q]);
+      }
+      for (; m < cmid; ++m) {
+        const float w = __ldg(w2t + long(m) * c + i);
+#pragma unroll
+        for (int q = 0; q < kSeSamples; ++q) a[q] = fmaf(w, hidden[q * cmid + m], a[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < kSeSamples; ++q) a[q] = __saturatef(fmaf(a[q], slope, offset));
+    }
+#pragma unroll
+    for (int q = 0; q < kSeSamples; ++q)
+      if (q < ns) gate[long(n0 + q) * cp + i] = a[q];
   }
 }
 
@@ -861,6 +1050,12 @@ inline int grid_for(long total, int threads = kThreads) {
 void launch_conv_simt(const TV& in, const TV& out, const __half* w, const float* bias,
                       const ConvGeom& g, const Epi& e, cudaStream_t s, const int* vw) {
   if (in.c == 3 && in.pitch == 8 && g.kh == 3 && g.kw == 3 && e.res == nullptr && (out.c == 8 || out.c == 16)) {
+    if (g.sh == 2 && g.sw == 2 && out.w >= 8 && e.act >= 0 && e.act <= 2 && !getenv("B200OCR_OLD_STEM")) {
+      const int sg = grid_for(long(out.n) * out.h * ((out.w + 3) / 4), 128);
+      if (out.c == 16) stem_conv_s2x4_kernel<16><<<sg, 128, 0, s>>>(in, out, w, bias, g, e, vw);
+      else stem_conv_s2x4_kernel<8><<<sg, 128, 0, s>>>(in, out, w, bias, g, e, vw);
+      return;
+    }
     const int grid = grid_for(long(out.n) * out.h * out.w);
     if (out.c == 16) stem_conv_kernel<16><<<grid, kThreads, 0, s>>>(in, out, w, bias, g, e, vw);
     else stem_conv_kernel<8><<<grid, kThreads, 0, s>>>(in, out, w, bias, g, e, vw);
@@ -914,8 +1109,13 @@ void launch_gap_partial(const TV& in, float* partial, int splits, cudaStream_t s
 void launch_se_fc(const float* partial, int splits, int hw, int n, int c, int cmid, const float* blk,
                   float slope, float offset, float* gate, cudaStream_t s, const int* vw_in, int h) {
   const int cp = (c + 7) / 8 * 8;
-  se_fc_kernel<<<n, kThreads, (cp + cmid) * sizeof(float), s>>>(partial, splits, 1.f / float(hw), c, cmid,
-                                                                 blk, slope, offset, gate, vw_in, h);
+  // samples per block: share the weight reads between samples once there are enough samples to fill the SMs
+  const int S = n >= 4 * 148 ? 4 : (n >= 2 * 148 ? 2 : 1);
+  const size_t smem = size_t(S) * (cp + 3 * cmid) * sizeof(float);
+  const float inv = 1.f / float(hw);
+  if (S == 4) se_fc_kernel<4><<<(n + 3) / 4, kThreads, smem, s>>>(partial, splits, inv, n, c, cmid, blk, slope, offset, gate, vw_in, h);
+  else if (S == 2) se_fc_kernel<2><<<(n + 1) / 2, kThreads, smem, s>>>(partial, splits, inv, n, c, cmid, blk, slope, offset, gate, vw_in, h);
+  else se_fc_kernel<1><<<n, kThreads, smem, s>>>(partial, splits, inv, n, c, cmid, blk, slope, offset, gate, vw_in, h);
 }
 
 void launch_scale(const TV& in, const float* gate, bool add_x, const TV& out, cudaStream_t s) {
@@ -960,6 +1160,7 @@ void launch_layernorm(const TV& in, const TV& out, const float* gb, float eps, c
 }
 
 void launch_attention(const TV& qkv, const TV& out, int heads, int hd, float scale, cudaStream_t s, const int* vw) {
+  if (launch_attention_mma(qkv, out, heads, hd, scale, s, vw)) return;
   const int T = qkv.h * qkv.w;
   const size_t smem = (size_t(2) * T * hd + size_t(4) * T) * sizeof(float);
   static size_t configured = 0;

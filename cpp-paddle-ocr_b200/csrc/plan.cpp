@@ -451,11 +451,13 @@ struct Builder {
     S.act_a = f2.act_a; S.act_b = f2.act_b;
     std::vector<float> blk;
     blk.reserve(size_t(2) * C * cm + C + cm);
-    for (int m = 0; m < cm; ++m)
-      for (int c = 0; c < C; ++c) blk.push_back(w1[size_t(m) * C + c] * f1.A[m]);
-    for (int m = 0; m < cm; ++m) blk.push_back(f1.B[m]);
+    // both matrices are stored with the OUTPUT index fastest (w1t[c][m], w2t[m][c]): in se_fc_kernel one thread owns
+    // one output and neighbouring threads read neighbouring words
     for (int c = 0; c < C; ++c)
-      for (int m = 0; m < cm; ++m) blk.push_back(w2[size_t(c) * cm + m] * f2.A[c]);
+      for (int m = 0; m < cm; ++m) blk.push_back(w1[size_t(m) * C + c] * f1.A[m]);
+    for (int m = 0; m < cm; ++m) blk.push_back(f1.B[m]);
+    for (int m = 0; m < cm; ++m)
+      for (int c = 0; c < C; ++c) blk.push_back(w2[size_t(c) * cm + m] * f2.A[c]);
     for (int c = 0; c < C; ++c) blk.push_back(f2.B[c]);
     S.wf_off = push_f(blk);
     S.out = new_tensor(f2.out_var, C, true);
