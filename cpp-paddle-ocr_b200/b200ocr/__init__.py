@@ -461,3 +461,42 @@ def rotate_crop(img, box, device=0):
     out = np.empty((r.value, c.value, 3), np.uint8)
     check(lib.b200ocr_rotate_crop(device, arr, b.ctypes.data, C.byref(r), C.byref(c), out.ctypes.data))
     return out
+
+
+# ---------------------------------------------------------------- kernel-level entry points (parity tests)
+_sig("b200ocr_kernel_dwconv", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+     C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
+     C.POINTER(C.c_int), C.POINTER(C.c_int))
+_sig("b200ocr_kernel_attention", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
+     C.c_void_p)
+
+
+def kernel_dwconv(x, filt, bias, k, sh, sw, act=0, post_scale=1.0, post_shift=0.0, fp16_weights=True, out_widths=None,
+                  device=0):
+    """x [n,c,h,w] fp32, filt [c,k,k], bias [c] -> [n,c,oh,ow] fp32 (device path: NHWC fp16, fp32 accumulation)."""
+    x = np.ascontiguousarray(x, np.float32)
+    filt = np.ascontiguousarray(filt, np.float32)
+    bias = np.ascontiguousarray(bias, np.float32)
+    n, c, h, w = x.shape
+    pad = k // 2
+    oh, ow = (h + 2 * pad - k) // sh + 1, (w + 2 * pad - k) // sw + 1
+    out = np.empty((n, c, oh, ow), np.float32)
+    wd = None if out_widths is None else np.ascontiguousarray(out_widths, np.int32)
+    rh, rw = C.c_int(), C.c_int()
+    check(lib.b200ocr_kernel_dwconv(device, x.ctypes.data, n, c, h, w, filt.ctypes.data, bias.ctypes.data, k, sh, sw, act,
+                                    post_scale, post_shift, 1 if fp16_weights else 0,
+                                    None if wd is None else wd.ctypes.data, out.ctypes.data, C.byref(rh), C.byref(rw)))
+    assert (rh.value, rw.value) == (oh, ow)
+    return out
+
+
+def kernel_attention(qkv, heads, head_dim, scale, valid=None, device=0):
+    """qkv [n,t,3*heads*head_dim] fp32 -> [n,t,heads*head_dim] fp32."""
+    qkv = np.ascontiguousarray(qkv, np.float32)
+    n, t, c3 = qkv.shape
+    assert c3 == 3 * heads * head_dim
+    out = np.empty((n, t, heads * head_dim), np.float32)
+    vd = None if valid is None else np.ascontiguousarray(valid, np.int32)
+    check(lib.b200ocr_kernel_attention(device, qkv.ctypes.data, n, t, heads, head_dim, scale,
+                                       None if vd is None else vd.ctypes.data, out.ctypes.data))
+    return out

@@ -221,6 +221,21 @@ int b200ocr_worker_profile(b200ocr_worker_t w, int warmup, int reps, char** json
 /* Number of kernels one forward pass launches for the last shape. */
 int b200ocr_net_launches(b200ocr_net_t net);
 
+/* ------------------------------------------------------------------ kernel-level entry points (parity tests)
+ * One hot kernel on host tensors (fp32 in / out; fp16 NHWC activations and fp32 accumulation on the device, exactly
+ * what the networks run), so that tests can sweep shapes the shipped graphs do not contain.
+ * Depthwise convolution = Paddle depthwise_conv2d (+ folded bias, activation 0 none / 1 relu / 2 hard-swish, scalar
+ * affine): x [n,c,h,w], filt [c][k*k], bias [c], k in {3,5}, padding k/2, strides 1|2.  fp16_weights = 0 keeps fp32
+ * filter taps (det / cls), 1 rounds them to fp16 (rec).  out_widths (may be NULL): ragged rows -- out[i] is zero at
+ * x >= out_widths[i].  out [n,c,out_h,out_w]. */
+int b200ocr_kernel_dwconv(int device, const float* x, int n, int c, int h, int w, const float* filt, const float* bias,
+                          int k, int sh, int sw, int act, float post_scale, float post_shift, int fp16_weights,
+                          const int* out_widths, float* out, int* out_h, int* out_w);
+/* SVTR self-attention on packed qkv rows [n][t][3][heads][head_dim] -> out [n][t][heads*head_dim];
+ * valid (may be NULL): tokens per sequence, keys beyond it are ignored and queries beyond it give zeros. */
+int b200ocr_kernel_attention(int device, const float* qkv, int n, int t, int heads, int head_dim, float scale,
+                             const int* valid, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,109 @@
+"""Kernel-level parity of the hand-written floating-point kernels against a plain PyTorch fp32 reference of the same
+op, through the C ABI (b200ocr_kernel_*).  Inputs are rounded to fp16 first (that is what the device stores), so the
+only differences left are fp16 rounding of the output (<= 2^-11 relative), fp16 rounding of the filter taps where the
+recognizer uses them, and fp32 summation order.  Tolerance: 2e-3 of the output scale + 2e-3 absolute."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _h(a):  # what the device sees
+    return np.asarray(a, np.float32).astype(np.float16).astype(np.float32)
+
+
+def _ref_dwconv(x, filt, bias, k, sh, sw, act, s2, t2):
+    import torch
+    import torch.nn.functional as F
+    c = x.shape[1]
+    y = F.conv2d(torch.tensor(x), torch.tensor(filt)[:, None], torch.tensor(bias), stride=(sh, sw), padding=k // 2, groups=c)
+    if act == 1:
+        y = torch.relu(y)
+    elif act == 2:
+        y = y * torch.clamp(y + 3, 0, 6) / 6
+    return (s2 * y + t2).numpy()
+
+
+# (k, sh, sw) x heights that hit every row-block path (static variants for 14/7/4/2 rows, generic tiles otherwise)
+@pytest.mark.parametrize("k,sh,sw", [(3, 1, 1), (3, 2, 1), (3, 1, 2), (3, 2, 2), (5, 1, 1), (5, 2, 1), (5, 2, 2)])
+@pytest.mark.parametrize("c,h,w", [(16, 14, 37), (64, 14, 200), (240, 7, 100), (480, 4, 53), (480, 2, 19), (24, 23, 31),
+                                   (88, 3, 96), (200, 2, 48), (8, 24, 96), (40, 9, 11), (96, 40, 64), (192, 20, 33)])
+@pytest.mark.parametrize("fp16w", [True, False], ids=["w16", "w32"])
+def test_dwconv_matches_torch(k, sh, sw, c, h, w, fp16w):
+    import b200ocr
+    rng = np.random.default_rng(k * 1000 + sh * 100 + sw * 10 + c + h)
+    n = 3
+    x = _h(rng.standard_normal((n, c, h, w)))
+    filt = rng.standard_normal((c, k, k)).astype(np.float32) / k
+    if fp16w:
+        filt = _h(filt)
+    bias = rng.standard_normal(c).astype(np.float32) * 0.3
+    act = int(rng.integers(0, 3))
+    s2, t2 = (1.07, -0.04) if act == 2 else (1.0, 0.0)
+    got = b200ocr.kernel_dwconv(x, filt, bias, k, sh, sw, act, s2, t2, fp16_weights=fp16w)
+    ref = _ref_dwconv(x, filt, bias, k, sh, sw, act, s2, t2)
+    assert got.shape == ref.shape
+    tol = 2e-3 * float(np.abs(ref).max()) + 2e-3
+    assert float(np.abs(got - ref).max()) <= tol, (float(np.abs(got - ref).max()), tol)
+
+
+@pytest.mark.parametrize("k,sh,sw,c,h,w", [(5, 1, 1, 240, 7, 100), (3, 1, 1, 64, 14, 61), (5, 2, 1, 480, 7, 40), (3, 1, 2, 128, 7, 90),
+                                           (5, 1, 1, 88, 3, 50)])
+def test_dwconv_ragged_rows_equal_dense_rows_bitwise(k, sh, sw, c, h, w):
+    """A row of a ragged batch (zero beyond its width) equals the same row run alone at its own width, bit for bit;
+    beyond the row's valid output width the result is zero."""
+    import b200ocr
+    rng = np.random.default_rng(7)
+    widths = [w, max(8, w // 2 + 1), max(8, w // 3), w - 3]
+    x = _h(rng.standard_normal((len(widths), c, h, w)))
+    for i, wd in enumerate(widths):
+        x[i, :, :, wd:] = 0
+    filt = _h(rng.standard_normal((c, k, k)) / k)
+    bias = rng.standard_normal(c).astype(np.float32) * 0.3
+    out_w = [(wd + 2 * (k // 2) - k) // sw + 1 for wd in widths]
+    got = b200ocr.kernel_dwconv(x, filt, bias, k, sh, sw, 2, 0.97, 0.02, fp16_weights=True, out_widths=out_w)
+    for i, wd in enumerate(widths):
+        alone = b200ocr.kernel_dwconv(x[i:i + 1, :, :, :wd], filt, bias, k, sh, sw, 2, 0.97, 0.02, fp16_weights=True)
+        assert np.array_equal(got[i, :, :, :out_w[i]], alone[0])
+        assert not got[i, :, :, out_w[i]:].any()
+
+
+def _ref_attention(qkv, heads, hd, scale, valid):
+    import torch
+    n, t, _ = qkv.shape
+    q, k, v = torch.tensor(qkv).reshape(n, t, 3, heads, hd).permute(2, 0, 3, 1, 4)  # [n, heads, t, hd]
+    out = torch.zeros(n, t, heads * hd)
+    for i in range(n):
+        tv = t if valid is None else int(valid[i])
+        s = (q[i, :, :tv] @ k[i, :, :tv].transpose(1, 2)) * scale
+        o = torch.softmax(s, -1) @ v[i, :, :tv]              # [heads, tv, hd]
+        out[i, :tv] = o.permute(1, 0, 2).reshape(tv, heads * hd)
+    return out.numpy()
+
+
+@pytest.mark.parametrize("t", [1, 7, 16, 24, 33, 50, 64, 100, 125, 160, 240])
+def test_attention_matches_torch(t):
+    import b200ocr
+    rng = np.random.default_rng(t)
+    heads, hd = 8, 15
+    qkv = _h(rng.standard_normal((4, t, 3 * heads * hd)) * 1.5)
+    got = b200ocr.kernel_attention(qkv, heads, hd, hd ** -0.5)
+    ref = _ref_attention(qkv, heads, hd, hd ** -0.5, None)
+    assert float(np.abs(got - ref).max()) <= 4e-3, float(np.abs(got - ref).max())
+
+
+def test_attention_ragged_rows_equal_dense_rows_bitwise():
+    import b200ocr
+    rng = np.random.default_rng(3)
+    heads, hd, t = 8, 15, 90
+    valid = np.array([90, 1, 33, 64, 17, 80], np.int32)
+    qkv = _h(rng.standard_normal((len(valid), t, 3 * heads * hd)))
+    for i, tv in enumerate(valid):
+        qkv[i, tv:] = 0
+    got = b200ocr.kernel_attention(qkv, heads, hd, hd ** -0.5, valid=valid)
+    ref = _ref_attention(qkv, heads, hd, hd ** -0.5, valid)
+    assert float(np.abs(got - ref).max()) <= 4e-3
+    for i, tv in enumerate(valid):
+        alone = b200ocr.kernel_attention(qkv[i:i + 1, :tv], heads, hd, hd ** -0.5)
+        assert np.array_equal(got[i, :tv], alone[0])
+        assert not got[i, tv:].any()
