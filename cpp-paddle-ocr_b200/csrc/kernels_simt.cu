@@ -382,11 +382,11 @@ stem_conv_kernel(TV in, TV out, const __half* __restrict__ w, const float* __res
   }
 }
 
-template <int COUT, int ACT>
+template <int COUT, int ACT, int PX>
 __device__ __forceinline__ void stem_store(float (*acc)[COUT], const float* sb, const Epi& e, const TV& out, long pix0, int ox0,
                                            int vwn) {
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
+  for (int p = 0; p < PX; ++p) {
     const int ox = ox0 + p;
     if (ox >= out.w) break;
     __half* op = out.p + (pix0 + p) * out.pitch;
@@ -409,12 +409,12 @@ __device__ __forceinline__ void stem_store(float (*acc)[COUT], const float* sb, 
   }
 }
 
-// First layer, stride 2: one thread = 4 consecutive output pixels x all COUT channels.  Per filter row the thread
-// loads its 9 input pixels once (8 B each: 3 of the 8 channel slots are real) and every filter tap's COUT weights
+// First layer, stride 2: one thread = PX consecutive output pixels x all COUT channels.  Per filter row the thread
+// loads its 2*PX+1 input pixels once (8 B each: 3 of the 8 channel slots are real) and every filter tap's COUT weights
 // come from shared memory as broadcast 16-byte loads shared by the 4 pixels: 27 * COUT / 4 shared loads per
 // 4 * 27 * COUT multiply-adds (the one-pixel kernel above issues one shared load per multiply-add).
-template <int COUT>
-__global__ void __launch_bounds__(128, 3)
+template <int COUT, int PX>
+__global__ void __launch_bounds__(128, PX == 4 ? 3 : 4)
 stem_conv_s2x4_kernel(TV in, TV out, const __half* __restrict__ w, const float* __restrict__ bias, ConvGeom g, Epi e,
                       const int* __restrict__ vw) {
   __shared__ __align__(16) float sw[9 * 3 * COUT];
@@ -425,28 +425,29 @@ stem_conv_s2x4_kernel(TV in, TV out, const __half* __restrict__ w, const float* 
   }
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
-  const int strips = (out.w + 3) >> 2;
+  const int strips = (out.w + PX - 1) / PX;
   const long total = long(out.n) * out.h * strips;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
     const int sx = int(t % strips);
     const int oy = int((t / strips) % out.h);
     const int n = int(t / (long(strips) * out.h));
-    const int ox0 = sx * 4;
+    const int ox0 = sx * PX;
     const int ix0 = ox0 * 2 - g.pw;
-    float acc[4][COUT];
+    float acc[PX][COUT];
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+    for (int p = 0; p < PX; ++p)
 #pragma unroll
       for (int i = 0; i < COUT; ++i) acc[p][i] = 0.f;
     // all 27 input pixels are requested before the first multiply-add (one round trip to memory per thread)
-    uint2 raw[3][9];
+    constexpr int WINX = 2 * PX + 1;
+    uint2 raw[3][WINX];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = oy * 2 - g.ph + ky;
       const bool y_ok = iy >= 0 && iy < in.h;
       const __half* row = in.p + (long(n) * in.h + (y_ok ? iy : 0)) * in.w * in.pitch;
 #pragma unroll
-      for (int j = 0; j < 9; ++j) {
+      for (int j = 0; j < WINX; ++j) {
         const int ix = ix0 + j;
         raw[ky][j] = make_uint2(0u, 0u);
         if (y_ok && ix >= 0 && ix < in.w) raw[ky][j] = *reinterpret_cast<const uint2*>(row + long(ix) * in.pitch);
@@ -454,9 +455,9 @@ stem_conv_s2x4_kernel(TV in, TV out, const __half* __restrict__ w, const float* 
     }
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      float x[9][3];
+      float x[WINX][3];
 #pragma unroll
-      for (int j = 0; j < 9; ++j) {
+      for (int j = 0; j < WINX; ++j) {
         const float2 ab = __half22float2(*reinterpret_cast<const __half2*>(&raw[ky][j].x));
         x[j][0] = ab.x; x[j][1] = ab.y;
         x[j][2] = __half2float(*reinterpret_cast<const __half*>(&raw[ky][j].y));
@@ -470,7 +471,7 @@ stem_conv_s2x4_kernel(TV in, TV out, const __half* __restrict__ w, const float* 
           for (int q = 0; q < COUT / 4; ++q) {
             const float4 wv = wp[q];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
+            for (int p = 0; p < PX; ++p) {
               const float xv = x[2 * p + kx][ci];
               acc[p][4 * q] = fmaf(xv, wv.x, acc[p][4 * q]);
               acc[p][4 * q + 1] = fmaf(xv, wv.y, acc[p][4 * q + 1]);
@@ -483,9 +484,9 @@ stem_conv_s2x4_kernel(TV in, TV out, const __half* __restrict__ w, const float* 
     const int vwn = vw ? vw[n] : out.w;
     const long pix0 = (long(n) * out.h + oy) * out.w + ox0;
     switch (e.act) {  // one activation dispatch per thread, not per value
-      case 1: stem_store<COUT, 1>(acc, sb, e, out, pix0, ox0, vwn); break;
-      case 2: stem_store<COUT, 2>(acc, sb, e, out, pix0, ox0, vwn); break;
-      default: stem_store<COUT, 0>(acc, sb, e, out, pix0, ox0, vwn); break;
+      case 1: stem_store<COUT, 1, PX>(acc, sb, e, out, pix0, ox0, vwn); break;
+      case 2: stem_store<COUT, 2, PX>(acc, sb, e, out, pix0, ox0, vwn); break;
+      default: stem_store<COUT, 0, PX>(acc, sb, e, out, pix0, ox0, vwn); break;
     }
   }
 }
@@ -1051,9 +1052,12 @@ void launch_conv_simt(const TV& in, const TV& out, const __half* w, const float*
                       const ConvGeom& g, const Epi& e, cudaStream_t s, const int* vw) {
   if (in.c == 3 && in.pitch == 8 && g.kh == 3 && g.kw == 3 && e.res == nullptr && (out.c == 8 || out.c == 16)) {
     if (g.sh == 2 && g.sw == 2 && out.w >= 8 && e.act >= 0 && e.act <= 2 && !getenv("B200OCR_OLD_STEM")) {
-      const int sg = grid_for(long(out.n) * out.h * ((out.w + 3) / 4), 128);
-      if (out.c == 16) stem_conv_s2x4_kernel<16><<<sg, 128, 0, s>>>(in, out, w, bias, g, e, vw);
-      else stem_conv_s2x4_kernel<8><<<sg, 128, 0, s>>>(in, out, w, bias, g, e, vw);
+      static const int px = getenv("B200OCR_STEM_PX") ? atoi(getenv("B200OCR_STEM_PX")) : 2;
+      const int sg = grid_for(long(out.n) * out.h * ((out.w + px - 1) / px), 128);
+      if (out.c == 16 && px == 4) stem_conv_s2x4_kernel<16, 4><<<sg, 128, 0, s>>>(in, out, w, bias, g, e, vw);
+      else if (out.c == 16) stem_conv_s2x4_kernel<16, 2><<<sg, 128, 0, s>>>(in, out, w, bias, g, e, vw);
+      else if (px == 4) stem_conv_s2x4_kernel<8, 4><<<sg, 128, 0, s>>>(in, out, w, bias, g, e, vw);
+      else stem_conv_s2x4_kernel<8, 2><<<sg, 128, 0, s>>>(in, out, w, bias, g, e, vw);
       return;
     }
     const int grid = grid_for(long(out.n) * out.h * out.w);
