@@ -22,6 +22,7 @@ namespace b200ocr {
 namespace {
 
 constexpr int kStagesMax = 4;
+constexpr int kStagesMaxP = 8;  // persistent kernel: the A ring is as deep as shared memory allows (bytes in flight per SM)
 // The epilogue is a chain of dependent instructions per 16-column group; with one warp per scheduler every latency
 // is exposed.  16 epilogue warps (4 per TMEM lane quadrant, each taking every 4th column group) keep all four
 // schedulers busy.  Block = 2 control warps + kEpiWarps.
@@ -141,6 +142,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& a, const float* 
   const long pix = (long(n) * a.oh + y) * a.ow + x;
   const bool masked = valid && a.vw && int(pix % a.mask_w) >= a.vw[pix / a.mask_hw];
   const int c8lim = (a.cout + 7) & ~7;
+  const bool st32 = (a.out_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 31) == 0;  // 32-byte aligned groups
   const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
   for (int col = cgrp * 16; col < a.bn; col += 16 * (kEpiWarps / 4)) {
     uint32_t v[16];
@@ -193,8 +195,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& a, const float* 
       h0[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
       h1[i] = __floats2half2_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
     }
-    *reinterpret_cast<uint4*>(op) = o0;
-    if (second) *reinterpret_cast<uint4*>(op + 8) = o1;
+    if (second && st32) {  // one full 32-byte sector per lane instead of two half-sector writes
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(o0.x), "r"(o0.y), "r"(o0.z),
+                   "r"(o0.w), "r"(o1.x), "r"(o1.y), "r"(o1.z), "r"(o1.w)
+                   : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(op) = o0;
+      if (second) *reinterpret_cast<uint4*>(op + 8) = o1;
+    }
   }
 }
 
@@ -307,8 +315,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* a_full = b_full + 1;
-  uint64_t* a_empty = a_full + kStagesMax;
-  uint64_t* t_full = a_empty + kStagesMax;  // [2]
+  uint64_t* a_empty = a_full + kStagesMaxP;
+  uint64_t* t_full = a_empty + kStagesMaxP;  // [2]
   uint64_t* t_empty = t_full + 2;           // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
   float* sbias = reinterpret_cast<float*>(smem_raw + 256);  // this N tile's folded bias (<= 256 floats), read by every tile
@@ -529,15 +537,22 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
   {
     const int m_tiles = a.tiles_x * a.tiles_y * tiles_n;
     const size_t b_bytes = size_t(k_iters) * a.bn * 128;
-    const int st = k_iters < kStagesMax ? (k_iters < 2 ? 2 : k_iters) : kStagesMax;
-    const size_t need = b_bytes + size_t(st) * kATileBytes + 1024 + 1024 + 256;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (2 * a.tmem_cols <= 512 && need <= 220 * 1024 && m_tiles >= 2 * sms / 3 && !getenv("B200OCR_NO_PERSISTENT_CONV")) {
-      int per_sm = int((227 * 1024) / need);
-      per_sm = std::min(per_sm, 512 / (2 * a.tmem_cols));
-      per_sm = std::max(1, std::min(per_sm, 4));
+    // CTAs per SM: bounded by TMEM (two accumulators each) and by shared memory (resident filter + >= 2 A stages);
+    // the A ring then takes what is left: an HBM-bound layer needs as many bytes in flight per SM as it can get
+    const size_t fixed = b_bytes + 1024 + 1024 + 256;
+    int per_sm = std::max(1, std::min(512 / (2 * a.tmem_cols), 4));
+    auto budget = [](int ctas) { return (size_t(227) * 1024 - size_t(ctas) * 1024) / size_t(ctas); };  // 1 KB/CTA is reserved
+    while (per_sm > 1 && fixed + 2 * kATileBytes > budget(per_sm)) --per_sm;
+    int st = 0;
+    if (fixed + 2 * kATileBytes <= budget(per_sm))
+      st = int(std::min<size_t>(kStagesMaxP, (budget(per_sm) - fixed) / kATileBytes));
+    static const int st_cap = getenv("B200OCR_CONV_STAGES") ? atoi(getenv("B200OCR_CONV_STAGES")) : kStagesMaxP;
+    st = std::min(st, std::max(2, st_cap));
+    const size_t need = fixed + size_t(st) * kATileBytes;
+    if (2 * a.tmem_cols <= 512 && st >= 2 && m_tiles >= 2 * sms / 3 && !getenv("B200OCR_NO_PERSISTENT_CONV")) {
       const int ctas = std::min(m_tiles, sms * per_sm);
       impl->persistent = true;
       impl->n_mtiles = m_tiles;
