@@ -71,6 +71,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 // K-major, 128B swizzle: 8-row atoms of 1024 B (SBO = 1024), descriptor version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return uint64_t((saddr >> 4) & 0x3FFF) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) |
@@ -129,9 +135,12 @@ struct ConvTcArgs {
 };
 
 // Drain one accumulator tile: the calling warp owns TMEM lanes 32*(warp%4) .. +31 (row r of the tile = lane of D).
+// `stage` != nullptr: the fp16 results go to shared memory instead (rows of 128 B per 64-channel chunk, 16-byte pieces
+// XOR-swizzled with the row like CU_TENSOR_MAP_SWIZZLE_128B expects) and leave with one TMA store per chunk.
 template <int ACT>
 __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& a, const float* __restrict__ bias_blk, uint32_t tmem_base,
-                                              int x0, int y0, int n0, int nblk, int warp, int lane) {
+                                              int x0, int y0, int n0, int nblk, int warp, int lane,
+                                              uint8_t* stage = nullptr) {
   const int q = warp & 3;               // TMEM lane quadrant this warp may read (hardware rule: warp id % 4)
   const int cgrp = (warp - 2) >> 2;     // which share of the 16-column groups
   const int r = q * 32 + lane;
@@ -149,7 +158,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& a, const float* 
     tmem_ld16(trow + col, v);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     const int c0 = nblk * a.bn + col;
-    if (!valid || c0 >= c8lim) continue;
+    if ((!valid && !stage) || c0 >= c8lim) continue;  // staged tiles: rows outside the tensor are clipped by the store
     float f[16];
     {
       const float4* bp = reinterpret_cast<const float4*>(bias_blk + col);  // bias is padded to a multiple of 16
@@ -165,7 +174,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& a, const float* 
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] = a.epi.s2 * act_fn<ACT>(f[i], a.epi.a, a.epi.b) + a.epi.t2;
     const bool second = c0 + 8 < c8lim;
-    if (a.epi.res) {
+    if (a.epi.res && valid) {
       const __half* rp = a.epi.res + pix * a.epi.res_pitch + c0;
       uint4 r0 = *reinterpret_cast<const uint4*>(rp);
       const __half2* h = reinterpret_cast<const __half2*>(&r0);
@@ -195,7 +204,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& a, const float* 
       h0[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
       h1[i] = __floats2half2_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
     }
-    if (second && st32) {  // one full 32-byte sector per lane instead of two half-sector writes
+    if (stage) {
+      uint8_t* row = stage + size_t(col >> 6) * kATileBytes + r * 128;
+      const int j = (col & 63) >> 3;
+      *reinterpret_cast<uint4*>(row + ((j ^ (r & 7)) << 4)) = o0;
+      *reinterpret_cast<uint4*>(row + (((j + 1) ^ (r & 7)) << 4)) = o1;
+    } else if (second && st32) {  // one full 32-byte sector per lane instead of two half-sector writes
       asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(o0.x), "r"(o0.y), "r"(o0.z),
                    "r"(o0.w), "r"(o1.x), "r"(o1.y), "r"(o1.z), "r"(o1.w)
                    : "memory");
@@ -311,7 +325,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int ACT>
 __global__ void __launch_bounds__(kThreadsTc)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const ConvTcArgs a, const int n_mtiles, const int kt /* taps * K chunks */) {
+                       const __grid_constant__ CUtensorMap tmC, const ConvTcArgs a, const int n_mtiles,
+                       const int kt /* taps * K chunks */, const int tma_store) {
   extern __shared__ uint8_t smem_raw[];
   uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* a_full = b_full + 1;
@@ -399,18 +414,37 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else {
+    // output staging tile behind the A ring (only with tma_store): ceil(bn / 64) chunks of 128 rows x 128 B
+    uint8_t* stage = tma_store ? tiles + a_ring + size_t(a.stages) * kATileBytes : nullptr;
+    const bool leader = warp == 2 && lane == 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x, ++lt) {
       int t = tile;
       const int tx = t % a.tiles_x; t /= a.tiles_x;
       const int ty = t % a.tiles_y; t /= a.tiles_y;
       const int buf = lt & 1;
+      if (stage) {  // the previous tile's stores must have finished READING the staging tile
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");
+      }
       mbar_wait(&t_full[buf], uint32_t(lt >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      epilogue_tile<ACT>(a, sbias, tmem_base + uint32_t(buf * a.tmem_cols), tx * a.tw, ty * a.th, t * a.tn, nblk, warp, lane);
+      epilogue_tile<ACT>(a, sbias, tmem_base + uint32_t(buf * a.tmem_cols), tx * a.tw, ty * a.th, t * a.tn, nblk, warp, lane,
+                         stage);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&t_empty[buf]);
+      if (stage) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");
+        if (leader) {
+          const int c8lim = (a.cout + 7) & ~7;
+          for (int c = 0; c * 64 < a.bn && nblk * a.bn + c * 64 < c8lim; ++c)
+            tma_store_4d(&tmC, stage + size_t(c) * kATileBytes, nblk * a.bn + c * 64, tx * a.tw, ty * a.th, t * a.tn);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
     }
+    if (stage && leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -459,7 +493,8 @@ void encode(CUtensorMap* tm, void* base, int rank, const cuuint64_t* dims, const
 }  // namespace
 
 struct ConvTcPlanImpl {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
+  bool tma_store = false;  // persistent kernel: results leave through a staged TMA store (no residual input)
   ConvTcArgs args;
   dim3 grid;
   size_t smem;
@@ -531,6 +566,12 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
   cuuint64_t sB[1] = {cuuint64_t(taps) * g.cin_pad * 2};
   cuuint32_t bB[2] = {64, cuuint32_t(a.bn)};
   encode(&impl->tmB, const_cast<__half*>(w), 2, dB, sB, bB);
+  {  // output view with the same tiling as the input box (rows of a tile = tw x th x tn pixels, 64 channels per store)
+    const int oc8 = (out.c + 7) & ~7;
+    cuuint64_t dC[4] = {cuuint64_t(oc8), cuuint64_t(out.w), cuuint64_t(out.h), cuuint64_t(out.n)};
+    cuuint64_t sC[3] = {cuuint64_t(out.pitch) * 2, cuuint64_t(out.pitch) * 2 * out.w, cuuint64_t(out.pitch) * 2 * out.w * out.h};
+    encode(&impl->tmC, out.p, 4, dC, sC, bA);
+  }
   impl->grid = dim3(unsigned(a.tiles_x * a.tiles_y * tiles_n), unsigned(n_tiles));
   impl->smem = size_t(a.stages) * (kATileBytes + a.bn * 128) + 1024 + 128;
   // persistent variant: filter block resident + A ring + double-buffered accumulator
@@ -542,10 +583,16 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // CTAs per SM: bounded by TMEM (two accumulators each) and by shared memory (resident filter + >= 2 A stages);
     // the A ring then takes what is left: an HBM-bound layer needs as many bytes in flight per SM as it can get
-    const size_t fixed = b_bytes + 1024 + 1024 + 256;
+    const size_t stage_bytes = size_t((a.bn + 63) / 64) * kATileBytes;  // output staging tile of the TMA-store epilogue
+    size_t fixed = b_bytes + 1024 + 1024 + 256;
     int per_sm = std::max(1, std::min(512 / (2 * a.tmem_cols), 4));
     auto budget = [](int ctas) { return (size_t(227) * 1024 - size_t(ctas) * 1024) / size_t(ctas); };  // 1 KB/CTA is reserved
     while (per_sm > 1 && fixed + 2 * kATileBytes > budget(per_sm)) --per_sm;
+    // measured on B200 (profiles/r01_notes.md): with a single staging tile the two extra CTA-wide barriers per tile cost
+    // more than the full-line stores save (39 us vs 31 us on the 240 -> 240 layers), so the staged path is opt-in
+    static const bool want_tma_store = getenv("B200OCR_TMA_STORE") != nullptr;
+    const bool staged = want_tma_store && fixed + stage_bytes + 2 * kATileBytes <= budget(per_sm);
+    if (staged) fixed += stage_bytes;
     int st = 0;
     if (fixed + 2 * kATileBytes <= budget(per_sm))
       st = int(std::min<size_t>(kStagesMaxP, (budget(per_sm) - fixed) / kATileBytes));
@@ -555,6 +602,7 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
     if (2 * a.tmem_cols <= 512 && st >= 2 && m_tiles >= 2 * sms / 3 && !getenv("B200OCR_NO_PERSISTENT_CONV")) {
       const int ctas = std::min(m_tiles, sms * per_sm);
       impl->persistent = true;
+      impl->tma_store = staged;
       impl->n_mtiles = m_tiles;
       impl->kt = k_iters;
       a.stages = st;
@@ -563,19 +611,29 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
     }
   }
   impl->args = a;
-  // per device (function attributes live in the context): cheap, done once per (layer, shape)
-  cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(conv_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  // function attributes live in the device context: set once per device
+  {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 64 || !done[dev]) {
+    cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_persist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_persist_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_persist_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_persist_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (dev < 64) done[dev] = true;
+    }
+  }
   ConvTcPlan p;
   p.impl = impl;
   return p;
@@ -593,13 +651,14 @@ void launch_conv_tc(const ConvTcPlan& p, const float* bias, const Epi& e, cudaSt
   a.vw = vw;
   if (p.impl->persistent) {
     const int nm = p.impl->n_mtiles, kt = p.impl->kt;
+    const int ts = p.impl->tma_store && e.res == nullptr ? 1 : 0;
     switch (e.act) {
-      case 1: conv_tc_persist_kernel<1><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
-      case 2: conv_tc_persist_kernel<2><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
-      case 3: conv_tc_persist_kernel<3><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
-      case 4: conv_tc_persist_kernel<4><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
-      case 5: conv_tc_persist_kernel<5><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
-      default: conv_tc_persist_kernel<0><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a, nm, kt); break;
+      case 1: conv_tc_persist_kernel<1><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
+      case 2: conv_tc_persist_kernel<2><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
+      case 3: conv_tc_persist_kernel<3><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
+      case 4: conv_tc_persist_kernel<4><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
+      case 5: conv_tc_persist_kernel<5><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
+      default: conv_tc_persist_kernel<0><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
     }
     return;
   }
