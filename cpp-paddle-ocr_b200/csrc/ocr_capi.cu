@@ -397,9 +397,17 @@ int b200ocr_worker_profile(b200ocr_worker_t w, int warmup, int reps, char** json
     if (!w || !json || reps < 1) throw std::invalid_argument("bad argument");
     Worker& k = *w->w;
     cuda_check(cudaSetDevice(k.device()), "cudaSetDevice");
-    std::string o = "{\"det\":" + profile_json(k.det().net(), k.stream(), warmup, reps, 51);
-    if (k.cls()) o += ",\"cls\":" + profile_json(k.cls()->net(), k.stream(), warmup, reps, -1);
-    o += ",\"rec\":" + profile_json(k.rec().net(), k.stream(), warmup, reps, -1) + "}";
+    // every network is timed at the largest forward pass of the worker's last call (dense: a ragged rec chunk is timed
+    // as the dense batch of its widest row)
+    auto timed = [&](Net& net, int n, int h, int wd, int thresh) {
+      if (n > 0) net.prepare(n, h, wd, nullptr, k.stream());
+      char shape[96];
+      snprintf(shape, sizeof shape, "{\"shape\":[%d,%d,%d],\"layers\":", n, h, wd);
+      return std::string(shape) + profile_json(net, k.stream(), warmup, reps, thresh) + "}";
+    };
+    std::string o = "{\"det\":" + timed(k.det().net(), k.det().prof_n, k.det().prof_h, k.det().prof_w, 51);
+    if (k.cls()) o += ",\"cls\":" + timed(k.cls()->net(), k.cls()->prof_n, k.cls()->prof_h, k.cls()->prof_w, -1);
+    o += ",\"rec\":" + timed(k.rec().net(), k.rec().prof_n, k.rec().prof_h, k.rec().prof_w, -1) + "}";
     *json = dup_string(o);
   });
 }

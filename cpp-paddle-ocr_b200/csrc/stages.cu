@@ -94,6 +94,7 @@ DetStage::DetStage(const std::string& model_dir, int device, const DetParams& p)
 void DetStage::run(const std::vector<DevImg>& imgs, std::vector<std::vector<Box>>* boxes, cudaStream_t s,
                    std::vector<double>* times) {
   boxes->assign(imgs.size(), {});
+  prof_n = prof_h = prof_w = 0;
   std::map<std::pair<int, int>, std::vector<int>> groups;  // resized (h, w) -> image indices
   for (size_t i = 0; i < imgs.size(); ++i) {
     int rh, rw;
@@ -127,6 +128,7 @@ void DetStage::run_group(const std::vector<DevImg>& imgs, const std::vector<int>
     inf.src_h = im.rows; inf.src_w = im.cols;
     h_info_.as<DbImageInfo>()[k] = inf;
   }
+  if (long(n) * rh * rw > long(prof_n) * prof_h * prof_w) { prof_n = n; prof_h = rh; prof_w = rw; }
   __half* in = net_.prepare(n, rh, rw, nullptr, s);
   cuda_check(cudaMemcpyAsync(items_.p, h_items_.p, sizeof(DetPreItem) * n, cudaMemcpyHostToDevice, s), "det items");
   cuda_check(cudaMemcpyAsync(info_.p, h_info_.p, sizeof(DbImageInfo) * n, cudaMemcpyHostToDevice, s), "det info");
@@ -257,6 +259,7 @@ void ClsStage::run(const std::vector<DevImg>& imgs, const std::vector<Roi>& rois
   for (int b0 = 0; b0 < n; b0 += max_batch) {
     const int nb = std::min(max_batch, n - b0);
     auto t0 = Clock::now();
+    if (b0 == 0) { prof_n = nb; prof_h = 48; prof_w = 192; }
     __half* in = net_.prepare(nb, 48, 192, nullptr, s);
     // pad value 0.0: the classifier pads AFTER normalisation (src/ocr_cls.cpp:52-56)
     launch_crop_preprocess(items_.as<CropItem>() + b0, nb, 48, 192, make_norm(kMean05, kScale2), 0.f, in, s);
@@ -419,7 +422,9 @@ void RecStage::run(const std::vector<DevImg>& imgs, const std::vector<std::vecto
   h_clen_.ensure(sizeof(int) * std::max<size_t>(rows.size(), 1));
   h_cscore_.ensure(sizeof(float) * std::max<size_t>(rows.size(), 1));
   std::vector<int> widths;
+  prof_n = prof_h = prof_w = 0;
   for (Chunk& ch : chunks) {
+    if (long(ch.nb) * ch.wmax > long(prof_n) * prof_w) { prof_n = ch.nb; prof_h = img_h_; prof_w = ch.wmax; }
     widths.resize(ch.nb);
     for (int k = 0; k < ch.nb; ++k) widths[k] = rows[ch.b0 + k].width;
     __half* in = net_.prepare(ch.nb, img_h_, ch.wmax, widths.data(), s);

@@ -82,6 +82,7 @@ class DetStage {
   static void resized_dims(int rows, int cols, const std::string& limit_type, int limit_side_len, int* rh, int* rw,
                            float* ratio_h, float* ratio_w);
   Net& net() { return net_; }
+  int prof_n = 0, prof_h = 0, prof_w = 0;  // largest forward pass of the last run() (what b200ocr_worker_profile times)
   int max_batch = 32;  // images per forward pass
   long launches = 0;   // kernels launched so far (bench accounting)
  private:
@@ -104,6 +105,7 @@ class ClsStage {
   // (reference src/ocr_worker.cpp:277-281; ROIs alias the image, order matters where they overlap).
   void rotate_rois(const std::vector<DevImg>& imgs, const std::vector<Roi>& rois, cudaStream_t s);
   Net& net() { return net_; }
+  int prof_n = 0, prof_h = 0, prof_w = 0;  // largest forward pass of the last run() (what b200ocr_worker_profile times)
   int max_batch = 512;
   long launches = 0;
  private:
@@ -126,6 +128,7 @@ class RecStage {
            std::vector<double>* times = nullptr);
   const std::vector<std::string>& labels() const { return label_list_; }
   Net& net() { return net_; }
+  int prof_n = 0, prof_h = 0, prof_w = 0;  // largest forward pass of the last run() (what b200ocr_worker_profile times)
   int max_rows = 1024;       // rows per forward pass
   long max_cols = 400000;    // rows x padded width per forward pass (bounds the activation arena)
   int last_chunks = 0; long last_cols = 0, last_real_cols = 0;  // trace: ragged chunking of the last run()
