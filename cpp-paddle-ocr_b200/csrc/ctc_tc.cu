@@ -6,7 +6,8 @@
 //   dimension streams through in tiles of 256 classes: TMA -> 2-stage smem ring -> one tcgen05.mma chain
 //   (M=128, N=256, K=16 x 8) per tile into one of two 256-column TMEM accumulators, while the four epilogue
 //   warps drain the other one (tcgen05.ld) into a per-token running (max, first arg-max, sum exp).
-//   Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issue, 2..5 = epilogue (one token per thread).
+//   Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issue, 2..17 = epilogue (a token = one TMEM lane; the four
+//   warps of a lane quadrant split the column groups and merge their (max, arg-max, sum) through shared memory).
 #include "kernels.h"
 
 #include <cuda.h>
@@ -21,6 +22,10 @@ namespace {
 
 constexpr int kTileN = 256;
 constexpr int kStages = 2;
+// The epilogue (one exponential per token and class) is a dependent chain per 16-column group: 16 epilogue warps
+// (4 per TMEM lane quadrant, each taking every 4th column group) keep all four schedulers and the MUFU busy.
+constexpr int kCtcEpiWarps = 16;
+constexpr int kCtcThreads = 64 + 32 * kCtcEpiWarps;
 constexpr int kABytes = 128 * 128 * 2;      // 128 tokens x 128 channels fp16 (two 64-channel swizzle atoms)
 constexpr int kBBytes = kTileN * 128 * 2;   // 256 classes x 128 channels
 
@@ -78,7 +83,7 @@ struct CtcArgs {
   float* prob;
 };
 
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(kCtcThreads)
 ctc_head_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const CtcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -97,7 +102,7 @@ ctc_head_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     mbar_init(a_full, 1);
     for (int s = 0; s < kStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 32 * kCtcEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -145,10 +150,10 @@ ctc_head_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else {
-    const int q = warp & 3;
-    const long row = row0 + q * 32 + lane;
+    const int q = warp & 3;             // TMEM lane quadrant (hardware rule: warp id % 4)
+    const int cg = (warp - 2) >> 2;     // this warp's share of the 16-column groups
     float mx = -FLT_MAX, sum = 0.f;
-    int am = 0;
+    int am = 0x7fffffff;
     for (int t = 0; t < a.ntiles; ++t) {
       const int buf = t & 1;
       mbar_wait(&t_full[buf], (t >> 1) & 1);
@@ -156,7 +161,7 @@ ctc_head_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16) + buf * kTileN;
       const int cbase = t * kTileN;
       const int ncol = min(kTileN, a.ncls_pad - cbase);
-      for (int col = 0; col < ncol; col += 16) {
+      for (int col = cg * 16; col < ncol; col += 16 * (kCtcEpiWarps / 4)) {
         uint32_t v[16];
         tmem_ld16(trow + col, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -193,10 +198,31 @@ ctc_head_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&t_empty[buf]);
     }
-    if (row < a.rows) {
-      const bool pad = a.vw && int(row % a.T) >= a.vw[row / a.T];
-      a.idx[row] = pad ? 0 : am;
-      a.prob[row] = pad ? 0.f : 1.f / sum;
+    // combine the column shares of a token: the pipeline's shared memory is idle by now (all tiles consumed)
+    float* pm = reinterpret_cast<float*>(tiles);                 // [4][128] running maxima
+    float* ps = pm + 4 * 128;                                     // [4][128] sums
+    int* pa = reinterpret_cast<int*>(ps + 4 * 128);               // [4][128] arg-max
+    const int rloc = q * 32 + lane;
+    pm[cg * 128 + rloc] = mx; ps[cg * 128 + rloc] = sum; pa[cg * 128 + rloc] = am;
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * kCtcEpiWarps) : "memory");
+    if (cg == 0) {
+      const long row = row0 + rloc;
+      float M = pm[rloc];
+#pragma unroll
+      for (int p = 1; p < 4; ++p) M = fmaxf(M, pm[p * 128 + rloc]);
+      float total = 0.f;
+      int best = 0x7fffffff;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float mp = pm[p * 128 + rloc];
+        total += ps[p * 128 + rloc] * __expf(mp - M);
+        if (mp == M) best = min(best, pa[p * 128 + rloc]);       // first maximum wins across the shares too
+      }
+      if (row < a.rows) {
+        const bool pad = a.vw && int(row % a.T) >= a.vw[row / a.T];
+        a.idx[row] = pad ? 0 : best;
+        a.prob[row] = pad ? 0.f : 1.f / total;
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -254,7 +280,7 @@ void launch_ctc_head_tc(const TV& feat, const __half* w, const float* bias, int 
   a.bias = bias; a.vw = vw; a.idx = idx; a.prob = prob;
   const size_t smem = kABytes + size_t(kStages) * kBBytes + 1024 + 128;
   cudaFuncSetAttribute(ctc_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  ctc_head_tc_kernel<<<unsigned((rows + 127) / 128), 192, smem, s>>>(tmA, tmB, a);
+  ctc_head_tc_kernel<<<unsigned((rows + 127) / 128), kCtcThreads, smem, s>>>(tmA, tmB, a);
 }
 
 }  // namespace b200ocr
