@@ -59,20 +59,26 @@ attention_mma_kernel(TV qkv, TV out, int heads, int hd, float scale_log2e, const
   }
   __syncthreads();
   {
-    const int vec_per_row = (3 * C) / 8;     // 45 16-byte vectors per token (3*C is a multiple of 8 for 8 x 15)
-    for (int i = threadIdx.x; i < Tv * vec_per_row; i += kAttnThreads) {
-      const int t = i / vec_per_row, v = i - t * vec_per_row;
-      const uint4 raw = *reinterpret_cast<const uint4*>(base + long(t) * qkv.pitch + v * 8);
-      const __half* h = reinterpret_cast<const __half*>(&raw);
+    // a thread keeps ONE 16-byte slot of the token row (45 slots for 8 x 15): where its 8 halves go is computed once
+    const int vec_per_row = (3 * C) / 8;
+    const int tpp = kAttnThreads / vec_per_row;            // tokens per pass
+    const int v = threadIdx.x % vec_per_row, t0 = threadIdx.x / vec_per_row;
+    int dbase[8], dstep[8];                                 // destination (in halves from attn_smem) = dbase + t * dstep
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = v * 8 + e;             // channel in [0, 3C)
-        const int which = c / C, r = c - which * C;
-        const int head = r / hd, d = r - head * hd;
-        if (which < 2) QK[size_t(t) * kTok + which * 128 + head * 16 + d] = h[e];
-        else Vt[(size_t(head) * 16 + d) * vpitch + t] = h[e];
-      }
+    for (int e = 0; e < 8; ++e) {
+      const int c = v * 8 + e;
+      const int which = c / C, r = c - which * C;
+      const int head = r / hd, d = r - head * hd;
+      if (which < 2) { dbase[e] = which * 128 + head * 16 + d; dstep[e] = kTok; }
+      else { dbase[e] = Tp * kTok + (head * 16 + d) * vpitch; dstep[e] = 1; }
     }
+    if (t0 < tpp)
+      for (int t = t0; t < Tv; t += tpp) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(base + long(t) * qkv.pitch + v * 8);
+        const __half* h = reinterpret_cast<const __half*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) QK[dbase[e] + t * dstep[e]] = h[e];
+      }
   }
   __syncthreads();
 
@@ -167,21 +173,26 @@ attention_mma_kernel(TV qkv, TV out, int heads, int hd, float scale_log2e, const
   // ---- write back: [T][C] halves, 16-byte vectors; rows beyond the valid length are zero
   {
     const int vec_per_row = C / 8;  // 15
-    __half* obase = out.p + long(n) * Tfull * out.pitch;
-    for (int i = threadIdx.x; i < Tfull * vec_per_row; i += kAttnThreads) {
-      const int t = i / vec_per_row, v = i - t * vec_per_row;
-      uint4 pk = make_uint4(0, 0, 0, 0);
-      if (t < Tv) {
-        __half* h = reinterpret_cast<__half*>(&pk);
+    const int tpp = kAttnThreads / vec_per_row;
+    const int v = threadIdx.x % vec_per_row, t0 = threadIdx.x / vec_per_row;
+    int sbase[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = v * 8 + e;
-          const int head = c / hd, d = c - head * hd;
-          h[e] = QK[size_t(t) * kTok + head * 16 + d];
-        }
-      }
-      *reinterpret_cast<uint4*>(obase + long(t) * out.pitch + v * 8) = pk;
+    for (int e = 0; e < 8; ++e) {
+      const int c = v * 8 + e;
+      const int head = c / hd, d = c - head * hd;
+      sbase[e] = head * 16 + d;
     }
+    __half* obase = out.p + long(n) * Tfull * out.pitch + v * 8;
+    if (t0 < tpp)
+      for (int t = t0; t < Tfull; t += tpp) {
+        uint4 pk = make_uint4(0, 0, 0, 0);
+        if (t < Tv) {
+          __half* h = reinterpret_cast<__half*>(&pk);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) h[e] = QK[size_t(t) * kTok + sbase[e]];
+        }
+        *reinterpret_cast<uint4*>(obase + long(t) * out.pitch) = pk;
+      }
   }
 }
 

@@ -510,13 +510,42 @@ gap_partial_kernel(TV in, float* __restrict__ partial, int splits) {
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (lane < lanes) {
     const __half* base = in.p + long(n) * hw * in.pitch + cg * 8;
-    for (int y = y0; y < y1; ++y)
-      for (int xx = lane; xx < in.w; xx += lanes) {
-        float x[8];
-        ld8(base + (long(y) * in.w + xx) * in.pitch).to_float(x);
+    // four independent partial sums per lane (columns lane + lanes * (4j + u)): four loads in flight instead of a
+    // load -> add chain.  Which partial sum a column feeds depends on x and the channel count only, so the result
+    // is still independent of the width of the surrounding tensor.
+    float part[4][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += x[i];
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) part[u][i] = 0.f;
+    for (int y = y0; y < y1; ++y) {
+      const __half* row = base + long(y) * in.w * in.pitch;
+      int xx = lane;
+      for (; xx + 3 * lanes < in.w; xx += 4 * lanes) {
+        H8 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld8(row + long(xx + u * lanes) * in.pitch);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float x[8];
+          v[u].to_float(x);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) part[u][i] += x[i];
+        }
       }
+      for (int u = 0; xx < in.w; xx += lanes, ++u) {
+        float x[8];
+        ld8(row + long(xx) * in.pitch).to_float(x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (u == 0) part[0][i] += x[i];
+          else if (u == 1) part[1][i] += x[i];
+          else part[2][i] += x[i];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = (part[0][i] + part[1][i]) + (part[2][i] + part[3][i]);
 #pragma unroll
     for (int i = 0; i < 8; ++i) sm[lane * cp + cg * 8 + i] = acc[i];
   }
