@@ -118,7 +118,8 @@ struct ConvTcArgs {
   // tile geometry over the output view (for 1x1 convs the view is flattened to n=1,h=1,w=P)
   int on, oh, ow;          // output dims as tiled
   int tw, th, tn;          // box: tw*th*tn <= 128 rows
-  int tiles_x, tiles_y;    // tiles_n = gridDim.x / (tiles_x*tiles_y)
+  int tiles_x, tiles_y;    // tiles_n = pixel tiles / (tiles_x*tiles_y)
+  int n_tiles;             // N tiles (non-persistent kernel: interleaved in blockIdx.x)
   int kh, kw, ph, pw;
   int cin, cin_pad;        // logical input channels; weight row stride per tap
   int bn;                  // N tile (multiple of 16, <= 256)
@@ -236,12 +237,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // tile coordinates
-  int t = blockIdx.x;
+  // tile coordinates.  The N tiles of one pixel tile are neighbours in launch order (blockIdx.x = tile * n_tiles +
+  // nblk): they run at the same time and the second one finds the activation tile in L2.
+  int t = blockIdx.x / a.n_tiles;
+  const int nblk = blockIdx.x - t * a.n_tiles;  // N tile index
   const int tx = t % a.tiles_x; t /= a.tiles_x;
   const int ty = t % a.tiles_y; t /= a.tiles_y;
   const int x0 = tx * a.tw, y0 = ty * a.th, n0 = t * a.tn;
-  const int nblk = blockIdx.y;  // N tile index
 
   const int kchunks = (a.cin + 63) >> 6;
 
@@ -572,7 +574,8 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
     cuuint64_t sC[3] = {cuuint64_t(out.pitch) * 2, cuuint64_t(out.pitch) * 2 * out.w, cuuint64_t(out.pitch) * 2 * out.w * out.h};
     encode(&impl->tmC, out.p, 4, dC, sC, bA);
   }
-  impl->grid = dim3(unsigned(a.tiles_x * a.tiles_y * tiles_n), unsigned(n_tiles));
+  a.n_tiles = n_tiles;
+  impl->grid = dim3(unsigned(a.tiles_x * a.tiles_y * tiles_n * n_tiles), 1u);
   impl->smem = size_t(a.stages) * (kATileBytes + a.bn * 128) + 1024 + 128;
   // persistent variant: filter block resident + A ring + double-buffered accumulator
   {
