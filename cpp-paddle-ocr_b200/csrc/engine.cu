@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <stdexcept>
@@ -54,6 +55,7 @@ Net::~Net() {
   cudaFree(d_wf_);
   cudaFree(arena_);
   cudaFree(vw_dev_);
+  cudaFree(se_cnt_);
   free(vw_pin_);
 }
 
@@ -255,6 +257,13 @@ __half* Net::prepare(int n, int h, int w, const int* widths, cudaStream_t stream
     }
   }
   cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+  if (n > se_cnt_cap_) {
+    cuda_check(cudaStreamSynchronize(stream), "sync before counter growth");
+    cudaFree(se_cnt_);
+    se_cnt_cap_ = n + n / 2 + 64;
+    cuda_check(cudaMalloc(&se_cnt_, size_t(se_cnt_cap_) * sizeof(int)), "cudaMalloc SE counters");
+    cuda_check(cudaMemset(se_cnt_, 0, size_t(se_cnt_cap_) * sizeof(int)), "cudaMemset SE counters");
+  }
   auto key = std::make_tuple(n, h, w);
   auto it = cache_.find(key);
   Inst* I = it != cache_.end() ? it->second.get() : instantiate(n, h, w);
@@ -283,6 +292,7 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
   auto vwp = [&](int t) -> const int* { return ragged_ ? vw_dev_ + size_t(t) * I.n : nullptr; };
   auto vecp = [&](int t) { return reinterpret_cast<float*>(arena_ + I.boff[plan_.tensors[t].buf]); };
   int launches = 0;
+  static const bool no_se_fuse = getenv("B200OCR_NO_SE_FUSE") != nullptr;
   for (size_t li = 0; li < plan_.layers.size(); ++li) {
     if (only >= 0 && int(li) != only) continue;
     const Layer& L = plan_.layers[li];
@@ -316,8 +326,28 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
         launch_dwconv(tv(L.in), tv(L.out), d_wf_ + L.wf_off, plan_.kind == "rec" ? d_wh_ + L.wh_off : nullptr, g, e, s,
                       vwp(L.out));
         break;
-      case LKind::Gap: launch_gap_partial(tv(L.in), vecp(L.out), I.splits[L.out], s); break;
+      case LKind::Gap: {
+        // pool + SE gate in one launch when the pooled vector only feeds the gate that follows
+        const bool fuse = !no_se_fuse && li + 1 < plan_.layers.size() && plan_.layers[li + 1].kind == LKind::SeFc &&
+                          plan_.layers[li + 1].in == L.out;
+        if (fuse) {
+          const Layer& F = plan_.layers[li + 1];
+          SeFuse f;
+          f.blk = d_wf_ + F.wf_off; f.gate = vecp(F.out); f.counters = se_cnt_;
+          f.c = F.cin; f.cmid = F.cmid; f.slope = F.act_a; f.offset = F.act_b;
+          f.inv_hw = 1.f / float(I.hw[L.out]);
+          f.vw_in = vwp(L.in); f.h = I.ts[L.in].h;
+          launch_gap_partial(tv(L.in), vecp(L.out), I.splits[L.out], s, &f);
+        } else {
+          launch_gap_partial(tv(L.in), vecp(L.out), I.splits[L.out], s);
+        }
+        break;
+      }
       case LKind::SeFc:
+        if (!no_se_fuse && li > 0 && plan_.layers[li - 1].kind == LKind::Gap && plan_.layers[li - 1].out == L.in) {
+          --launches;  // fused into the pooling kernel above: nothing is launched for this layer
+          break;
+        }
         launch_se_fc(vecp(L.in), I.splits[L.in], I.hw[L.in], I.ts[L.in].n, L.cin, L.cmid, d_wf_ + L.wf_off,
                      L.act_a, L.act_b, vecp(L.out), s, vwp(I.gap_src[L.in]), I.ts[I.gap_src[L.in]].h);
         break;

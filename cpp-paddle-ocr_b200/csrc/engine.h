@@ -94,6 +94,8 @@ class Net {
   int* vw_pin_ = nullptr;
   int* vw_dev_ = nullptr;
   size_t vw_cap_ = 0;
+  int* se_cnt_ = nullptr;   // ticket counters of the fused pool + SE-gate kernel (int[n], self-resetting)
+  int se_cnt_cap_ = 0;
 };
 
 void cuda_check(cudaError_t e, const char* what);

@@ -54,7 +54,17 @@ bool launch_dwconv_tile(const TV& in, const TV& out, const float* w_bias, const 
 
 // ---- SE block ---------------------------------------------------------------
 int gap_splits(int h);
-void launch_gap_partial(const TV& in, float* partial, int splits, cudaStream_t s);
+// SE gate fused into the pooling kernel (the block that finishes a sample's last split computes its gate):
+// counters = int[n] device scratch, zero before the first use (the kernel leaves it zero)
+struct SeFuse {
+  const float* blk = nullptr;  // w1t[c][cmid], b1[cmid], w2t[cmid][c], b2[c]
+  float* gate = nullptr;
+  int* counters = nullptr;
+  int c = 0, cmid = 0, h = 0;
+  float slope = 0.f, offset = 0.f, inv_hw = 0.f;
+  const int* vw_in = nullptr;
+};
+void launch_gap_partial(const TV& in, float* partial, int splits, cudaStream_t s, const SeFuse* fuse = nullptr);
 // vw_in: valid width of the pooled tensor per row (mean over h * vw_in[n] pixels), h its height
 void launch_se_fc(const float* partial, int splits, int hw, int n, int c, int cmid, const float* blk,
                   float slope, float offset, float* gate, cudaStream_t s, const int* vw_in = nullptr, int h = 0);

@@ -4,6 +4,7 @@
 // is fp32.  HBM/L2-bound kernels: one thread per (pixel, 8-channel group), coalesced along C.
 #include "kernels.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <cstdlib>
 
@@ -493,9 +494,7 @@ stem_conv_s2x4_kernel(TV in, TV out, const __half* __restrict__ w, const float* 
 
 // ---------------------------------------------------------------- SE block
 // partial[n][split][cp] = sum over the split's pixels (fp32, fixed order -> deterministic)
-__global__ void __launch_bounds__(kThreads)
-gap_partial_kernel(TV in, float* __restrict__ partial, int splits) {
-  extern __shared__ float sm[];
+__device__ __forceinline__ void gap_partial_body(TV in, float* __restrict__ partial, int splits, float* sm) {
   const int cgs = (in.c + 7) >> 3;
   const int cp = cgs * 8;
   const int lanes = max(1, kThreads / cgs);
@@ -557,20 +556,24 @@ gap_partial_kernel(TV in, float* __restrict__ partial, int splits) {
   }
 }
 
-// blk: w1[cmid][c], b1[cmid], w2[c][cmid], b2[c]
-template <int kSeSamples>
 __global__ void __launch_bounds__(kThreads)
-se_fc_kernel(const float* __restrict__ partial, int splits, float inv_hw0, int n_total, int c, int cmid,
-             const float* __restrict__ blk, float slope, float offset, float* __restrict__ gate,
-             const int* __restrict__ vw_in, int h) {
-  // One block = kSeSamples consecutive samples: the two small matrices (c x cmid floats each) are read once per
-  // block instead of once per sample; one thread owns one output neuron of all its samples (no reductions).
-  // blk: w1t[c][cmid], b1[cmid], w2t[cmid][c], b2[c].
+gap_partial_kernel(TV in, float* __restrict__ partial, int splits) {
   extern __shared__ float sm[];
+  gap_partial_body(in, partial, splits, sm);
+}
+
+// blk: w1[cmid][c], b1[cmid], w2[c][cmid], b2[c]
+// SE gate of kSeSamples consecutive samples starting at n0, computed by one block: the two small matrices (c x cmid
+// floats each) are read once per block; one thread owns one output neuron of all its samples (no reductions).
+// blk: w1t[c][cmid], b1[cmid], w2t[cmid][c], b2[c].  `partial` may have been written by other blocks of the SAME
+// kernel (fused pool + gate): it is read through L2 (__ldcg).
+template <int kSeSamples>
+__device__ __forceinline__ void se_fc_body(float* sm, const float* partial, int splits, float inv_hw0, int n0, int n_total,
+                                           int c, int cmid, const float* __restrict__ blk, float slope, float offset,
+                                           float* __restrict__ gate, const int* __restrict__ vw_in, int h) {
   const int cp = (c + 7) / 8 * 8;
   float* pooled = sm;                      // [kSeSamples][cp]
   float* hidden = sm + kSeSamples * cp;    // [kSeSamples][cmid]
-  const int n0 = blockIdx.x * kSeSamples;
   const int ns = min(kSeSamples, n_total - n0);
   for (int t = threadIdx.x; t < kSeSamples * cp; t += blockDim.x) {
     const int sidx = t / cp, i = t - sidx * cp;
@@ -579,7 +582,7 @@ se_fc_kernel(const float* __restrict__ partial, int splits, float inv_hw0, int n
       const int n = n0 + sidx;
       const float inv_hw = vw_in ? 1.f / float(h * vw_in[n]) : inv_hw0;
       float s = 0.f;
-      for (int k = 0; k < splits; ++k) s += partial[(long(n) * splits + k) * cp + i];
+      for (int k = 0; k < splits; ++k) s += __ldcg(partial + (long(n) * splits + k) * cp + i);
       v = s * inv_hw;
     }
     pooled[t] = v;
@@ -651,6 +654,39 @@ se_fc_kernel(const float* __restrict__ partial, int splits, float inv_hw0, int n
     for (int q = 0; q < kSeSamples; ++q)
       if (q < ns) gate[long(n0 + q) * cp + i] = a[q];
   }
+}
+
+template <int kSeSamples>
+__global__ void __launch_bounds__(kThreads)
+se_fc_kernel(const float* __restrict__ partial, int splits, float inv_hw0, int n_total, int c, int cmid,
+             const float* __restrict__ blk, float slope, float offset, float* __restrict__ gate,
+             const int* __restrict__ vw_in, int h) {
+  extern __shared__ float sm[];
+  se_fc_body<kSeSamples>(sm, partial, splits, inv_hw0, blockIdx.x * kSeSamples, n_total, c, cmid, blk, slope, offset, gate,
+                         vw_in, h);
+}
+
+// Global average pool fused with the SE gate: the block that finishes a sample's LAST row split (ticket counter) turns
+// the sample's partial sums into its gate right away -- one launch less per SE block, and the gates of the first
+// samples are computed while the later samples are still being pooled.  The sums are added in split order by that
+// one block, so the result does not depend on which block came last.
+__global__ void __launch_bounds__(kThreads)
+gap_se_kernel(TV in, float* __restrict__ partial, int splits, SeFuse fc) {
+  extern __shared__ float sm[];
+  __shared__ int s_last;
+  gap_partial_body(in, partial, splits, sm);
+  __threadfence();
+  __syncthreads();
+  const int n = blockIdx.y;
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(fc.counters + n, 1);
+    s_last = ticket == splits - 1;
+    if (s_last) fc.counters[n] = 0;  // ready for the next launch (every other block of this sample is past its atomicAdd)
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  se_fc_body<1>(sm, partial, splits, fc.inv_hw, n, in.n, fc.c, fc.cmid, fc.blk, fc.slope, fc.offset, fc.gate, fc.vw_in, fc.h);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -1132,10 +1168,15 @@ int gap_splits(int h) {
   return h < 1 ? 1 : (h > 8 ? 8 : h);
 }
 
-void launch_gap_partial(const TV& in, float* partial, int splits, cudaStream_t s) {
+void launch_gap_partial(const TV& in, float* partial, int splits, cudaStream_t s, const SeFuse* fuse) {
   const int cgs = (in.c + 7) / 8;
   const int lanes = kThreads / cgs > 0 ? kThreads / cgs : 1;
-  const size_t smem = size_t(lanes) * cgs * 8 * sizeof(float);
+  size_t smem = size_t(lanes) * cgs * 8 * sizeof(float);
+  if (fuse) {
+    smem = std::max(smem, size_t(cgs * 8 + 3 * fuse->cmid) * sizeof(float));
+    gap_se_kernel<<<dim3(splits, in.n), kThreads, smem, s>>>(in, partial, splits, *fuse);
+    return;
+  }
   gap_partial_kernel<<<dim3(splits, in.n), kThreads, smem, s>>>(in, partial, splits);
 }
 
