@@ -500,3 +500,25 @@ def kernel_attention(qkv, heads, head_dim, scale, valid=None, device=0):
     check(lib.b200ocr_kernel_attention(device, qkv.ctypes.data, n, t, heads, head_dim, scale,
                                        None if vd is None else vd.ctypes.data, out.ctypes.data))
     return out
+
+
+_sig("b200ocr_kernel_conv", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+     C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
+
+
+def kernel_conv(x, filt, bias, act=0, post_scale=1.0, post_shift=0.0, residual=None, out_widths=None, force_simt=False,
+                device=0):
+    """x [n,cin,h,w], filt [cout,cin,kh,kw] (stride 1, same padding), bias [cout] -> [n,cout,h,w] fp32."""
+    x = np.ascontiguousarray(x, np.float32)
+    filt = np.ascontiguousarray(filt, np.float32)
+    bias = np.ascontiguousarray(bias, np.float32)
+    n, cin, h, w = x.shape
+    cout, cin2, kh, kw = filt.shape
+    assert cin2 == cin
+    out = np.empty((n, cout, h, w), np.float32)
+    res = None if residual is None else np.ascontiguousarray(residual, np.float32)
+    wd = None if out_widths is None else np.ascontiguousarray(out_widths, np.int32)
+    check(lib.b200ocr_kernel_conv(device, x.ctypes.data, n, cin, h, w, filt.ctypes.data, bias.ctypes.data, cout, kh, kw, act,
+                                  post_scale, post_shift, None if res is None else res.ctypes.data,
+                                  None if wd is None else wd.ctypes.data, 1 if force_simt else 0, out.ctypes.data))
+    return out

@@ -114,4 +114,59 @@ int b200ocr_kernel_attention(int device, const float* qkv, int n, int t, int hea
   });
 }
 
+int b200ocr_kernel_conv(int device, const float* x, int n, int cin, int h, int w, const float* filt, const float* bias,
+                        int cout, int kh, int kw, int act, float post_scale, float post_shift, const float* residual,
+                        const int* out_widths, int force_simt, float* out) {
+  return capi_guard([&] {
+    if (!x || !filt || !bias || !out || n < 1 || cin < 1 || cout < 1 || h < 1 || w < 1) throw std::invalid_argument("bad argument");
+    if (kh < 1 || kw < 1 || !(kh & 1) || !(kw & 1)) throw std::invalid_argument("odd filter sizes only (same padding, stride 1)");
+    cuda_check(cudaSetDevice(device), "cudaSetDevice");
+    const int ip = round_up(cin, 8), op = round_up(cout, 8), taps = kh * kw;
+    const int cin_pad = round_up(cin, 64), cout_pad = round_up(cout, 16);
+    std::vector<uint16_t> hx = to_nhwc_f16(x, n, cin, h, w, ip);
+    // dense filter as plan.cpp packs it: fp16 [cout_pad][taps][cin_pad]; filt is [cout][cin][kh][kw]
+    std::vector<uint16_t> hw(size_t(cout_pad) * taps * cin_pad, 0);
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int t = 0; t < taps; ++t)
+          hw[(size_t(co) * taps + t) * cin_pad + ci] = f32_to_f16_bits(filt[(size_t(co) * cin + ci) * taps + t]);
+    std::vector<float> hb(cout_pad, 0.f);
+    for (int co = 0; co < cout; ++co) hb[co] = bias[co];
+    std::vector<uint16_t> hr;
+    if (residual) hr = to_nhwc_f16(residual, n, cout, h, w, op);
+    DevMem dx(hx.size() * 2), dy(size_t(n) * h * w * op * 2), dw(hw.size() * 2), db(hb.size() * 4), dr(hr.size() * 2 + 16),
+        dvw(size_t(n) * 4);
+    cuda_check(cudaMemcpy(dx.p, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice), "upload");
+    cuda_check(cudaMemcpy(dw.p, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice), "upload");
+    cuda_check(cudaMemcpy(db.p, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice), "upload");
+    if (residual) cuda_check(cudaMemcpy(dr.p, hr.data(), hr.size() * 2, cudaMemcpyHostToDevice), "upload");
+    if (out_widths) cuda_check(cudaMemcpy(dvw.p, out_widths, size_t(n) * 4, cudaMemcpyHostToDevice), "upload");
+    cuda_check(cudaMemset(dy.p, 0xff, size_t(n) * h * w * op * 2), "memset");
+    TV in, o;
+    in.p = dx.as<__half>(); in.n = n; in.h = h; in.w = w; in.c = cin; in.pitch = ip;
+    o.p = dy.as<__half>(); o.n = n; o.h = h; o.w = w; o.c = cout; o.pitch = op;
+    ConvGeom g;
+    g.kh = kh; g.kw = kw; g.sh = g.sw = 1; g.ph = kh / 2; g.pw = kw / 2; g.cin_pad = cin_pad; g.cout_pad = cout_pad;
+    Epi e;
+    e.act = act; e.s2 = post_scale; e.t2 = post_shift;
+    if (residual) { e.res = dr.as<__half>(); e.res_pitch = op; }
+    const int* vw = out_widths ? dvw.as<int>() : nullptr;
+    if (!force_simt && conv_tc_eligible(in, o, g)) {
+      ConvTcPlan plan = make_conv_tc_plan(in, o, dw.as<__half>(), g);
+      launch_conv_tc(plan, db.as<float>(), e, nullptr, vw);
+      cuda_check(cudaDeviceSynchronize(), "conv_tc");
+      free_conv_tc_plan(&plan);
+    } else {
+      launch_conv_simt(in, o, dw.as<__half>(), db.as<float>(), g, e, nullptr, vw);
+      cuda_check(cudaDeviceSynchronize(), "conv_simt");
+    }
+    cuda_check(cudaGetLastError(), "conv launch");
+    std::vector<uint16_t> hy(size_t(n) * h * w * op);
+    cuda_check(cudaMemcpy(hy.data(), dy.p, hy.size() * 2, cudaMemcpyDeviceToHost), "download");
+    for (size_t i = 0; i < hy.size(); ++i)
+      if (int(i % op) >= cout && hy[i] != 0) throw std::runtime_error("conv left a non-zero pad channel");
+    from_nhwc_f16(hy, n, cout, h, w, op, out);
+  });
+}
+
 }  // extern "C"

@@ -231,6 +231,13 @@ int b200ocr_net_launches(b200ocr_net_t net);
 int b200ocr_kernel_dwconv(int device, const float* x, int n, int c, int h, int w, const float* filt, const float* bias,
                           int k, int sh, int sw, int act, float post_scale, float post_shift, int fp16_weights,
                           const int* out_widths, float* out, int* out_h, int* out_w);
+/* Dense convolution = Paddle conv2d (stride 1, "same" padding, odd kh x kw; + folded bias, activation 0 none / 1 relu /
+ * 2 hard-swish / 3 swish, scalar affine, optional residual [n,cout,h,w] added after the affine): x [n,cin,h,w], filt
+ * [cout][cin][kh][kw].  Takes the tcgen05 implicit-GEMM kernel when the shape is eligible (cin >= 8), the CUDA-core
+ * kernel otherwise or when force_simt != 0.  out_widths as above.  out [n,cout,h,w]. */
+int b200ocr_kernel_conv(int device, const float* x, int n, int cin, int h, int w, const float* filt, const float* bias,
+                        int cout, int kh, int kw, int act, float post_scale, float post_shift, const float* residual,
+                        const int* out_widths, int force_simt, float* out);
 /* SVTR self-attention on packed qkv rows [n][t][3][heads][head_dim] -> out [n][t][heads*head_dim];
  * valid (may be NULL): tokens per sequence, keys beyond it are ignored and queries beyond it give zeros. */
 int b200ocr_kernel_attention(int device, const float* qkv, int n, int t, int heads, int head_dim, float scale,

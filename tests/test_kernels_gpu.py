@@ -107,3 +107,63 @@ def test_attention_ragged_rows_equal_dense_rows_bitwise():
         alone = b200ocr.kernel_attention(qkv[i:i + 1, :tv], heads, hd, hd ** -0.5)
         assert np.array_equal(got[i, :tv], alone[0])
         assert not got[i, tv:].any()
+
+
+def _ref_conv(x, filt, bias, act, s2, t2, residual):
+    import torch
+    import torch.nn.functional as F
+    kh, kw = filt.shape[2:]
+    y = F.conv2d(torch.tensor(x), torch.tensor(filt), torch.tensor(bias), padding=(kh // 2, kw // 2))
+    if act == 1:
+        y = torch.relu(y)
+    elif act == 2:
+        y = y * torch.clamp(y + 3, 0, 6) / 6
+    elif act == 3:
+        y = y * torch.sigmoid(y)
+    y = s2 * y + t2
+    if residual is not None:
+        y = y + torch.tensor(residual)
+    return y.numpy()
+
+
+# tcgen05 implicit GEMM on shapes the shipped graphs do not contain: pixel counts that are not a multiple of the 128-row
+# tile, channel counts that leave partial K chunks / partial 16-column groups / more than one N tile, 1x1, 1x3, 3x3
+@pytest.mark.parametrize("n,cin,cout,h,w,kh,kw", [
+    (3, 16, 32, 14, 37, 1, 1), (2, 64, 64, 7, 100, 1, 1), (5, 240, 240, 7, 33, 1, 1), (2, 480, 480, 2, 51, 1, 1),
+    (1, 120, 360, 1, 97, 1, 1), (4, 96, 24, 20, 32, 3, 3), (2, 24, 24, 40, 64, 3, 3), (1, 96, 96, 10, 16, 3, 3),
+    (3, 64, 120, 1, 61, 1, 3), (2, 8, 16, 9, 9, 1, 1), (1, 40, 136, 5, 13, 3, 3), (7, 200, 72, 3, 19, 1, 1),
+    (2, 384, 96, 10, 16, 1, 1), (1, 72, 264, 6, 50, 1, 1), (2, 136, 8, 12, 12, 3, 3), (40, 240, 240, 7, 100, 1, 1),
+])
+@pytest.mark.parametrize("simt", [False, True], ids=["tcgen05", "cuda-core"])
+def test_conv_matches_torch(n, cin, cout, h, w, kh, kw, simt):
+    import b200ocr
+    if simt and cin * cout * kh * kw * h * w * n > 3e8:
+        pytest.skip("CUDA-core path only on the small shapes")
+    rng = np.random.default_rng(cin * 7 + cout * 3 + h + w + kh)
+    x = _h(rng.standard_normal((n, cin, h, w)))
+    filt = _h(rng.standard_normal((cout, cin, kh, kw)) / np.sqrt(cin * kh * kw))
+    bias = rng.standard_normal(cout).astype(np.float32) * 0.2
+    act = int(rng.integers(0, 4))
+    s2, t2 = (0.95, 0.03) if act == 2 else (1.0, 0.0)
+    res = _h(rng.standard_normal((n, cout, h, w))) if (cin + cout) % 3 == 0 else None
+    got = b200ocr.kernel_conv(x, filt, bias, act, s2, t2, residual=res, force_simt=simt)
+    ref = _ref_conv(x, filt, bias, act, s2, t2, res)
+    tol = 2e-3 * float(np.abs(ref).max()) + 2e-3
+    assert float(np.abs(got - ref).max()) <= tol, (float(np.abs(got - ref).max()), tol)
+
+
+def test_conv_ragged_rows_equal_dense_rows_bitwise():
+    import b200ocr
+    rng = np.random.default_rng(11)
+    for (cin, cout, h, w, kh, kw) in [(240, 240, 7, 100, 1, 1), (64, 120, 1, 97, 1, 3), (96, 24, 4, 60, 3, 3)]:
+        widths = [w, w // 2 + 3, 9, w - 1]
+        x = _h(rng.standard_normal((len(widths), cin, h, w)))
+        for i, wd in enumerate(widths):
+            x[i, :, :, wd:] = 0
+        filt = _h(rng.standard_normal((cout, cin, kh, kw)) / np.sqrt(cin * kh * kw))
+        bias = rng.standard_normal(cout).astype(np.float32) * 0.2
+        got = b200ocr.kernel_conv(x, filt, bias, 2, 1.03, -0.02, out_widths=widths)
+        for i, wd in enumerate(widths):
+            alone = b200ocr.kernel_conv(x[i:i + 1, :, :, :wd], filt, bias, 2, 1.03, -0.02)
+            assert np.array_equal(got[i, :, :, :wd], alone[0]), (cin, cout, kh, kw, i)
+            assert not got[i, :, :, wd:].any()
