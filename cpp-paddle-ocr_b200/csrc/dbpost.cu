@@ -148,6 +148,12 @@ __device__ __forceinline__ int outer_bg(const int* L, const int* touch, int C, i
 struct Slot {  // per-pixel arrays, meaningful at contour start pixels only
   int* flag;
   int* x0; int* y0; int* x1; int* y1;
+  // "slow" score mode only (nullptr otherwise).  Fixed-point (Q32) sums of the probability map and pixel counts:
+  //   at the first pixel of a component (foreground or hole): over the component AND everything nested inside it,
+  //   at the start pixel of a hole border (the pixel left of the hole's first pixel): over that border's pixels.
+  // The two kinds of index never coincide (a hole's first pixel lies below the first row of the component around it).
+  unsigned long long* sum;
+  int* cnt;
 };
 
 __global__ void __launch_bounds__(256)
@@ -155,13 +161,59 @@ slot_init_kernel(Slot s, long total) {
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
     s.flag[t] = 0;
     s.x0[t] = 0x7fffffff; s.y0[t] = 0x7fffffff; s.x1[t] = -1; s.y1[t] = -1;
+    if (s.sum) { s.sum[t] = 0ull; s.cnt[t] = 0; }
+  }
+}
+
+// Q32 fixed point: exact for p >= 2^-9, truncated below (error < 2^-32 per pixel); integer sums make the score
+// independent of the order in which the atomics arrive
+__device__ __forceinline__ unsigned long long prob_q32(float p) {
+  return (unsigned long long)(double(fminf(fmaxf(p, 0.f), 1.f)) * 4294967296.0);
+}
+
+// ---------------------------------------------------------------- "slow" score: sums over nested regions
+// PolygonScoreAcc (reference src/postprocess_op.cpp:170-214) fills the contour polygon and averages the probability
+// map under it.  A traced border only has horizontal, vertical and diagonal unit steps, so cv::fillPoly of it is the
+// border's pixels plus everything the border encloses.  Set-based: the components form a containment tree
+// (a foreground component's parent is the background component left of its first pixel; a hole's parent is the
+// foreground component left of its first pixel; the frame-connected background is the root).  The polygon of C's
+// outer border covers C and all its descendants; the polygon of hole B's border covers B, its descendants and the
+// border pixels themselves.  Every pixel adds its value to all its ancestors (depth is 1-3 on text maps).
+__global__ void __launch_bounds__(256)
+nest_sum_kernel(const uint8_t* __restrict__ bm, const float* __restrict__ prob, const int* __restrict__ L,
+                const int* __restrict__ touch, Slot s, int n, int h, int w) {
+  const long per = long(h) * w, total = per * n;
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    const unsigned long long q = prob_q32(prob[t]);
+    const long ibase = (t / per) * per;
+    int node;           // global index of the first pixel of the current ancestor
+    bool fg = bm[t] != 0;
+    if (fg) node = L[t];
+    else {
+      node = canon_bg(L, touch, t);
+      if (node == kFrame) continue;
+    }
+    for (int depth = 0; depth < 4096; ++depth) {
+      atomicAdd(&s.sum[node], q);
+      atomicAdd(&s.cnt[node], 1);
+      if (fg) {  // parent of a foreground component: the background left of its first pixel
+        const int local = int(node - ibase);
+        const int b = (local % w) == 0 ? kFrame : canon_bg(L, touch, long(node) - 1);
+        if (b == kFrame) break;
+        node = b;
+        fg = false;
+      } else {   // parent of a hole: the foreground component left of its first pixel
+        node = L[node - 1];
+        fg = true;
+      }
+    }
   }
 }
 
 // ---------------------------------------------------------------- 2. border pixels -> start pixel
 __global__ void __launch_bounds__(256)
 mark_kernel(const uint8_t* __restrict__ bm, const int* __restrict__ L, const int* __restrict__ touch, Slot s,
-            int n, int h, int w) {
+            int n, int h, int w, const float* __restrict__ prob) {
   const long per = long(h) * w, total = per * n;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
     if (bm[t] == 0) continue;
@@ -192,6 +244,10 @@ mark_kernel(const uint8_t* __restrict__ bm, const int* __restrict__ L, const int
       s.flag[slot] = 1;
       atomicMin(&s.x0[slot], x); atomicMin(&s.y0[slot], y);
       atomicMax(&s.x1[slot], x); atomicMax(&s.y1[slot], y);
+      if (s.sum && B != bout) {  // "slow" score: the hole border's own pixels
+        atomicAdd(&s.sum[slot], prob_q32(prob[t]));
+        atomicAdd(&s.cnt[slot], 1);
+      }
     }
   }
 }
@@ -348,10 +404,21 @@ boxes_kernel(DbPostParams P, const float* __restrict__ prob, const uint8_t* __re
   }
   __syncthreads();
   if (!sh_i[1]) return;
-  // ---- BoxScoreFast: masked mean of the probability map over the filled (integer-truncated) quad
   geom::P2 mb[4];
   for (int k = 0; k < 4; ++k) { mb[k].x = sh_f[2 * k]; mb[k].y = sh_f[2 * k + 1]; }
-  {
+  if (P.score_slow) {
+    // ---- PolygonScoreAcc: mean over the filled contour polygon = nested-region sums (see nest_sum_kernel)
+    if (threadIdx.x == 0) {
+      unsigned long long qs;
+      long long qc;
+      if (outer) { qs = s.sum[C]; qc = s.cnt[C]; }
+      else { qs = s.sum[slot + 1] + s.sum[slot]; qc = (long long)s.cnt[slot + 1] + s.cnt[slot]; }
+      const float score = qc > 0 ? float(double(qs) / 4294967296.0 / double(qc)) : 0.f;
+      sh_f[8] = score;
+      sh_i[1] = !(score < P.box_thresh);
+    }
+  } else {
+    // ---- BoxScoreFast: masked mean of the probability map over the filled (integer-truncated) quad
     float mnx = mb[0].x, mxx = mb[0].x, mny = mb[0].y, mxy = mb[0].y;
     for (int k = 1; k < 4; ++k) {
       mnx = fminf(mnx, mb[k].x); mxx = fmaxf(mxx, mb[k].x);
@@ -442,9 +509,10 @@ inline size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 }  // namespace
 
 // workspace layout: L | touch | flag | x0 | y0 | x1 | y1 (int32 per pixel each) | list [n*max_candidates]
+//                   [| sum (u64 per pixel) | cnt (int32 per pixel)   in "slow" score mode]
 size_t dbpost_workspace_bytes(const DbPostParams& p) {
   const size_t px = size_t(p.n) * p.h * p.w;
-  return 7 * al(px * 4) + al(size_t(p.n) * p.max_candidates * 4);
+  return 7 * al(px * 4) + al(size_t(p.n) * p.max_candidates * 4) + (p.score_slow ? al(px * 8) + al(px * 4) : 0);
 }
 
 void launch_dbpost(const DbPostParams& p, const float* prob, const uint8_t* bitmap, const DbImageInfo* info_dev,
@@ -460,6 +528,12 @@ void launch_dbpost(const DbPostParams& p, const float* prob, const uint8_t* bitm
   s.x1 = reinterpret_cast<int*>(ws + 5 * al(px * 4));
   s.y1 = reinterpret_cast<int*>(ws + 6 * al(px * 4));
   int* list = reinterpret_cast<int*>(ws + 7 * al(px * 4));
+  s.sum = nullptr; s.cnt = nullptr;
+  if (p.score_slow) {
+    uint8_t* extra = ws + 7 * al(px * 4) + al(size_t(p.n) * p.max_candidates * 4);
+    s.sum = reinterpret_cast<unsigned long long*>(extra);
+    s.cnt = reinterpret_cast<int*>(extra + al(px * 8));
+  }
   const int g = grid_for(long(px));
   if (p.w % 32 == 0) ccl_runs_init_kernel<<<g, 256, 0, st>>>(bitmap, L, touch, long(px));
   else ccl_init_kernel<<<g, 256, 0, st>>>(L, touch, long(px));
@@ -467,7 +541,8 @@ void launch_dbpost(const DbPostParams& p, const float* prob, const uint8_t* bitm
   if (p.w % 32 == 0) ccl_runs_merge_kernel<<<g, 256, 0, st>>>(bitmap, L, p.n, p.h, p.w);
   else ccl_merge_kernel<<<g, 256, 0, st>>>(bitmap, L, p.n, p.h, p.w);
   ccl_flatten_kernel<<<g, 256, 0, st>>>(bitmap, L, touch, p.n, p.h, p.w);
-  mark_kernel<<<g, 256, 0, st>>>(bitmap, L, touch, s, p.n, p.h, p.w);
+  mark_kernel<<<g, 256, 0, st>>>(bitmap, L, touch, s, p.n, p.h, p.w, prob);
+  if (p.score_slow) nest_sum_kernel<<<g, 256, 0, st>>>(bitmap, prob, L, touch, s, p.n, p.h, p.w);
   list_kernel<<<p.n, 1024, 0, st>>>(s.flag, p.h, p.w, p.max_candidates, counts_dev, list);
   const size_t smem = size_t(2) * p.h * sizeof(int);
   boxes_kernel<<<dim3(p.max_candidates, p.n), kBoxThreads, smem, st>>>(p, prob, bitmap, L, touch, s, counts_dev, list,

@@ -126,6 +126,7 @@ struct DbPostParams {
   int n, h, w;            // batch of bitmaps / probability maps
   float box_thresh, unclip_ratio;
   int max_candidates;     // 1000 in the reference
+  int score_slow = 0;     // det_db_score_mode "slow": PolygonScoreAcc (mean over the filled contour polygon)
 };
 struct DbImageInfo { float ratio_h, ratio_w; int src_h, src_w; };
 struct DbBox { int valid; int pts[8]; float score; int start; };  // start = start pixel (y*w+x) of the contour

@@ -244,6 +244,7 @@ int b200ocr_det_postprocess(b200ocr_det_t d, const float* pred, int h, int w, in
     pp.box_thresh = float(d->p.det_db_box_thresh);
     pp.unclip_ratio = float(d->p.det_db_unclip_ratio);
     pp.max_candidates = 1000;
+    pp.score_slow = d->p.det_db_score_mode == "slow";
     DbImageInfo inf;
     // the detector feeds a map of the resized size; ratios as DBDetector::Run computes them (src/preprocess_op.cpp:91-92)
     inf.ratio_h = float(h) / float(src_h);

@@ -84,9 +84,8 @@ void DetStage::resized_dims(int rows, int cols, const std::string& limit_type, i
 DetStage::DetStage(const std::string& model_dir, int device, const DetParams& p)
     : net_(model_dir, device, NetOptions()), p_(p) {
   if (net_.kind() != "det") throw std::runtime_error("model in " + model_dir + " is not a DB detector graph");
-  if (p.det_db_score_mode != "fast")
-    throw std::invalid_argument("det_db_score_mode \"" + p.det_db_score_mode +
-                                "\" is not implemented on the GPU path yet (only \"fast\", the worker's setting)");
+  if (p.det_db_score_mode != "fast" && p.det_db_score_mode != "slow")
+    throw std::invalid_argument("det_db_score_mode \"" + p.det_db_score_mode + "\" is neither \"fast\" nor \"slow\"");
   // cv::threshold on 8-bit data floors the threshold: bit = cbuf > floor(thresh * 255)  (src/ocr_det.cpp:151-154)
   thresh_u8_ = int(std::floor(double(float(p.det_db_thresh)) * 255));
 }
@@ -146,6 +145,7 @@ void DetStage::run_group(const std::vector<DevImg>& imgs, const std::vector<int>
   pp.box_thresh = float(p_.det_db_box_thresh);
   pp.unclip_ratio = float(p_.det_db_unclip_ratio);
   pp.max_candidates = 1000;
+  pp.score_slow = p_.det_db_score_mode == "slow";  // PolygonScoreAcc instead of BoxScoreFast (postprocess_op.cpp:285-288)
   ws_.ensure(dbpost_workspace_bytes(pp));
   counts_.ensure(sizeof(int) * n);
   boxes_.ensure(sizeof(DbBox) * size_t(n) * pp.max_candidates);
@@ -159,7 +159,7 @@ void DetStage::run_group(const std::vector<DevImg>& imgs, const std::vector<int>
     ++launches;
   }
   launch_dbpost(pp, net_.out_f32(), bitmap, info_.as<DbImageInfo>(), ws_.p, counts_.as<int>(), boxes_.as<DbBox>(), s);
-  launches += 7;
+  launches += 7 + pp.score_slow;
   cuda_check(cudaMemcpyAsync(h_counts_.p, counts_.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s), "det counts");
   cuda_check(cudaStreamSynchronize(s), "det post-process");
   // second copy sized by what was found (boxes of image k live at [k * max_candidates, +count))

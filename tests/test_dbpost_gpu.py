@@ -106,5 +106,34 @@ def test_dilation_and_other_thresholds(models_dir):
     ref, rbm = _oracle(pred, 320, 512, det_db_thresh=0.3, det_db_box_thresh=0.5, det_db_unclip_ratio=2.0, use_dilation=True)
     assert np.array_equal(bm, rbm)
     _compare(got, ref)
-    with pytest.raises(b200ocr.Error, match="slow"):
-        b200ocr.Detector(f"{models_dir}/det", det_db_score_mode="slow")
+    with pytest.raises(b200ocr.Error, match="neither"):
+        b200ocr.Detector(f"{models_dir}/det", det_db_score_mode="medium")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_slow_score_mode_matches_polygon_score_acc(models_dir, seed):
+    """det_db_score_mode = "slow": PolygonScoreAcc (cv2.fillPoly of the contour + masked mean, postprocess_op.cpp:170-214)
+    against the GPU's nested-region sums, on maps with rings (hole borders, whose polygon covers the low-probability
+    hole) and nested blobs; a box_thresh in the middle of the score range makes the scores decide which boxes survive."""
+    import b200ocr, synth_data
+    from oracle import ocr_ops
+    h, w = [(320, 512), (192, 384), (160, 256), (96, 160)][seed % 4]
+    pred = synth_data.prob_map(100 + seed, h, w, n_boxes=5 + seed, rings=4, lines=2)
+    if seed % 2:  # nested: a blob inside a ring's hole, and a hole inside that blob
+        pred[h // 2 - 6:h // 2 + 6, w // 2 - 20:w // 2 + 20] = 0.95
+        pred[h // 2 - 2:h // 2 + 2, w // 2 - 8:w // 2 + 8] = 0.02
+        pred[h // 2 - 14:h // 2 - 10, w // 2 - 30:w // 2 + 30] = 0.9
+        pred[h // 2 + 10:h // 2 + 14, w // 2 - 30:w // 2 + 30] = 0.9
+        pred[h // 2 - 14:h // 2 + 14, w // 2 - 30:w // 2 - 26] = 0.9
+        pred[h // 2 - 14:h // 2 + 14, w // 2 + 26:w // 2 + 30] = 0.9
+    differs = False
+    for box_thresh in (0.3, 0.55, 0.7):
+        d = b200ocr.Detector(f"{models_dir}/det", det_db_thresh=0.2, det_db_box_thresh=box_thresh, det_db_unclip_ratio=1.8,
+                             det_db_score_mode="slow")
+        got = d.postprocess(pred, 2 * h, 2 * w)
+        ref, _ = ocr_ops.det_postprocess(pred, np.float32(0.5), np.float32(0.5), 2 * h, 2 * w, 0.2, box_thresh, 1.8, "slow", False)
+        fast, _ = ocr_ops.det_postprocess(pred, np.float32(0.5), np.float32(0.5), 2 * h, 2 * w, 0.2, box_thresh, 1.8, "fast", False)
+        _compare(got, ref, tol=2)
+        differs |= len(fast) != len(ref)
+    if seed == 0:
+        assert differs  # the two score modes do select different boxes on this map
