@@ -46,6 +46,7 @@ _sig("b200ocr_net_out_shape", C.c_int, C.c_void_p, C.POINTER(C.c_int))
 _sig("b200ocr_net_output", C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
 _sig("b200ocr_net_fetch", C.c_int, C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int))
 _sig("b200ocr_net_launches", C.c_int, C.c_void_p)
+_sig("b200ocr_pool_status", C.c_int, C.c_void_p, C.POINTER(C.c_void_p))
 
 
 def check(rc):
@@ -387,6 +388,12 @@ class Pool(_Handle):
     @property
     def idle_count(self):
         return lib.b200ocr_pool_idle_count(self._h)
+
+    def status(self) -> dict:
+        """Service counters (reference OCRIPCService::getStatusInfo, src/ocr_ipc_service.cpp:438-448)."""
+        p = C.c_void_p()
+        check(lib.b200ocr_pool_status(self._h, C.byref(p)))
+        return json.loads(_take_string(p))
 
 
 def resize_u8(img, dst_rows, dst_cols, device=0):

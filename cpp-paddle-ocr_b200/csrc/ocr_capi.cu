@@ -1,5 +1,6 @@
 // C ABI of the stages, the worker and the per-device pool (declared in include/b200ocr.h).
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -81,6 +82,7 @@ struct b200ocr_pool {
     int request_id;
     std::vector<uint8_t> pixels;  // deep copy, like OCRRequest (reference include/paddle_ocr/ocr_worker.h:28-29)
     int rows, cols;
+    std::chrono::steady_clock::time_point t_submit;
   };
   struct Device {
     int device;
@@ -99,6 +101,11 @@ struct b200ocr_pool {
   std::condition_variable res_cv;
   std::map<long long, std::string> results;
   int max_batch = 64;
+  // status counters (reference OCRIPCService::getStatusInfo, src/ocr_ipc_service.cpp:438-448 -- whose success / time
+  // counters are declared but never updated; these are)
+  std::atomic<long long> total_requests{0}, successful_requests{0}, failed_requests{0}, batches{0};
+  std::atomic<long long> total_time_us{0};   // sum over requests of (completion - submission)
+  std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
 
   void loop(Device* d, Worker* w) {
     while (true) {
@@ -128,6 +135,12 @@ struct b200ocr_pool {
                    ",\"success\":false,\"worker_id\":" + std::to_string(w->worker_id()) + "}";
       }
       {
+        const auto now = std::chrono::steady_clock::now();
+        for (size_t i = 0; i < take.size(); ++i) {
+          (out[i].find("\"success\":true") != std::string::npos ? successful_requests : failed_requests) += 1;
+          total_time_us += std::chrono::duration_cast<std::chrono::microseconds>(now - take[i]->t_submit).count();
+        }
+        batches += 1;
         std::lock_guard<std::mutex> lk(res_mu);
         for (size_t i = 0; i < take.size(); ++i) results[take[i]->ticket] = std::move(out[i]);
       }
@@ -147,6 +160,9 @@ struct b200ocr_pool {
 };
 
 extern "C" {
+
+int b200ocr_pool_worker_count(b200ocr_pool_t pool);
+int b200ocr_pool_idle_count(b200ocr_pool_t pool);
 
 void* b200ocr_host_alloc(size_t bytes) {
   void* p = nullptr;
@@ -445,6 +461,8 @@ int b200ocr_pool_submit(b200ocr_pool_t pool, int request_id, const b200ocr_image
     auto r = std::make_shared<b200ocr_pool::Request>();
     r->ticket = pool->next_ticket++;
     r->request_id = request_id;
+    r->t_submit = std::chrono::steady_clock::now();
+    pool->total_requests += 1;
     r->rows = img->rows; r->cols = img->cols;
     if (img->data && img->rows > 0 && img->cols > 0) {
       const size_t row = size_t(img->cols) * 3, step = img->step ? img->step : row;
@@ -474,6 +492,28 @@ int b200ocr_pool_wait(b200ocr_pool_t pool, long long ticket, char** json) {
     pool->res_cv.wait(lk, [&] { return pool->results.count(ticket) != 0; });
     *json = dup_string(pool->results[ticket]);
     pool->results.erase(ticket);
+  });
+}
+int b200ocr_pool_status(b200ocr_pool_t pool, char** json) {
+  return capi_guard([&] {
+    if (!pool || !json) throw std::invalid_argument("null argument");
+    const long long done = pool->successful_requests.load() + pool->failed_requests.load();
+    const double avg_ms = done > 0 ? double(pool->total_time_us.load()) / 1e3 / double(done) : 0.0;
+    const double up = std::chrono::duration<double>(std::chrono::steady_clock::now() - pool->t_start).count();
+    size_t queued = 0;
+    for (auto& d : pool->devs) { std::lock_guard<std::mutex> lk(d->mu); queued += d->queue.size(); }
+    // compact, keys in alphabetical order like jsoncpp writes them
+    std::string o = "{\"average_processing_time_ms\":" + json_double(avg_ms) +
+                    ",\"batches\":" + std::to_string(pool->batches.load()) +
+                    ",\"failed_requests\":" + std::to_string(pool->failed_requests.load()) +
+                    ",\"idle_workers\":" + std::to_string(b200ocr_pool_idle_count(pool)) +
+                    ",\"queued_requests\":" + std::to_string(queued) +
+                    ",\"running\":" + (pool->running.load() ? "true" : "false") +
+                    ",\"successful_requests\":" + std::to_string(pool->successful_requests.load()) +
+                    ",\"total_requests\":" + std::to_string(pool->total_requests.load()) +
+                    ",\"uptime_s\":" + json_double(up) +
+                    ",\"workers\":" + std::to_string(b200ocr_pool_worker_count(pool)) + "}";
+    *json = dup_string(o);
   });
 }
 int b200ocr_pool_worker_count(b200ocr_pool_t pool) {

@@ -168,6 +168,11 @@ int b200ocr_pool_submit(b200ocr_pool_t pool, int request_id, const b200ocr_image
 /* Blocks until the request is done; *json is the worker's result line (free with b200ocr_free). */
 int b200ocr_pool_wait(b200ocr_pool_t pool, long long ticket, char** json);
 int b200ocr_pool_worker_count(b200ocr_pool_t pool);
+/* Service counters as one compact JSON object (free with b200ocr_free); the reference's getStatusInfo
+ * (src/ocr_ipc_service.cpp:438-448) plus what it declares but never updates:
+ * {"average_processing_time_ms","batches","failed_requests","idle_workers","queued_requests","running",
+ *  "successful_requests","total_requests","uptime_s","workers"}; the average is submission -> completion. */
+int b200ocr_pool_status(b200ocr_pool_t pool, char** json);
 int b200ocr_pool_idle_count(b200ocr_pool_t pool);
 
 /* ------------------------------------------------------------------ stand-alone image ops (test / utility surface)
