@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(kDwThreads, 4) dwconv_tile_kernel(const DwArgs
       const __half* src = img + long(iy0) * row_stride + long(gx) * a.in.pitch;
       uint32_t dst = sbase + (uint32_t(x + x / SPAN) << (wcl + 2));
       for (int y = 0; y < iht; ++y, src += row_stride, dst += srow) {
-        const bool ok = x_ok && unsigned(iy0 + y) < unsigned(a.in.h);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src : a.in.p), "r"(ok ? 16 : 0)
+        if (unsigned(iy0 + y) >= unsigned(a.in.h)) continue;  // rows above / below the tensor are never read (see below)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(x_ok ? src : a.in.p), "r"(x_ok ? 16 : 0)
                      : "memory");
       }
     }
@@ -144,9 +144,20 @@ __global__ void __launch_bounds__(kDwThreads, 4) dwconv_tile_kernel(const DwArgs
   const uint32_t* tile = reinterpret_cast<const uint32_t*>(dw_smem);
   const int row_words = phys_iw << wcl;
   const uint32_t* base = tile + (rb * R * SH) * row_words + ((sx * (SPAN + 1)) << wcl) + lane_c;
+  // input rows above / below the tensor are all zero (the conv's vertical padding): a whole feature map per tile
+  // (the recognizer: 7 rows, 11 with the 5x5 halo) spends a sixth of its multiply-adds on them unless they are skipped
+  // Static stride-1 variants cover the whole height (in.h == RB * R, padding K / 2: checked on the host), so which of a
+  // row block's rows are padding is known at compile time for RB == 1 and costs nothing; otherwise a warp-uniform test.
+  constexpr bool kStaticRows = STATIC && SH == 1 && RB_T == 1;
+  const int vy0 = -(iy0 + rb * R * SH), vy1 = a.in.h - (iy0 + rb * R * SH);  // valid rows of this thread's window
 #pragma unroll
   for (int iy = 0; iy < IHR; ++iy) {
     if (!STATIC && iy > (nrows - 1) * SH + K - 1) break;  // below the last row that matters
+    if (kStaticRows) {
+      if (iy < K / 2 || iy >= K / 2 + R) continue;
+    } else if (iy < vy0 || iy >= vy1) {
+      continue;                                            // warp-uniform
+    }
     uint32_t win[WIN];
 #pragma unroll
     for (int j = 0; j < WIN; ++j) win[j] = base[iy * row_words + ((j + j / SPAN) << wcl)];
@@ -261,7 +272,7 @@ bool launch_dwconv_tile(const TV& in, const TV& out, const float* wb, const __ha
   { dw_launch<K_, SH_, SW_, R_, F_, RB_, WCL_>(a, s); return true; }
   // ---- fully static variants for the recognizer's feature-map heights (14 / 7 / 4 / 2 at rec_img_h = 28):
   // R rows per thread = the whole height, 64-channel chunks (16 for the two narrow 3x3 layers)
-  if (!f32 && !no_static && lane_fill(c8, out.w, 5, 1) >= 0.8) {
+  if (!f32 && !no_static && g.ph == K / 2 && g.pw == K / 2 && (g.sh != 1 || in.h == out.h) && lane_fill(c8, out.w, 5, 1) >= 0.8) {
     if (K == 5 && g.sh == 1 && g.sw == 1 && out.h == 7) DW_CASE(5, 1, 1, 7, false, 1, 5)
     if (K == 5 && g.sh == 1 && g.sw == 1 && out.h == 4) DW_CASE(5, 1, 1, 4, false, 1, 5)
     if (K == 5 && g.sh == 1 && g.sw == 1 && out.h == 2) DW_CASE(5, 1, 1, 2, false, 1, 5)
@@ -272,7 +283,8 @@ bool launch_dwconv_tile(const TV& in, const TV& out, const float* wb, const __ha
     if (K == 3 && g.sh == 2 && g.sw == 1 && out.h == 7) DW_CASE(3, 2, 1, 7, false, 1, 5)
     if (K == 3 && g.sh == 1 && g.sw == 2 && out.h == 7) DW_CASE(3, 1, 2, 7, false, 1, 5)
   }
-  if (!f32 && !no_static && K == 3 && g.sh == 1 && g.sw == 1 && out.h == 14 && lane_fill(c8, out.w, 3, 2) >= 0.8)
+  if (!f32 && !no_static && g.ph == 1 && g.pw == 1 && in.h == out.h && K == 3 && g.sh == 1 && g.sw == 1 && out.h == 14 &&
+      lane_fill(c8, out.w, 3, 2) >= 0.8)
     DW_CASE(3, 1, 1, 7, false, 2, 3)
   // ---- generic variants: rows per thread 8 (4 with fp32 weights or a vertical stride: register budget), chunk =
   // the one that wastes the fewest lanes (channels x columns), the larger one when it is within 3 %
