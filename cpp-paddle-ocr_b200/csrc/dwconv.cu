@@ -242,6 +242,148 @@ void dw_launch(DwArgs& a, cudaStream_t s) {
   kern<<<unsigned(blocks), kDwThreads, smem, s>>>(a);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant of the static full-height kernels (recognizer: fp16 taps, 64-channel chunks, one row block, column
+// stride 1).  A CTA stays on ONE channel chunk (blockIdx.y) and walks over (image, column tile) pairs: the K*K weights,
+// the bias and all index arithmetic are set up once, and the halo tile is double-buffered so that tile i+1 streams in
+// (cp.async) while tile i is multiplied -- the load -> barrier -> compute bubble of the one-tile-per-CTA kernel is gone.
+template <int K, int SH, int R>
+__global__ void __launch_bounds__(kDwThreads, 4) dwconv_persist_kernel(const DwArgs a, const int n_tiles) {
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  constexpr int SW = 1, TW = 16, WIN = (kS - 1) * SW + K, IHR = (R - 1) * SH + K, IW = (TW - 1) * SW + K;
+  constexpr uint32_t kTileBytes = IHR * IW * 128;
+  const int c0 = blockIdx.y * 64;
+  const int c8 = (a.in.c + 7) & ~7;
+  const uint32_t sbase = uint32_t(__cvta_generic_to_shared(dw_smem));
+  const long row_stride = long(a.in.w) * a.in.pitch;
+  const int vy0 = a.ph, vy1 = a.ph + a.in.h;   // tile rows that hold real input rows (the rest is the conv's zero padding)
+
+  auto load_tile = [&](int tile, int buf) {
+    const int tx = tile % a.tiles_x, n = tile / a.tiles_x;
+    const int piece = threadIdx.x & 7;
+    const bool c_ok = c0 + piece * 8 < c8;
+    const __half* img = a.in.p + long(n) * a.in.h * row_stride + c0 + piece * 8;
+    const int ix0 = tx * TW * SW - a.pw;
+#pragma unroll
+    for (int pass = 0; pass < (IW + 15) / 16; ++pass) {
+      const int x = (threadIdx.x >> 3) + 16 * pass;
+      if (x < IW) {
+        const int gx = ix0 + x;
+        const bool x_ok = c_ok && gx >= 0 && gx < a.in.w;
+        const __half* src = img + long(gx) * a.in.pitch;      // input row 0
+        uint32_t dst = sbase + buf * kTileBytes + (uint32_t(vy0 * IW + x) << 7) + piece * 16;
+        for (int gy = 0; gy < a.in.h && vy0 + gy < IHR; ++gy, src += row_stride, dst += IW * 128)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(x_ok ? src : a.in.p), "r"(x_ok ? 16 : 0)
+                       : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int tile = blockIdx.x;
+  if (tile < n_tiles) load_tile(tile, 0);
+
+  const int lane_c = threadIdx.x & 31, sx = threadIdx.x >> 5;
+  const int ch = c0 + 2 * lane_c;
+  const bool ch_ok = ch < c8;
+  const int chc = ch_ok ? ch : 0;
+  uint32_t wq[K * K];
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) wq[t] = __ldg(reinterpret_cast<const uint32_t*>(a.wh + long(t) * a.cp + chc));
+  const float2 bias = __ldg(reinterpret_cast<const float2*>(a.wb + long(K * K) * a.cp + chc));
+  const bool c_lo = ch < a.out.c, c_hi = ch + 1 < a.out.c;
+  const uint32_t keep = (c_lo ? 0x0000ffffu : 0u) | (c_hi ? 0xffff0000u : 0u);
+  const uint32_t off_row = uint32_t(a.out.w * a.out.pitch);
+  constexpr bool kStaticRows = SH == 1;  // in.h == R, padding K / 2 (host-checked): padding rows known at compile time
+
+  for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int next = tile + gridDim.x;
+    if (next < n_tiles) {
+      load_tile(next, (it + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int tx = tile % a.tiles_x, n = tile / a.tiles_x;
+    const int col0 = tx * TW + sx * kS;
+    if (ch_ok && col0 < a.out.w) {
+      float acc[R][kS][2];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int s_ = 0; s_ < kS; ++s_) { acc[r][s_][0] = bias.x; acc[r][s_][1] = bias.y; }
+      const uint32_t* base = reinterpret_cast<const uint32_t*>(dw_smem + (it & 1) * kTileBytes) + sx * kS * SW * 32 + lane_c;
+#pragma unroll
+      for (int iy = 0; iy < IHR; ++iy) {
+        if (kStaticRows) {
+          if (iy < K / 2 || iy >= K / 2 + R) continue;
+        } else if (iy < vy0 || iy >= vy1) {
+          continue;
+        }
+        uint32_t win[WIN];
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) win[j] = base[(iy * IW + j) * 32];
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+          if ((iy - ky) % SH != 0) continue;
+          const int r = (iy - ky) / SH;
+          if (r < 0 || r >= R) continue;
+#pragma unroll
+          for (int s_ = 0; s_ < kS; ++s_)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) fhfma2(win[s_ * SW + kx], wq[ky * K + kx], acc[r][s_][0], acc[r][s_][1]);
+        }
+      }
+      const int vwn = a.vw ? min(a.vw[n], a.out.w) : a.out.w;
+      uint32_t cmask[kS];
+      bool cstore[kS];
+#pragma unroll
+      for (int s_ = 0; s_ < kS; ++s_) { cmask[s_] = col0 + s_ < vwn ? keep : 0u; cstore[s_] = col0 + s_ < a.out.w; }
+      uint32_t off = uint32_t((n * a.out.h * a.out.w + col0) * a.out.pitch + ch);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int s_ = 0; s_ < kS; ++s_) {
+          float v0 = acc[r][s_][0], v1 = acc[r][s_][1];
+          if (a.act == 2) {
+            v0 *= __saturatef(fmaf(v0, 1.f / 6.f, 0.5f));
+            v1 *= __saturatef(fmaf(v1, 1.f / 6.f, 0.5f));
+          } else if (a.act == 1) {
+            v0 = fmaxf(v0, 0.f);
+            v1 = fmaxf(v1, 0.f);
+          }
+          const __half2 h = __floats2half2_rn(fmaf(a.s2, v0, a.t2), fmaf(a.s2, v1, a.t2));
+          if (cstore[s_])
+            *reinterpret_cast<uint32_t*>(a.out.p + (off + uint32_t(s_ * a.out.pitch))) = *reinterpret_cast<const uint32_t*>(&h) & cmask[s_];
+        }
+        off += off_row;
+      }
+    }
+    __syncthreads();  // everyone is done with this buffer before the load of tile it+2 overwrites it
+  }
+}
+
+template <int K, int SH, int R>
+void dw_persist_launch(DwArgs& a, cudaStream_t s) {
+  constexpr int IHR = (R - 1) * SH + K, IW = 15 + K;
+  a.chunks = (((a.out.c + 7) & ~7) + 63) / 64;
+  a.tiles_x = (a.out.w + 15) / 16;
+  const size_t smem = 2 * size_t(IHR) * IW * 128;
+  auto kern = dwconv_persist_kernel<K, SH, R>;
+  if (smem > 48 * 1024) {
+    static int done_dev[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !done_dev[dev]) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      done_dev[dev] = 1;
+    }
+  }
+  const int n_tiles = a.out.n * a.tiles_x;
+  const int per_chunk = std::max(1, std::min(n_tiles, (148 * 4 + a.chunks - 1) / a.chunks));
+  kern<<<dim3(unsigned(per_chunk), unsigned(a.chunks)), kDwThreads, smem, s>>>(a, n_tiles);
+}
+
 // fraction of the tile's lanes that hold real channels x real columns, for a chunk of 2^(l2+1) channels
 double lane_fill(int c8, int w, int l2, int rbn) {
   const int cc = 2 << l2, wc = 1 << l2;
@@ -272,6 +414,17 @@ bool launch_dwconv_tile(const TV& in, const TV& out, const float* wb, const __ha
   { dw_launch<K_, SH_, SW_, R_, F_, RB_, WCL_>(a, s); return true; }
   // ---- fully static variants for the recognizer's feature-map heights (14 / 7 / 4 / 2 at rec_img_h = 28):
   // R rows per thread = the whole height, 64-channel chunks (16 for the two narrow 3x3 layers)
+  static const bool no_persist = getenv("B200OCR_DWCONV_NO_PERSIST") != nullptr;
+  if (!f32 && !no_static && !no_persist && g.ph == K / 2 && g.pw == K / 2 && g.sw == 1 && (g.sh != 1 || in.h == out.h) &&
+      lane_fill(c8, out.w, 5, 1) >= 0.8) {
+    if (K == 5 && g.sh == 1 && out.h == 7) { dw_persist_launch<5, 1, 7>(a, s); return true; }
+    if (K == 5 && g.sh == 1 && out.h == 4) { dw_persist_launch<5, 1, 4>(a, s); return true; }
+    if (K == 5 && g.sh == 1 && out.h == 2) { dw_persist_launch<5, 1, 2>(a, s); return true; }
+    if (K == 5 && g.sh == 2 && out.h == 4) { dw_persist_launch<5, 2, 4>(a, s); return true; }
+    if (K == 5 && g.sh == 2 && out.h == 2) { dw_persist_launch<5, 2, 2>(a, s); return true; }
+    if (K == 3 && g.sh == 1 && out.h == 7) { dw_persist_launch<3, 1, 7>(a, s); return true; }
+    if (K == 3 && g.sh == 2 && out.h == 7) { dw_persist_launch<3, 2, 7>(a, s); return true; }
+  }
   if (!f32 && !no_static && g.ph == K / 2 && g.pw == K / 2 && (g.sh != 1 || in.h == out.h) && lane_fill(c8, out.w, 5, 1) >= 0.8) {
     if (K == 5 && g.sh == 1 && g.sw == 1 && out.h == 7) DW_CASE(5, 1, 1, 7, false, 1, 5)
     if (K == 5 && g.sh == 1 && g.sw == 1 && out.h == 4) DW_CASE(5, 1, 1, 4, false, 1, 5)
