@@ -248,7 +248,7 @@ void dw_launch(DwArgs& a, cudaStream_t s) {
 // the bias and all index arithmetic are set up once, and the halo tile is double-buffered so that tile i+1 streams in
 // (cp.async) while tile i is multiplied -- the load -> barrier -> compute bubble of the one-tile-per-CTA kernel is gone.
 template <int K, int SH, int R>
-__global__ void __launch_bounds__(kDwThreads, 4) dwconv_persist_kernel(const DwArgs a, const int n_tiles) {
+__global__ void __launch_bounds__(kDwThreads, 3) dwconv_persist_kernel(const DwArgs a, const int n_tiles) {
   extern __shared__ __align__(16) uint8_t dw_smem[];
   constexpr int SW = 1, TW = 16, WIN = (kS - 1) * SW + K, IHR = (R - 1) * SH + K, IW = (TW - 1) * SW + K;
   constexpr uint32_t kTileBytes = IHR * IW * 128;
