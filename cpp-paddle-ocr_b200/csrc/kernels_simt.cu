@@ -918,7 +918,7 @@ attention_kernel(TV qkv, TV out, int heads, int hd, float scale, const int* __re
 // ---------------------------------------------------------------- heads
 // blk: w1[q][ci][cm], b1[cm], w2[cm][4], b2.  One thread per 1/4-scale pixel -> 4x4 output block.
 template <int CIN, int CMID>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 dbhead_kernel(TV in, const float* __restrict__ blk, float* __restrict__ prob,
               uint8_t* __restrict__ bitmap, int thresh_u8) {
   __shared__ float sw1[4 * CIN * CMID];
