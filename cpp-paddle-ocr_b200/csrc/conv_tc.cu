@@ -120,6 +120,15 @@ struct ConvTcArgs {
   int tw, th, tn;          // box: tw*th*tn <= 128 rows
   int tiles_x, tiles_y;    // tiles_n = pixel tiles / (tiles_x*tiles_y)
   int n_tiles;             // N tiles (non-persistent kernel: interleaved in blockIdx.x)
+  // halo mode (persistent kernel, kh*kw > 1): ONE TMA box of (tw+kw-1) x (th+kh-1) pixels per K chunk instead of one
+  // shifted box per filter tap.  The MMA's 128 rows walk the PADDED row pitch row_w = tw+kw-1 (outputs at x >= tw are
+  // discarded), so filter tap (ky,kx) is the same tile read (ky*row_w + kx) rows further down: the descriptor's start
+  // address moves by that many 128-byte rows.  Measured on B200 (tools/diag_halo.py): the 128B-swizzle XOR is taken from
+  // the absolute shared-memory address bits, so a start address that is not 1024-byte aligned needs NO base-offset
+  // field (setting it to (addr >> 7) & 7, as the field's description suggests, gives wrong data).
+  int halo;                // 0 / 1
+  int row_w;               // pixels per tile row as the MMA sees them: tw, or tw+kw-1 in halo mode
+  int a_stage;             // bytes per A ring stage
   int kh, kw, ph, pw;
   int cin, cin_pad;        // logical input channels; weight row stride per tap
   int bn;                  // N tile (multiple of 16, <= 256)
@@ -145,10 +154,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& a, const float* 
   const int q = warp & 3;               // TMEM lane quadrant this warp may read (hardware rule: warp id % 4)
   const int cgrp = (warp - 2) >> 2;     // which share of the 16-column groups
   const int r = q * 32 + lane;
-  const int rows = a.tw * a.th * a.tn;
-  const int tw_ = r % a.tw, th_ = (r / a.tw) % a.th, tn_ = r / (a.tw * a.th);
+  const int rows = a.row_w * a.th * a.tn;
+  const int tw_ = r % a.row_w, th_ = (r / a.row_w) % a.th, tn_ = r / (a.row_w * a.th);
   const int x = x0 + tw_, y = y0 + th_, n = n0 + tn_;
-  const bool valid = r < rows && x < a.ow && y < a.oh && n < a.on;
+  const bool valid = r < rows && tw_ < a.tw && x < a.ow && y < a.oh && n < a.on;
   const long pix = (long(n) * a.oh + y) * a.ow + x;
   const bool masked = valid && a.vw && int(pix % a.mask_w) >= a.vw[pix / a.mask_hw];
   const int c8lim = (a.cout + 7) & ~7;
@@ -372,20 +381,29 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int tap = 0, it = 0; tap < a.kh * a.kw; ++tap)
         for (int kc = 0; kc < kchunks; ++kc, ++it)
           tma_load_2d(&tmB, b_full, tiles + size_t(it) * b_chunk, tap * a.cin_pad + kc * 64, nblk * a.bn);
-      const uint32_t a_bytes = uint32_t(a.tw * a.th * a.tn * 128);
+      const uint32_t a_bytes = a.halo ? uint32_t(a.row_w * (a.th + a.kh - 1) * 128) : uint32_t(a.tw * a.th * a.tn * 128);
       int g = 0;
       for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x) {
         int t = tile;
         const int tx = t % a.tiles_x; t /= a.tiles_x;
         const int ty = t % a.tiles_y; t /= a.tiles_y;
         const int x0 = tx * a.tw, y0 = ty * a.th, n0 = t * a.tn;
+        if (a.halo) {
+          for (int kc = 0; kc < kchunks; ++kc, ++g) {
+            const int s = g % a.stages;
+            mbar_wait(&a_empty[s], (uint32_t(g / a.stages) & 1u) ^ 1u);
+            mbar_expect_tx(&a_full[s], a_bytes);
+            tma_load_4d(&tmA, &a_full[s], tiles + a_ring + size_t(s) * a.a_stage, kc * 64, x0 - a.pw, y0 - a.ph, n0);
+          }
+          continue;
+        }
         for (int ky = 0; ky < a.kh; ++ky)
           for (int kx = 0; kx < a.kw; ++kx)
             for (int kc = 0; kc < kchunks; ++kc, ++g) {
               const int s = g % a.stages;
               mbar_wait(&a_empty[s], (uint32_t(g / a.stages) & 1u) ^ 1u);
               mbar_expect_tx(&a_full[s], a_bytes);
-              tma_load_4d(&tmA, &a_full[s], tiles + a_ring + size_t(s) * kATileBytes, kc * 64, x0 + kx - a.pw,
+              tma_load_4d(&tmA, &a_full[s], tiles + a_ring + size_t(s) * a.a_stage, kc * 64, x0 + kx - a.pw,
                           y0 + ky - a.ph, n0);
             }
       }
@@ -400,12 +418,32 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         mbar_wait(&t_empty[buf], (uint32_t(lt >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t dst = tmem_base + uint32_t(buf * a.tmem_cols);
+        if (a.halo) {
+          for (int kc = 0; kc < kchunks; ++kc, ++g) {
+            const int s = g % a.stages;
+            mbar_wait(&a_full[s], uint32_t(g / a.stages) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = tiles_base + a_ring + uint32_t(s) * a.a_stage;
+            const int rem = a.cin - kc * 64;
+            const int k16 = rem >= 64 ? 4 : (rem + 15) >> 4;
+            for (int ky = 0; ky < a.kh; ++ky)
+              for (int kx = 0; kx < a.kw; ++kx) {
+                const uint32_t sb = tiles_base + uint32_t((ky * a.kw + kx) * kchunks + kc) * b_chunk;
+                const uint32_t sat = sa + uint32_t(ky * a.row_w + kx) * 128;
+                for (int k = 0; k < k16; ++k)
+                  umma_f16(dst, umma_desc(sat + k * 32), umma_desc(sb + k * 32), idesc, (kc | ky | kx | k) != 0);
+              }
+            umma_commit(&a_empty[s]);
+          }
+          umma_commit(&t_full[buf]);
+          continue;
+        }
         for (int tap = 0, it = 0; tap < a.kh * a.kw; ++tap)
           for (int kc = 0; kc < kchunks; ++kc, ++it, ++g) {
             const int s = g % a.stages;
             mbar_wait(&a_full[s], uint32_t(g / a.stages) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = tiles_base + a_ring + uint32_t(s) * kATileBytes;
+            const uint32_t sa = tiles_base + a_ring + uint32_t(s) * a.a_stage;
             const uint32_t sb = tiles_base + uint32_t(it) * b_chunk;
             const int rem = a.cin - kc * 64;
             const int k16 = rem >= 64 ? 4 : (rem + 15) >> 4;
@@ -417,7 +455,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   } else {
     // output staging tile behind the A ring (only with tma_store): ceil(bn / 64) chunks of 128 rows x 128 B
-    uint8_t* stage = tma_store ? tiles + a_ring + size_t(a.stages) * kATileBytes : nullptr;
+    uint8_t* stage = tma_store ? tiles + a_ring + size_t(a.stages) * a.a_stage : nullptr;
     const bool leader = warp == 2 && lane == 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x, ++lt) {
@@ -575,6 +613,7 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
     encode(&impl->tmC, out.p, 4, dC, sC, bA);
   }
   a.n_tiles = n_tiles;
+  a.halo = 0; a.row_w = a.tw; a.a_stage = kATileBytes;
   impl->grid = dim3(unsigned(a.tiles_x * a.tiles_y * tiles_n * n_tiles), 1u);
   impl->smem = size_t(a.stages) * (kATileBytes + a.bn * 128) + 1024 + 128;
   // persistent variant: filter block resident + A ring + double-buffered accumulator
@@ -611,6 +650,40 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
       a.stages = st;
       impl->grid = dim3(unsigned(ctas), unsigned(n_tiles));
       impl->smem = need;
+    }
+    // ---- halo mode for kxk filters: one input box per K chunk instead of one per filter tap (see ConvTcArgs::halo).
+    static const bool want_halo = getenv("B200OCR_CONV_HALO") != nullptr;
+    if (impl->persistent && !staged && want_halo && taps > 1 && g.kw <= 5 && g.kh <= 5) {
+      // output tile = th rows x tw columns with (tw + kw - 1) * th <= 128 MMA rows; the best cover of the output wins
+      int btw = 0, bth = 0;
+      double bcov = 0;
+      for (int tw = 1; tw + g.kw - 1 <= 128 && tw <= out.w; ++tw) {
+        const int pwid = tw + g.kw - 1;
+        int th = std::min(128 / pwid, out.h);
+        if (th < 1 || pwid > 256 || th + g.kh - 1 > 256) continue;
+        const long tiles = long((out.w + tw - 1) / tw) * ((out.h + th - 1) / th) * out.n;
+        const double cov = double(long(out.n) * out.h * out.w) / double(tiles * 128);
+        if (cov > bcov + 1e-9) { bcov = cov; btw = tw; bth = th; }
+      }
+      const int pwid = btw + g.kw - 1;
+      const size_t stage = ((size_t((g.kh - 1) * pwid + g.kw - 1 + 128) * 128) + 1023) & ~size_t(1023);
+      const size_t fixed_h = b_bytes + 1024 + 1024 + 256;
+      int per_sm_h = std::max(1, std::min(512 / (2 * a.tmem_cols), 4));
+      while (per_sm_h > 1 && fixed_h + 2 * stage > budget(per_sm_h)) --per_sm_h;
+      const int kch = (in.c + 63) / 64;
+      if (btw > 0 && bcov >= 0.5 && fixed_h + 2 * stage <= budget(per_sm_h)) {
+        const int st_h = int(std::min<size_t>(std::max(2, std::min(kStagesMaxP, 2 * kch)), (budget(per_sm_h) - fixed_h) / stage));
+        a.tw = btw; a.th = bth; a.tn = 1;
+        a.tiles_x = (out.w + a.tw - 1) / a.tw;
+        a.tiles_y = (out.h + a.th - 1) / a.th;
+        a.halo = 1; a.row_w = pwid; a.a_stage = int(stage); a.stages = st_h;
+        cuuint32_t bH[4] = {64, cuuint32_t(pwid), cuuint32_t(a.th + g.kh - 1), 1};
+        encode(&impl->tmA, in.p, 4, dA, sA, bH);
+        impl->n_mtiles = a.tiles_x * a.tiles_y * out.n;
+        impl->grid = dim3(unsigned(std::min(impl->n_mtiles, sms * per_sm_h)), unsigned(n_tiles));
+        impl->smem = fixed_h + size_t(st_h) * stage;
+        impl->tma_store = false;
+      }
     }
   }
   impl->args = a;

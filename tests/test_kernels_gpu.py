@@ -133,6 +133,7 @@ def _ref_conv(x, filt, bias, act, s2, t2, residual):
     (1, 120, 360, 1, 97, 1, 1), (4, 96, 24, 20, 32, 3, 3), (2, 24, 24, 40, 64, 3, 3), (1, 96, 96, 10, 16, 3, 3),
     (3, 64, 120, 1, 61, 1, 3), (2, 8, 16, 9, 9, 1, 1), (1, 40, 136, 5, 13, 3, 3), (7, 200, 72, 3, 19, 1, 1),
     (2, 384, 96, 10, 16, 1, 1), (1, 72, 264, 6, 50, 1, 1), (2, 136, 8, 12, 12, 3, 3), (40, 240, 240, 7, 100, 1, 1),
+    (6, 96, 24, 80, 128, 3, 3), (3, 24, 24, 160, 250, 3, 3), (50, 64, 120, 1, 97, 1, 3),
 ])
 @pytest.mark.parametrize("simt", [False, True], ids=["tcgen05", "cuda-core"])
 def test_conv_matches_torch(n, cin, cout, h, w, kh, kw, simt):
