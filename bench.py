@@ -295,12 +295,12 @@ def run_ours(args):
 
     # p50 latency of ONE image through the reference-facing call (b200ocr_worker_process: host image in, JSON out)
     lat = []
-    for i in range(40):
+    for i in range(0 if args.no_latency else 40):
         t0 = time.perf_counter()
         worker.process(i, host_sets[0][i % B])
         lat.append((time.perf_counter() - t0) * 1e3)
     lat = sorted(lat[8:])
-    p50_single = lat[len(lat) // 2]
+    p50_single = lat[len(lat) // 2] if lat else None
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -343,6 +343,7 @@ def main():
     ap.add_argument("--ref-images", type=int, default=16, help="images per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-layer profile pass (clean ncu launch lists)")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-image latency loop (clean ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
