@@ -14,16 +14,6 @@ namespace {
 
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ float apply_act(float v, int act, float a, float b) {
-  switch (act) {
-    case 1: return fmaxf(v, 0.f);
-    case 2: return v * __saturatef(fmaf(v, 1.f / 6.f, 0.5f));  // x * relu6(x + 3) / 6: one FFMA.SAT + one FMUL
-    case 3: return v / (1.f + __expf(-v));
-    case 4: return __saturatef(fmaf(v, a, b));
-    case 5: return 1.f / (1.f + __expf(-v));
-    default: return v;
-  }
-}
 
 struct H8 {
   uint4 u;
