@@ -93,6 +93,25 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same MMA with the descriptors split into their constant high word and the low word that carries the start
+// address: advancing 32 bytes along K is `lo + 2`, so the single issuing thread spends one add per operand and MMA
+// instead of rebuilding both 64-bit descriptors (the issue loop, not the tensor pipe, bounds the narrow-N layers:
+// ~170 clk per tcgen05.mma measured on the 96 -> 24 3x3 layers).
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024, descriptor version 1, 128B swizzle
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -308,8 +327,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sb = sa + kATileBytes;
           const int rem = a.cin - kc * 64;
           const int k16 = rem >= 64 ? 4 : (rem + 15) >> 4;
-          for (int k = 0; k < k16; ++k)
-            umma_f16(tmem_base, umma_desc(sa + k * 32), umma_desc(sb + k * 32), idesc, (it | k) != 0);
+          const uint32_t alo = umma_desc_lo(sa), blo = umma_desc_lo(sb);
+          for (int k = 0; k < k16; ++k) umma_f16_lo(tmem_base, alo + 2 * k, blo + 2 * k, idesc, (it | k) != 0);
           umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
         }
       umma_commit(tmem_full);
@@ -430,8 +449,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               for (int kx = 0; kx < a.kw; ++kx) {
                 const uint32_t sb = tiles_base + uint32_t((ky * a.kw + kx) * kchunks + kc) * b_chunk;
                 const uint32_t sat = sa + uint32_t(ky * a.row_w + kx) * 128;
-                for (int k = 0; k < k16; ++k)
-                  umma_f16(dst, umma_desc(sat + k * 32), umma_desc(sb + k * 32), idesc, (kc | ky | kx | k) != 0);
+                const uint32_t alo = umma_desc_lo(sat), blo = umma_desc_lo(sb);
+                for (int k = 0; k < k16; ++k) umma_f16_lo(dst, alo + 2 * k, blo + 2 * k, idesc, (kc | ky | kx | k) != 0);
               }
             umma_commit(&a_empty[s]);
           }
@@ -447,7 +466,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint32_t sb = tiles_base + uint32_t(it) * b_chunk;
             const int rem = a.cin - kc * 64;
             const int k16 = rem >= 64 ? 4 : (rem + 15) >> 4;
-            for (int k = 0; k < k16; ++k) umma_f16(dst, umma_desc(sa + k * 32), umma_desc(sb + k * 32), idesc, (it | k) != 0);
+            const uint32_t alo = umma_desc_lo(sa), blo = umma_desc_lo(sb);
+            for (int k = 0; k < k16; ++k) umma_f16_lo(dst, alo + 2 * k, blo + 2 * k, idesc, (it | k) != 0);
             umma_commit(&a_empty[s]);
           }
         umma_commit(&t_full[buf]);
@@ -672,7 +692,7 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
       while (per_sm_h > 1 && fixed_h + 2 * stage > budget(per_sm_h)) --per_sm_h;
       const int kch = (in.c + 63) / 64;
       if (btw > 0 && bcov >= 0.5 && fixed_h + 2 * stage <= budget(per_sm_h)) {
-        const int st_h = int(std::min<size_t>(std::max(2, std::min(kStagesMaxP, 2 * kch)), (budget(per_sm_h) - fixed_h) / stage));
+        const int st_h = int(std::min<size_t>(kStagesMaxP, (budget(per_sm_h) - fixed_h) / stage));  // as deep as fits (kch stages = one tile)
         a.tw = btw; a.th = bth; a.tn = 1;
         a.tiles_x = (out.w + a.tw - 1) / a.tw;
         a.tiles_y = (out.h + a.th - 1) / a.th;
