@@ -661,7 +661,8 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
     static const int st_cap = getenv("B200OCR_CONV_STAGES") ? atoi(getenv("B200OCR_CONV_STAGES")) : kStagesMaxP;
     st = std::min(st, std::max(2, st_cap));
     const size_t need = fixed + size_t(st) * kATileBytes;
-    if (2 * a.tmem_cols <= 512 && st >= 2 && m_tiles >= 2 * sms / 3 && !getenv("B200OCR_NO_PERSISTENT_CONV")) {
+    static const int min_tiles_x3 = getenv("B200OCR_CONV_PERSIST_MIN") ? atoi(getenv("B200OCR_CONV_PERSIST_MIN")) : 6;  // persistent from 2 tiles per SM on (measured: fewer tiles run faster one tile per CTA)
+    if (2 * a.tmem_cols <= 512 && st >= 2 && 3 * m_tiles >= min_tiles_x3 * sms && !getenv("B200OCR_NO_PERSISTENT_CONV")) {
       const int ctas = std::min(m_tiles, sms * per_sm);
       impl->persistent = true;
       impl->tma_store = staged;
