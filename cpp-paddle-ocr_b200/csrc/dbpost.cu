@@ -24,6 +24,7 @@
 #include "kernels.h"
 #include "geom.h"
 
+#include <algorithm>
 #include <cstdio>
 
 namespace b200ocr {
@@ -326,18 +327,16 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
   return r;
 }
 
-__global__ void __launch_bounds__(kBoxThreads)
-boxes_kernel(DbPostParams P, const float* __restrict__ prob, const uint8_t* __restrict__ bm,
-             const int* __restrict__ L, const int* __restrict__ touch, Slot s, const int* __restrict__ counts,
-             const int* __restrict__ list, const DbImageInfo* __restrict__ info, DbBox* __restrict__ boxes) {
-  extern __shared__ int dyn[];  // rowmin[h], rowmax[h]
+// one candidate (image `img`, position `ord` in the ordered list) by one CTA
+__device__ void boxes_one(const DbPostParams& P, const float* __restrict__ prob, const uint8_t* __restrict__ bm,
+                          const int* __restrict__ L, const int* __restrict__ touch, const Slot& s,
+                          const int* __restrict__ list, const DbImageInfo* __restrict__ info, DbBox* __restrict__ boxes,
+                          int img, int ord, int* dyn) {
   __shared__ geom::P2 hull[kHullCap];
   __shared__ float sc_a[kHullCap], sc_b[kHullCap], sc_c[kHullCap];
   __shared__ double red[kBoxThreads / 32];
   __shared__ int sh_i[16];
   __shared__ float sh_f[16];
-  const int img = blockIdx.y, ord = blockIdx.x;
-  if (ord >= counts[img]) return;
   const int h = P.h, w = P.w;
   const long per = long(h) * w;
   const long ibase = img * per;
@@ -479,6 +478,21 @@ boxes_kernel(DbPostParams P, const float* __restrict__ prob, const uint8_t* __re
   ob->valid = 1;
 }
 
+// The grid is a fixed number of CTAs per image that walk over the image's candidates: a text image has 10-50 of them,
+// a grid of max_candidates (1000) CTAs per image would be 97 % empty CTAs whose launch costs more than the real work.
+__global__ void __launch_bounds__(kBoxThreads)
+boxes_kernel(DbPostParams P, const float* __restrict__ prob, const uint8_t* __restrict__ bm,
+             const int* __restrict__ L, const int* __restrict__ touch, Slot s, const int* __restrict__ counts,
+             const int* __restrict__ list, const DbImageInfo* __restrict__ info, DbBox* __restrict__ boxes) {
+  extern __shared__ int dyn[];  // rowmin[h], rowmax[h]
+  const int img = blockIdx.y;
+  const int cnt = counts[img];
+  for (int ord = blockIdx.x; ord < cnt; ord += gridDim.x) {
+    boxes_one(P, prob, bm, L, touch, s, list, info, boxes, img, ord, dyn);
+    __syncthreads();  // the shared scratch is reused by the next candidate
+  }
+}
+
 __global__ void __launch_bounds__(256)
 dilate2x2_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int n, int h, int w) {
   // cv::dilate with a 2x2 rectangle, anchor (1,1): out(y,x) = max over rows y-1..y, cols x-1..x
@@ -545,8 +559,9 @@ void launch_dbpost(const DbPostParams& p, const float* prob, const uint8_t* bitm
   if (p.score_slow) nest_sum_kernel<<<g, 256, 0, st>>>(bitmap, prob, L, touch, s, p.n, p.h, p.w);
   list_kernel<<<p.n, 1024, 0, st>>>(s.flag, p.h, p.w, p.max_candidates, counts_dev, list);
   const size_t smem = size_t(2) * p.h * sizeof(int);
-  boxes_kernel<<<dim3(p.max_candidates, p.n), kBoxThreads, smem, st>>>(p, prob, bitmap, L, touch, s, counts_dev, list,
-                                                                      info_dev, boxes_dev);
+  const int per_image = std::min(p.max_candidates, std::max(16, (148 * 8 + p.n - 1) / p.n));
+  boxes_kernel<<<dim3(per_image, p.n), kBoxThreads, smem, st>>>(p, prob, bitmap, L, touch, s, counts_dev, list, info_dev,
+                                                                 boxes_dev);
 }
 
 void launch_threshold(const float* prob, long n, int thresh_u8, uint8_t* bitmap, cudaStream_t s) {
