@@ -155,7 +155,11 @@ struct Slot {  // per-pixel arrays, meaningful at contour start pixels only
   // The two kinds of index never coincide (a hole's first pixel lies below the first row of the component around it).
   unsigned long long* sum;
   int* cnt;
+  // start pixels appended by mark_kernel (first setter of a flag appends): cand[img][kCandCap], cand_n[img]
+  int* cand;
+  int* cand_n;
 };
+constexpr int kCandCap = 4096;
 
 __global__ void __launch_bounds__(256)
 slot_init_kernel(Slot s, long total) {
@@ -242,7 +246,11 @@ mark_kernel(const uint8_t* __restrict__ bm, const int* __restrict__ L, const int
       seen[ns++] = B;
       const int slot = (B == bout) ? C : B - 1;  // outer border of C, or border of hole B
       if (slot < 0) continue;  // cannot happen: a component that touches the frame has the frame as outer background
-      s.flag[slot] = 1;
+      if (atomicExch(&s.flag[slot], 1) == 0) {  // first border pixel of this contour: register its start pixel
+        const int img = int(t / per);
+        const int pos = atomicAdd(&s.cand_n[img], 1);
+        if (pos < kCandCap) s.cand[img * kCandCap + pos] = slot;
+      }
       atomicMin(&s.x0[slot], x); atomicMin(&s.y0[slot], y);
       atomicMax(&s.x1[slot], x); atomicMax(&s.y1[slot], y);
       if (s.sum && B != bout) {  // "slow" score: the hole border's own pixels
@@ -254,14 +262,47 @@ mark_kernel(const uint8_t* __restrict__ bm, const int* __restrict__ L, const int
 }
 
 // ---------------------------------------------------------------- 3. ordered candidate list
+// Fast path: the start pixels mark_kernel appended (unordered) are sorted in shared memory, descending = the reference's
+// contour order; the first max_cand stay.  Only when an image has more than kCandCap contours (noise) does the
+// scan-based list_kernel below do the work.
+__global__ void __launch_bounds__(1024)
+sort_candidates_kernel(const int* __restrict__ cand, const int* __restrict__ cand_n, int max_cand, int* __restrict__ counts,
+                       int* __restrict__ list) {
+  __shared__ int key[kCandCap];
+  const int img = blockIdx.x;
+  const int n = cand_n[img];
+  if (n > kCandCap) return;  // list_kernel takes this image
+  int m = 1;
+  while (m < n) m <<= 1;     // bitonic network size
+  for (int i = threadIdx.x; i < m; i += blockDim.x) key[i] = i < n ? cand[img * kCandCap + i] : -1;
+  __syncthreads();
+  for (int k = 2; k <= m; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int p = i ^ j;
+        if (p > i) {
+          const bool desc = (i & k) == 0;  // descending overall
+          const int a = key[i], b = key[p];
+          if (desc ? a < b : a > b) { key[i] = b; key[p] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  const int keep = n < max_cand ? n : max_cand;
+  for (int i = threadIdx.x; i < keep; i += blockDim.x) list[long(img) * max_cand + i] = key[i];
+  if (threadIdx.x == 0) counts[img] = keep;
+}
+
 // One CTA per image; walks the flag array from the last pixel backwards in chunks, block-scans the flags and
 // appends start pixels (global indices) until max_candidates are collected.
 __global__ void __launch_bounds__(1024)
-list_kernel(const int* __restrict__ flag, int h, int w, int max_cand, int* __restrict__ counts, int* __restrict__ list) {
+list_kernel(const int* __restrict__ flag, int h, int w, int max_cand, int* __restrict__ counts, int* __restrict__ list,
+            const int* __restrict__ cand_n) {
   constexpr int kPer = 8;
   __shared__ int warp_sums[32];
   __shared__ int base;
   const int img = blockIdx.x;
+  if (cand_n[img] <= kCandCap) return;  // sort_candidates_kernel already listed this image
   const long per = long(h) * w;
   const int* f = flag + img * per;
   int* out = list + long(img) * max_cand;
@@ -523,10 +564,12 @@ inline size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 }  // namespace
 
 // workspace layout: L | touch | flag | x0 | y0 | x1 | y1 (int32 per pixel each) | list [n*max_candidates]
+//                   | cand [n*kCandCap] | cand_n [n]
 //                   [| sum (u64 per pixel) | cnt (int32 per pixel)   in "slow" score mode]
 size_t dbpost_workspace_bytes(const DbPostParams& p) {
   const size_t px = size_t(p.n) * p.h * p.w;
-  return 7 * al(px * 4) + al(size_t(p.n) * p.max_candidates * 4) + (p.score_slow ? al(px * 8) + al(px * 4) : 0);
+  return 7 * al(px * 4) + al(size_t(p.n) * p.max_candidates * 4) + al(size_t(p.n) * kCandCap * 4) + al(size_t(p.n) * 4) +
+         (p.score_slow ? al(px * 8) + al(px * 4) : 0);
 }
 
 void launch_dbpost(const DbPostParams& p, const float* prob, const uint8_t* bitmap, const DbImageInfo* info_dev,
@@ -542,9 +585,12 @@ void launch_dbpost(const DbPostParams& p, const float* prob, const uint8_t* bitm
   s.x1 = reinterpret_cast<int*>(ws + 5 * al(px * 4));
   s.y1 = reinterpret_cast<int*>(ws + 6 * al(px * 4));
   int* list = reinterpret_cast<int*>(ws + 7 * al(px * 4));
+  s.cand = reinterpret_cast<int*>(ws + 7 * al(px * 4) + al(size_t(p.n) * p.max_candidates * 4));
+  s.cand_n = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(s.cand) + al(size_t(p.n) * kCandCap * 4));
+  cudaMemsetAsync(s.cand_n, 0, size_t(p.n) * 4, st);
   s.sum = nullptr; s.cnt = nullptr;
   if (p.score_slow) {
-    uint8_t* extra = ws + 7 * al(px * 4) + al(size_t(p.n) * p.max_candidates * 4);
+    uint8_t* extra = reinterpret_cast<uint8_t*>(s.cand_n) + al(size_t(p.n) * 4);
     s.sum = reinterpret_cast<unsigned long long*>(extra);
     s.cnt = reinterpret_cast<int*>(extra + al(px * 8));
   }
@@ -557,7 +603,8 @@ void launch_dbpost(const DbPostParams& p, const float* prob, const uint8_t* bitm
   ccl_flatten_kernel<<<g, 256, 0, st>>>(bitmap, L, touch, p.n, p.h, p.w);
   mark_kernel<<<g, 256, 0, st>>>(bitmap, L, touch, s, p.n, p.h, p.w, prob);
   if (p.score_slow) nest_sum_kernel<<<g, 256, 0, st>>>(bitmap, prob, L, touch, s, p.n, p.h, p.w);
-  list_kernel<<<p.n, 1024, 0, st>>>(s.flag, p.h, p.w, p.max_candidates, counts_dev, list);
+  sort_candidates_kernel<<<p.n, 1024, 0, st>>>(s.cand, s.cand_n, p.max_candidates, counts_dev, list);
+  list_kernel<<<p.n, 1024, 0, st>>>(s.flag, p.h, p.w, p.max_candidates, counts_dev, list, s.cand_n);
   const size_t smem = size_t(2) * p.h * sizeof(int);
   const int per_image = std::min(p.max_candidates, std::max(16, (148 * 8 + p.n - 1) / p.n));
   boxes_kernel<<<dim3(per_image, p.n), kBoxThreads, smem, st>>>(p, prob, bitmap, L, touch, s, counts_dev, list, info_dev,

@@ -159,7 +159,7 @@ void DetStage::run_group(const std::vector<DevImg>& imgs, const std::vector<int>
     ++launches;
   }
   launch_dbpost(pp, net_.out_f32(), bitmap, info_.as<DbImageInfo>(), ws_.p, counts_.as<int>(), boxes_.as<DbBox>(), s);
-  launches += 7 + pp.score_slow;
+  launches += 8 + pp.score_slow;
   cuda_check(cudaMemcpyAsync(h_counts_.p, counts_.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s), "det counts");
   cuda_check(cudaStreamSynchronize(s), "det post-process");
   // second copy sized by what was found (boxes of image k live at [k * max_candidates, +count))
