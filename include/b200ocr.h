@@ -64,7 +64,9 @@ int b200ocr_device_count(void);
  * Constructor arguments of PaddleOCR::DBDetector (include/paddle_ocr/ocr_det.h:60-69), same order and meaning.
  * use_gpu, gpu_mem, cpu_math_library_num_threads, use_mkldnn, use_tensorrt and precision are accepted for
  * signature compatibility and ignored: this implementation always runs on GPU `gpu_id` in fp16 with fp32
- * accumulation.  det_db_score_mode must be "fast" (the worker's setting); "slow" returns B200OCR_ERR_INVALID. */
+ * accumulation.  det_db_score_mode: "fast" (the worker's setting; BoxScoreFast) or "slow" (PolygonScoreAcc); anything else
+ * returns B200OCR_ERR_INVALID.  A C++ caller can use include/paddle_ocr/b200ocr_shim.h instead: the same three classes
+ * with the reference's constructor and Run() signatures over these entry points. */
 typedef struct b200ocr_det_config {
   const char* model_dir;
   int use_gpu, gpu_id, gpu_mem, cpu_math_library_num_threads, use_mkldnn;
