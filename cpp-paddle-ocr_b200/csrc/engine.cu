@@ -101,7 +101,7 @@ void Net::infer(int n, int h, int w, std::vector<Shape3>* ts_, std::vector<int>*
         break;
       case LKind::Gap:
         o = Shape3{in.n, 1, 1};
-        if (splits) (*splits)[L.out] = gap_splits(in.h);
+        if (splits) (*splits)[L.out] = gap_splits(in.n, in.h, in.w, L.cin, plan_.kind == "rec");
         if (hwv) (*hwv)[L.out] = in.h * in.w;
         if (gap_src) (*gap_src)[L.out] = L.in;
         break;
@@ -337,9 +337,9 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
           f.c = F.cin; f.cmid = F.cmid; f.slope = F.act_a; f.offset = F.act_b;
           f.inv_hw = 1.f / float(I.hw[L.out]);
           f.vw_in = vwp(L.in); f.h = I.ts[L.in].h;
-          launch_gap_partial(tv(L.in), vecp(L.out), I.splits[L.out], s, &f);
+          launch_gap_partial(tv(L.in), vecp(L.out), I.splits[L.out], plan_.kind == "rec", s, &f);
         } else {
-          launch_gap_partial(tv(L.in), vecp(L.out), I.splits[L.out], s);
+          launch_gap_partial(tv(L.in), vecp(L.out), I.splits[L.out], plan_.kind == "rec", s);
         }
         break;
       }

@@ -53,7 +53,7 @@ bool launch_dwconv_tile(const TV& in, const TV& out, const float* w_bias, const 
                         const Epi& e, cudaStream_t s, const int* vw);
 
 // ---- SE block ---------------------------------------------------------------
-int gap_splits(int h);
+int gap_splits(int n, int h, int w, int c, bool ragged_safe);
 // SE gate fused into the pooling kernel (the block that finishes a sample's last split computes its gate):
 // counters = int[n] device scratch, zero before the first use (the kernel leaves it zero)
 struct SeFuse {
@@ -64,7 +64,8 @@ struct SeFuse {
   float slope = 0.f, offset = 0.f, inv_hw = 0.f;
   const int* vw_in = nullptr;
 };
-void launch_gap_partial(const TV& in, float* partial, int splits, cudaStream_t s, const SeFuse* fuse = nullptr);
+void launch_gap_partial(const TV& in, float* partial, int splits, bool ragged_safe, cudaStream_t s,
+                        const SeFuse* fuse = nullptr);
 // vw_in: valid width of the pooled tensor per row (mean over h * vw_in[n] pixels), h its height
 void launch_se_fc(const float* partial, int splits, int hw, int n, int c, int cmid, const float* blk,
                   float slope, float offset, float* gate, cudaStream_t s, const int* vw_in = nullptr, int h = 0);

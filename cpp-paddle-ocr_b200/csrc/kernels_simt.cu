@@ -484,57 +484,86 @@ stem_conv_s2x4_kernel(TV in, TV out, const __half* __restrict__ w, const float* 
 
 // ---------------------------------------------------------------- SE block
 // partial[n][split][cp] = sum over the split's pixels (fp32, fixed order -> deterministic)
-__device__ __forceinline__ void gap_partial_body(TV in, float* __restrict__ partial, int splits, float* sm) {
+// Two ways of cutting a sample into splits:
+//  * cbs > 0 (recognizer, whose batches may be ragged): split = (row range, block of gap_col_block() columns).  A lane owns
+//    the columns x == x0 + lane (mod lanes) of its block and adds them in (row, column) order, so the order in which
+//    its accumulator sees the valid pixels of a text line does not depend on how wide the surrounding tensor is: zero
+//    columns add exactly 0, and so do the all-zero blocks a wider tensor appends to the sum over splits.  Pooled
+//    values are bit-identical to a dense run of the line's own width.
+//  * cbs == 0 (detector / classifier, always dense): split = a contiguous range of the sample's pixels, so that every
+//    lane has a full ring of loads in flight whatever the aspect ratio.
+// The pixels are staged through shared memory by cp.async: each thread keeps kGapStages 16-byte copies in flight into
+// ring slots of its own (bytes in flight do not cost registers, and no block barrier sits in the loop).
+constexpr int kGapColBlockDefault = 256;
+constexpr int kGapStages = 8;  // 16-byte cp.async copies in flight per thread (its own ring slots: no block barrier)
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(smem))), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// sm: kGapStages * kThreads * 16 bytes (ring), reused for the cross-lane reduction
+__device__ __forceinline__ void gap_partial_body(TV in, float* __restrict__ partial, int splits, int cbs, int cbw,
+                                                 float* sm) {
   const int cgs = (in.c + 7) >> 3;
   const int cp = cgs * 8;
   const int lanes = max(1, kThreads / cgs);
   const int split = blockIdx.x, n = blockIdx.y;
   const int hw = in.h * in.w;
-  // A split owns a range of ROWS and a lane owns the columns x == lane (mod lanes): the order in which one
-  // accumulator sees the valid pixels of a text line does not depend on how wide the surrounding tensor is
-  // (zero columns of a ragged batch add exactly 0), so pooled values are bit-identical to a dense run.
-  const int rows_per = (in.h + splits - 1) / splits;
-  const int y0 = split * rows_per, y1 = min(in.h, y0 + rows_per);
   const int cg = threadIdx.x % cgs, lane = threadIdx.x / cgs;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // One accumulator per channel, fed in (row, column) order: the loads are decoupled from the adds by the ring, so
+  // a single fixed-order chain costs nothing, and interleaved zero columns leave it unchanged.
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (lane < lanes) {
-    const __half* base = in.p + long(n) * hw * in.pitch + cg * 8;
-    // four independent partial sums per lane (columns lane + lanes * (4j + u)): four loads in flight instead of a
-    // load -> add chain.  Which partial sum a column feeds depends on x and the channel count only, so the result
-    // is still independent of the width of the surrounding tensor.
-    float part[4][8];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) part[u][i] = 0.f;
-    for (int y = y0; y < y1; ++y) {
-      const __half* row = base + long(y) * in.w * in.pitch;
-      int xx = lane;
-      for (; xx + 3 * lanes < in.w; xx += 4 * lanes) {
-        H8 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ld8(row + long(xx + u * lanes) * in.pitch);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float x[8];
-          v[u].to_float(x);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) part[u][i] += x[i];
-        }
-      }
-      for (int u = 0; xx < in.w; xx += lanes, ++u) {
-        float x[8];
-        ld8(row + long(xx) * in.pitch).to_float(x);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (u == 0) part[0][i] += x[i];
-          else if (u == 1) part[1][i] += x[i];
-          else part[2][i] += x[i];
-        }
-      }
+    int y0 = 0, y1 = 1, xa, xb;  // rows [y0, y1); this lane's pixels of a row: xa + lane + k * lanes < xb
+    long row_pix = 0;
+    if (cbs > 0) {
+      const int rs = splits / cbs, rsplit = split / cbs, cb = split - rsplit * cbs;
+      const int rows_per = (in.h + rs - 1) / rs;
+      y0 = rsplit * rows_per;
+      y1 = min(in.h, y0 + rows_per);
+      xa = cb * cbw;
+      xb = min(in.w, xa + cbw);
+      row_pix = in.w;
+    } else {
+      const int chunk = (hw + splits - 1) / splits;
+      xa = split * chunk;
+      xb = min(hw, xa + chunk);
     }
+    const int k_per_row = xb - xa > lane ? (xb - xa - lane + lanes - 1) / lanes : 0;
+    const int total = k_per_row * max(0, y1 - y0);
+    const __half* base = in.p + (long(n) * hw + xa + lane) * in.pitch + cg * 8;
+    uint4* ring = reinterpret_cast<uint4*>(sm) + threadIdx.x;  // slot s at ring[s * kThreads]
+    int iy = y0, ik = 0, issued = 0;
+    auto issue = [&](int slot) {
+      cp_async16(ring + slot * kThreads, base + (long(iy) * row_pix + long(ik) * lanes) * in.pitch);
+      if (++ik == k_per_row) { ik = 0; ++iy; }
+      ++issued;
+    };
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = (part[0][i] + part[1][i]) + (part[2][i] + part[3][i]);
+    for (int s = 0; s < kGapStages; ++s) {  // one group per slot, empty past the end: the wait count stays uniform
+      if (s < total) issue(s);
+      cp_async_commit();
+    }
+    for (int j = 0; j < total; ++j) {
+      cp_async_wait<kGapStages - 1>();
+      const int slot = j % kGapStages;
+      H8 v;
+      v.u = ring[slot * kThreads];
+      float x[8];
+      v.to_float(x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += x[i];
+      if (issued < total) issue(slot);
+      cp_async_commit();
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();  // every ring slot has been consumed: the buffer becomes the reduction scratch
+  if (lane < lanes) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) sm[lane * cp + cg * 8 + i] = acc[i];
   }
@@ -547,9 +576,9 @@ __device__ __forceinline__ void gap_partial_body(TV in, float* __restrict__ part
 }
 
 __global__ void __launch_bounds__(kThreads)
-gap_partial_kernel(TV in, float* __restrict__ partial, int splits) {
+gap_partial_kernel(TV in, float* __restrict__ partial, int splits, int cbs, int cbw) {
   extern __shared__ float sm[];
-  gap_partial_body(in, partial, splits, sm);
+  gap_partial_body(in, partial, splits, cbs, cbw, sm);
 }
 
 // blk: w1[cmid][c], b1[cmid], w2[c][cmid], b2[c]
@@ -557,6 +586,8 @@ gap_partial_kernel(TV in, float* __restrict__ partial, int splits) {
 // floats each) are read once per block; one thread owns one output neuron of all its samples (no reductions).
 // blk: w1t[c][cmid], b1[cmid], w2t[cmid][c], b2[c].  `partial` may have been written by other blocks of the SAME
 // kernel (fused pool + gate): it is read through L2 (__ldcg).
+constexpr int kSeMaxParts = 16;  // partitions of a contraction in the vector path of se_fc_body
+
 template <int kSeSamples>
 __device__ __forceinline__ void se_fc_body(float* sm, const float* partial, int splits, float inv_hw0, int n0, int n_total,
                                            int c, int cmid, const float* __restrict__ blk, float slope, float offset,
@@ -572,7 +603,16 @@ __device__ __forceinline__ void se_fc_body(float* sm, const float* partial, int 
       const int n = n0 + sidx;
       const float inv_hw = vw_in ? 1.f / float(h * vw_in[n]) : inv_hw0;
       float s = 0.f;
-      for (int k = 0; k < splits; ++k) s += __ldcg(partial + (long(n) * splits + k) * cp + i);
+      const float* pp = partial + long(n) * splits * cp + i;
+      int k = 0;
+      for (; k + 8 <= splits; k += 8) {  // eight loads in flight, added in split order
+        float q[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) q[u] = __ldcg(pp + long(k + u) * cp);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += q[u];
+      }
+      for (; k < splits; ++k) s += __ldcg(pp + long(k) * cp);
       v = s * inv_hw;
     }
     pooled[t] = v;
@@ -582,6 +622,112 @@ __device__ __forceinline__ void se_fc_body(float* sm, const float* partial, int 
   const float* b1 = w1t + long(cmid) * c;
   const float* w2t = b1 + cmid;
   const float* b2 = w2t + long(c) * cmid;
+  if ((c & 3) == 0 && (cmid & 3) == 0) {
+    // Vector path (every SE block of det and rec).  The gate is on the critical path of the fused pool + gate kernel
+    // (the block that pooled a sample's last split computes it alone), so the two mat-vecs are cut for LATENCY:
+    // thread = (four neighbouring neurons, one partition of the contraction), eight 16-byte weight loads in flight,
+    // partitions added in index order afterwards.
+    float* scratch = hidden + kSeSamples * cmid;  // [P][kSeSamples][cmid] then [P][kSeSamples][c]
+    {
+      const int quads = cmid >> 2;
+      const int parts = max(1, min(min(int(blockDim.x) / quads, kSeMaxParts), c));
+      const int per = (c + parts - 1) / parts;
+      for (int t = threadIdx.x; t < quads * parts; t += blockDim.x) {
+        const int pt = t / quads, mq = t - pt * quads;
+        const int i0 = pt * per, i1 = min(c, i0 + per);
+        float4 a[kSeSamples];
+#pragma unroll
+        for (int q = 0; q < kSeSamples; ++q) a[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* wp = reinterpret_cast<const float4*>(w1t) + mq;
+        int i = i0;
+        for (; i + 8 <= i1; i += 8) {
+          float4 w[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) w[u] = __ldg(wp + long(i + u) * quads);
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int q = 0; q < kSeSamples; ++q) {
+              const float x = pooled[q * cp + i + u];
+              a[q].x = fmaf(w[u].x, x, a[q].x); a[q].y = fmaf(w[u].y, x, a[q].y);
+              a[q].z = fmaf(w[u].z, x, a[q].z); a[q].w = fmaf(w[u].w, x, a[q].w);
+            }
+        }
+        for (; i < i1; ++i) {
+          const float4 w = __ldg(wp + long(i) * quads);
+#pragma unroll
+          for (int q = 0; q < kSeSamples; ++q) {
+            const float x = pooled[q * cp + i];
+            a[q].x = fmaf(w.x, x, a[q].x); a[q].y = fmaf(w.y, x, a[q].y);
+            a[q].z = fmaf(w.z, x, a[q].z); a[q].w = fmaf(w.w, x, a[q].w);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kSeSamples; ++q)
+          reinterpret_cast<float4*>(scratch + (long(pt) * kSeSamples + q) * cmid)[mq] = a[q];
+      }
+      __syncthreads();
+      for (int t = threadIdx.x; t < kSeSamples * cmid; t += blockDim.x) {
+        const int q = t / cmid, m = t - q * cmid;
+        float v = b1[m];
+        for (int pt = 0; pt < parts; ++pt) v += scratch[(long(pt) * kSeSamples + q) * cmid + m];
+        hidden[t] = fmaxf(v, 0.f);
+      }
+      __syncthreads();
+    }
+    {
+      const int quads = c >> 2;
+      const int parts = max(1, min(min(int(blockDim.x) / quads, kSeMaxParts), cmid));
+      const int per = (cmid + parts - 1) / parts;
+      for (int t = threadIdx.x; t < quads * parts; t += blockDim.x) {
+        const int pt = t / quads, iq = t - pt * quads;
+        const int m0 = pt * per, m1 = min(cmid, m0 + per);
+        float4 a[kSeSamples];
+#pragma unroll
+        for (int q = 0; q < kSeSamples; ++q) a[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* wp = reinterpret_cast<const float4*>(w2t) + iq;
+        int m = m0;
+        for (; m + 8 <= m1; m += 8) {
+          float4 w[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) w[u] = __ldg(wp + long(m + u) * quads);
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int q = 0; q < kSeSamples; ++q) {
+              const float x = hidden[q * cmid + m + u];
+              a[q].x = fmaf(w[u].x, x, a[q].x); a[q].y = fmaf(w[u].y, x, a[q].y);
+              a[q].z = fmaf(w[u].z, x, a[q].z); a[q].w = fmaf(w[u].w, x, a[q].w);
+            }
+        }
+        for (; m < m1; ++m) {
+          const float4 w = __ldg(wp + long(m) * quads);
+#pragma unroll
+          for (int q = 0; q < kSeSamples; ++q) {
+            const float x = hidden[q * cmid + m];
+            a[q].x = fmaf(w.x, x, a[q].x); a[q].y = fmaf(w.y, x, a[q].y);
+            a[q].z = fmaf(w.z, x, a[q].z); a[q].w = fmaf(w.w, x, a[q].w);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kSeSamples; ++q)
+          reinterpret_cast<float4*>(scratch + (long(pt) * kSeSamples + q) * c)[iq] = a[q];
+      }
+      __syncthreads();
+      for (int t = threadIdx.x; t < kSeSamples * cp; t += blockDim.x) {
+        const int q = t / cp, i = t - q * cp;
+        float v = 0.f;
+        if (i < c) {
+          v = b2[i];
+          for (int pt = 0; pt < parts; ++pt) v += scratch[(long(pt) * kSeSamples + q) * c + i];
+          v = __saturatef(fmaf(v, slope, offset));
+        }
+        if (q < ns) gate[long(n0 + q) * cp + i] = v;
+      }
+    }
+    return;
+  }
+  // Scalar path (channel counts that are not multiples of four: some classifier blocks).
   // fc1: thread = (half of the input channels, hidden neuron); 8 independent weight loads in flight per thread
   float* part = hidden + kSeSamples * cmid;  // [2][kSeSamples][cmid] partial sums
   for (int t = threadIdx.x; t < 2 * cmid; t += blockDim.x) {
@@ -661,21 +807,23 @@ se_fc_kernel(const float* __restrict__ partial, int splits, float inv_hw0, int n
 // samples are computed while the later samples are still being pooled.  The sums are added in split order by that
 // one block, so the result does not depend on which block came last.
 __global__ void __launch_bounds__(kThreads)
-gap_se_kernel(TV in, float* __restrict__ partial, int splits, SeFuse fc) {
+gap_se_kernel(TV in, float* __restrict__ partial, int splits, int cbs, int cbw, SeFuse fc) {
   extern __shared__ float sm[];
   __shared__ int s_last;
-  gap_partial_body(in, partial, splits, sm);
-  __threadfence();
+  gap_partial_body(in, partial, splits, cbs, cbw, sm);
+  // Release / acquire through the ticket, by ONE thread: the block barrier orders every thread's partial sums before
+  // thread 0's gpu-scope acq_rel atomic (cumulativity), and the last block's threads read them after the second
+  // barrier, through L2 (__ldcg).  A __threadfence() by all 256 threads was the kernel's top stall (ncu: ERRBAR).
   __syncthreads();
   const int n = blockIdx.y;
   if (threadIdx.x == 0) {
-    const int ticket = atomicAdd(fc.counters + n, 1);
+    int ticket;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(ticket) : "l"(fc.counters + n) : "memory");
     s_last = ticket == splits - 1;
-    if (s_last) fc.counters[n] = 0;  // ready for the next launch (every other block of this sample is past its atomicAdd)
+    if (s_last) fc.counters[n] = 0;  // ready for the next launch (every other block of this sample is past its atomic)
   }
   __syncthreads();
   if (!s_last) return;
-  __threadfence();
   se_fc_body<1>(sm, partial, splits, fc.inv_hw, n, in.n, fc.c, fc.cmid, fc.blk, fc.slope, fc.offset, fc.gate, fc.vw_in, fc.h);
 }
 
@@ -783,13 +931,34 @@ pool_kernel(TV in, TV out, int kh, int kw, int sh, int sw, int is_max, const int
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = is_max ? -FLT_MAX : 0.f;
-    for (int y = y0; y < y1; ++y)
-      for (int x = x0; x < x1; ++x) {
-        float v[8];
-        ld8(in.p + ((long(n) * in.h + y) * in.w + x) * in.pitch + cg * 8).to_float(v);
+    if (kh <= 3 && kw <= 2) {
+      // windows of up to 3 x 2 (the recognizer's pool): all loads first, then the same y-outer / x-inner order of adds
+      H8 v[6];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = is_max ? fmaxf(acc[i], v[i]) : acc[i] + v[i];
-      }
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx)
+          if (y0 + dy < y1 && x0 + dx < x1)
+            v[dy * 2 + dx] = ld8(in.p + ((long(n) * in.h + y0 + dy) * in.w + x0 + dx) * in.pitch + cg * 8);
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx)
+          if (y0 + dy < y1 && x0 + dx < x1) {
+            float f[8];
+            v[dy * 2 + dx].to_float(f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = is_max ? fmaxf(acc[i], f[i]) : acc[i] + f[i];
+          }
+    } else {
+      for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+          float v[8];
+          ld8(in.p + ((long(n) * in.h + y) * in.w + x) * in.pitch + cg * 8).to_float(v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = is_max ? fmaxf(acc[i], v[i]) : acc[i] + v[i];
+        }
+    }
     if (!is_max) {
       const float inv = 1.f / float((y1 - y0) * (x1 - x0));
 #pragma unroll
@@ -1152,22 +1321,48 @@ void launch_dwconv(const TV& in, const TV& out, const float* wb, const __half* w
   else abort();
 }
 
-int gap_splits(int h) {
-  // splits divide the ROWS (see gap_partial_kernel) and depend on the height only, so that a ragged batch
-  // reduces every text line in the same order as a dense batch of its own width would
-  return h < 1 ? 1 : (h > 8 ? 8 : h);
+// pooled [S][cp] + hidden [S][cmid] + scratch: [2][S][cmid] (scalar path) or [parts][S][cmid | c] with
+// parts * cmid, parts * c <= 4 * kThreads (vector path)
+static int gap_col_block() {
+  static const int v = [] {
+    const char* e = getenv("B200OCR_GAP_COLBLOCK");
+    return e ? std::max(8, atoi(e)) : kGapColBlockDefault;
+  }();
+  return v;
 }
 
-void launch_gap_partial(const TV& in, float* partial, int splits, cudaStream_t s, const SeFuse* fuse) {
+static size_t se_fc_smem_floats(int S, int cp, int cmid) {
+  return size_t(S) * (size_t(cp) + cmid + std::max(2 * cmid, 4 * kThreads));
+}
+
+int gap_splits(int n, int h, int w, int c, bool ragged_safe) {
+  if (ragged_safe) {
+    // row ranges x fixed-width column blocks: depends on the height and on the number of column blocks only, and a
+    // wider (ragged) tensor only appends all-zero blocks, so every text line is reduced in the order a dense batch of
+    // its own width would use (see gap_partial_body)
+    const int rs = h < 1 ? 1 : (h > 8 ? 8 : h);
+    return rs * ((w + gap_col_block() - 1) / gap_col_block());
+  }
+  // dense: splits of >= 8 pixels per lane (two rounds of the unrolled loop), at most 32 per sample; a function of the
+  // sample's shape only, never of the batch size, so that batching leaves every pooled value unchanged
+  (void)n;
+  const int cgs = (c + 7) / 8;
+  const int lanes = kThreads / cgs > 0 ? kThreads / cgs : 1;
+  return std::max(1, std::min(h * w / (lanes * 8), 32));
+}
+
+void launch_gap_partial(const TV& in, float* partial, int splits, bool ragged_safe, cudaStream_t s, const SeFuse* fuse) {
   const int cgs = (in.c + 7) / 8;
   const int lanes = kThreads / cgs > 0 ? kThreads / cgs : 1;
-  size_t smem = size_t(lanes) * cgs * 8 * sizeof(float);
+  const int cbw = gap_col_block();
+  const int cbs = ragged_safe ? (in.w + cbw - 1) / cbw : 0;
+  size_t smem = std::max(size_t(lanes) * cgs * 8 * sizeof(float), size_t(kGapStages) * kThreads * 16);
   if (fuse) {
-    smem = std::max(smem, size_t(cgs * 8 + 3 * fuse->cmid) * sizeof(float));
-    gap_se_kernel<<<dim3(splits, in.n), kThreads, smem, s>>>(in, partial, splits, *fuse);
+    smem = std::max(smem, se_fc_smem_floats(1, cgs * 8, fuse->cmid) * sizeof(float));
+    gap_se_kernel<<<dim3(splits, in.n), kThreads, smem, s>>>(in, partial, splits, cbs, cbw, *fuse);
     return;
   }
-  gap_partial_kernel<<<dim3(splits, in.n), kThreads, smem, s>>>(in, partial, splits);
+  gap_partial_kernel<<<dim3(splits, in.n), kThreads, smem, s>>>(in, partial, splits, cbs, cbw);
 }
 
 void launch_se_fc(const float* partial, int splits, int hw, int n, int c, int cmid, const float* blk,
@@ -1175,7 +1370,7 @@ void launch_se_fc(const float* partial, int splits, int hw, int n, int c, int cm
   const int cp = (c + 7) / 8 * 8;
   // samples per block: share the weight reads between samples once there are enough samples to fill the SMs
   const int S = n >= 4 * 148 ? 4 : (n >= 2 * 148 ? 2 : 1);
-  const size_t smem = size_t(S) * (cp + 3 * cmid) * sizeof(float);
+  const size_t smem = se_fc_smem_floats(S, cp, cmid) * sizeof(float);
   const float inv = 1.f / float(hw);
   if (S == 4) se_fc_kernel<4><<<(n + 3) / 4, kThreads, smem, s>>>(partial, splits, inv, n, c, cmid, blk, slope, offset, gate, vw_in, h);
   else if (S == 2) se_fc_kernel<2><<<(n + 1) / 2, kThreads, smem, s>>>(partial, splits, inv, n, c, cmid, blk, slope, offset, gate, vw_in, h);
