@@ -380,7 +380,7 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
         float* prob = vecp(L.out);
         int* idx = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(prob) + align_up(size_t(in.n) * in.w * 4, 256));
         if (!opt_.force_simt && ctc_tc_eligible(in, L.cin_pad))
-          launch_ctc_head_tc(in, d_wh_ + L.wh_off, d_wf_ + L.bias_off, L.cin_pad, L.cout, L.cout_pad, idx, prob, s,
+          launch_ctc_head_tc(in, d_wh_ + L.wh_off, d_wf_ + L.wf_off, L.cin_pad, L.cout, L.cout_pad, idx, prob, s,
                              vwp(L.in));
         else
           launch_ctc_head_simt(in, d_wh_ + L.wh_off, d_wf_ + L.bias_off, L.cin_pad, L.cout, L.cout_pad, idx, prob, s,

@@ -370,6 +370,10 @@ struct Builder {
     if (ctc) {
       // padded classes must never win the argmax nor contribute to the softmax sum
       for (int co = L.cout; co < L.cout_pad; ++co) plan.wf[L.bias_off + co] = -30000.f;
+      // the tcgen05 head works in the log2 domain (logit * log2(e) in one FFMA, then a bare ex2): bias * log2(e)
+      std::vector<float> b2(size_t(L.cout_pad));
+      for (int co = 0; co < L.cout_pad; ++co) b2[co] = plan.wf[L.bias_off + co] * 1.4426950408889634f;
+      L.wf_off = push_f(b2);
       L.out = new_tensor(prog.ops[j].out("Out"), N, true);  // (prob, idx) per token, not [T,6625]
     } else {
       L.out = new_tensor(op.out("Out"), N);
