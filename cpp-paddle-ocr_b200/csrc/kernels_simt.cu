@@ -974,45 +974,69 @@ pool_kernel(TV in, TV out, int kh, int kw, int sh, int sw, int is_max, const int
 }
 
 // ---------------------------------------------------------------- SVTR neck
-// one warp per token; C <= 256
+// LPT lanes (16 for C <= 128, else 32; 8 channels per lane, C <= 256) own one token, and a lane group normalises
+// kLnTok consecutive tokens at a time: all their 16-byte loads are issued before the first reduction, so a warp has
+// 4-8 tokens in flight instead of one load followed by two shuffle chains.
+constexpr int kLnTok = 4;
+
+template <int LPT>
 __global__ void __launch_bounds__(kThreads)
 layernorm_kernel(TV in, TV out, const float* __restrict__ gb, float eps, const int* __restrict__ vw) {
   const long rows = long(in.n) * in.h * in.w;
-  const int lane = threadIdx.x & 31;
-  const long row = (blockIdx.x * long(blockDim.x) + threadIdx.x) >> 5;
-  if (row >= rows) return;
+  const int lane = threadIdx.x % LPT;
+  const long group = (blockIdx.x * long(blockDim.x) + threadIdx.x) / LPT;
+  const long row0 = group * kLnTok;
+  if (row0 >= rows) return;  // uniform over the lane group (and over the warp's shuffles: masks below are per group)
+  const unsigned gmask = LPT == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
   const int c0 = lane * 8;
   const bool have = c0 < in.c;
-  if (vw && int(row % in.w) >= vw[row / (long(in.h) * in.w)]) {
-    if (have) { H8 z; z.u = make_uint4(0, 0, 0, 0); st8(out.p + row * out.pitch + c0, z); }
-    return;
+  const long hw = long(in.h) * in.w;
+  H8 raw[kLnTok];
+  bool live[kLnTok], pad[kLnTok];
+#pragma unroll
+  for (int t = 0; t < kLnTok; ++t) {
+    const long row = row0 + t;
+    live[t] = row < rows;
+    pad[t] = live[t] && vw && int(row % in.w) >= vw[row / hw];
+    raw[t].u = make_uint4(0, 0, 0, 0);
+    if (live[t] && !pad[t] && have) raw[t] = ld8(in.p + row * in.pitch + c0);
   }
-  float x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (have) ld8(in.p + row * in.pitch + c0).to_float(x);
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s += (c0 + i < in.c) ? x[i] : 0.f;
-#pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / float(in.c);
-  float v = 0.f;
+  float g[8], bta[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float d = (c0 + i < in.c) ? x[i] - mean : 0.f;
-    v = fmaf(d, d, v);
+    const int c = c0 + i;
+    g[i] = c < in.c ? gb[c] : 0.f;
+    bta[i] = c < in.c ? gb[in.c + c] : 0.f;
   }
+  const float inv_c = 1.f / float(in.c);
 #pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const float rstd = rsqrtf(v / float(in.c) + eps);
-  if (have) {
+  for (int t = 0; t < kLnTok; ++t) {
+    if (!live[t]) continue;
+    const long row = row0 + t;
+    float x[8];
+    raw[t].to_float(x);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += (c0 + i < in.c) ? x[i] : 0.f;
+#pragma unroll
+    for (int o = LPT / 2; o; o >>= 1) s += __shfl_xor_sync(gmask, s, o);
+    const float mean = s * inv_c;
+    float v = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int c = c0 + i;
-      x[i] = (c < in.c) ? (x[i] - mean) * rstd * gb[c] + gb[in.c + c] : 0.f;
+      const float d = (c0 + i < in.c) ? x[i] - mean : 0.f;
+      v = fmaf(d, d, v);
     }
-    H8 o;
-    o.from_float(x);
-    st8(out.p + row * out.pitch + c0, o);
+#pragma unroll
+    for (int o = LPT / 2; o; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+    const float rstd = rsqrtf(v * inv_c + eps);
+    if (have) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = (c0 + i < in.c && !pad[t]) ? (x[i] - mean) * rstd * g[i] + bta[i] : 0.f;
+      H8 o;
+      o.from_float(x);
+      st8(out.p + row * out.pitch + c0, o);
+    }
   }
 }
 
@@ -1414,8 +1438,9 @@ void launch_pool(const TV& in, const TV& out, int kh, int kw, int sh, int sw, bo
 
 void launch_layernorm(const TV& in, const TV& out, const float* gb, float eps, cudaStream_t s, const int* vw) {
   const long rows = long(in.n) * in.h * in.w;
-  const long blocks = (rows * 32 + kThreads - 1) / kThreads;
-  layernorm_kernel<<<int(blocks), kThreads, 0, s>>>(in, out, gb, eps, vw);
+  const long groups = (rows + kLnTok - 1) / kLnTok;
+  if (in.c <= 128) layernorm_kernel<16><<<int((groups * 16 + kThreads - 1) / kThreads), kThreads, 0, s>>>(in, out, gb, eps, vw);
+  else layernorm_kernel<32><<<int((groups * 32 + kThreads - 1) / kThreads), kThreads, 0, s>>>(in, out, gb, eps, vw);
 }
 
 void launch_attention(const TV& qkv, const TV& out, int heads, int hd, float scale, cudaStream_t s, const int* vw) {
