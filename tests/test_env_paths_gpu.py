@@ -1,0 +1,81 @@
+"""The diagnostic switches documented in INTEGRATION.md select alternative kernels for the same layers (un-fused SE
+gate, one-tile-per-CTA depthwise kernel, generic depthwise kernel, CUDA-core attention, scalar stem ...).  They are read
+once per process, so every variant runs in its own interpreter on the same seeded inputs; results must agree with the
+default path: bit for bit where the arithmetic is the same, within fp16 output rounding where the summation order
+differs.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r"""
+import os, sys, numpy as np
+root = sys.argv[1]
+for p in (root, os.path.join(root, "cpp-paddle-ocr_b200"), os.path.join(root, "tools")):
+    sys.path.insert(0, p)
+import b200ocr
+models = sys.argv[2]
+rng = np.random.default_rng(7)
+out = {}
+net = b200ocr.Net(f"{models}/rec", 0, 0)
+x = rng.standard_normal((5, 3, 28, 232)).astype(np.float32)
+prob, idx = net.forward(x, widths=np.array([232, 200, 96, 57, 180], np.int32))
+out["rec_prob"], out["rec_idx"] = prob, idx
+net.close()
+net = b200ocr.Net(f"{models}/det", 0, 0)
+prob, _ = net.forward(rng.standard_normal((2, 3, 96, 160)).astype(np.float32), thresh_u8=51)
+out["det_prob"] = prob
+net.close()
+net = b200ocr.Net(f"{models}/cls", 0, 0)
+out["cls"] = net.forward(rng.standard_normal((9, 3, 48, 192)).astype(np.float32))
+net.close()
+np.savez(sys.argv[3], **out)
+"""
+
+
+def _run(models_dir, tmp_path, name, env):
+    path = os.path.join(str(tmp_path), name + ".npz")
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", SCRIPT, ROOT, models_dir, path], capture_output=True, text=True, env=e,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return dict(np.load(path))
+
+
+@pytest.fixture(scope="module")
+def default(models_dir, tmp_path_factory):
+    return _run(models_dir, tmp_path_factory.mktemp("env"), "default", {})
+
+
+# (switch, bit-identical?)
+VARIANTS = [
+    ({"B200OCR_NO_SE_FUSE": "1"}, True),          # same se_fc_body arithmetic, launched on its own
+    ({"B200OCR_DWCONV_NO_PERSIST": "1"}, False),  # one tile per CTA
+    ({"B200OCR_DWCONV_GENERIC": "1"}, False),
+    ({"B200OCR_GAP_COLBLOCK": "64"}, False),      # more pooling splits: different summation order
+    ({"B200OCR_OLD_ATTENTION": "1"}, False),      # CUDA-core attention: fp32 probabilities instead of fp16 fragments
+    ({"B200OCR_OLD_STEM": "1"}, False),
+    ({"B200OCR_TMA_STORE": "1"}, True),           # same accumulators, stored through shared memory + TMA
+    ({"B200OCR_CONV_PERSIST_MIN": "1000000"}, True),  # never the persistent convolution kernel
+]
+
+
+@pytest.mark.parametrize("env,exact", VARIANTS, ids=[next(iter(v[0])) for v in VARIANTS])
+def test_switch_agrees_with_default(models_dir, tmp_path, default, env, exact):
+    got = _run(models_dir, tmp_path, "variant", env)
+    for k, ref in default.items():
+        if exact:
+            assert np.array_equal(got[k], ref), k
+        elif k == "rec_idx":
+            # a different arg-max only where the two runs' own max-probabilities are close to a tie
+            diff = got[k] != ref
+            assert diff.mean() < 0.05, (k, diff.mean())
+        else:
+            assert np.allclose(got[k], ref, rtol=0, atol=3e-2), (k, np.abs(got[k] - ref).max())
