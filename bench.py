@@ -341,7 +341,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
-    ap.add_argument("--workers", type=int, default=2, help="workers (streams) per GPU sharing a step's batch")
+    ap.add_argument("--workers", type=int, default=3, help="workers (streams) per GPU sharing a step's batch")
     ap.add_argument("--e2e-workers", type=int, default=3, help="workers per GPU in the host-buffer (e2e) measurement")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-images", type=int, default=24, help="size of the cpu_baseline sample")

@@ -515,7 +515,8 @@ _sig("b200ocr_kernel_conv", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_
 
 def kernel_conv(x, filt, bias, act=0, post_scale=1.0, post_shift=0.0, residual=None, out_widths=None, force_simt=False,
                 device=0):
-    """x [n,cin,h,w], filt [cout,cin,kh,kw] (stride 1, same padding), bias [cout] -> [n,cout,h,w] fp32."""
+    """x [n,cin,h,w], filt [cout,cin,kh,kw] (stride 1, same padding), bias [cout] -> [n,cout,h,w] fp32.
+    force_simt: 0/False = the engine's choice, 1/True = CUDA-core kernel, 2 = skip the narrow-1x1 mma.sync kernel."""
     x = np.ascontiguousarray(x, np.float32)
     filt = np.ascontiguousarray(filt, np.float32)
     bias = np.ascontiguousarray(bias, np.float32)
@@ -527,5 +528,5 @@ def kernel_conv(x, filt, bias, act=0, post_scale=1.0, post_shift=0.0, residual=N
     wd = None if out_widths is None else np.ascontiguousarray(out_widths, np.int32)
     check(lib.b200ocr_kernel_conv(device, x.ctypes.data, n, cin, h, w, filt.ctypes.data, bias.ctypes.data, cout, kh, kw, act,
                                   post_scale, post_shift, None if res is None else res.ctypes.data,
-                                  None if wd is None else wd.ctypes.data, 1 if force_simt else 0, out.ctypes.data))
+                                  None if wd is None else wd.ctypes.data, int(force_simt), out.ctypes.data))
     return out

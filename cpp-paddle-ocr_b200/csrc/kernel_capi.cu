@@ -151,7 +151,11 @@ int b200ocr_kernel_conv(int device, const float* x, int n, int cin, int h, int w
     e.act = act; e.s2 = post_scale; e.t2 = post_shift;
     if (residual) { e.res = dr.as<__half>(); e.res_pitch = op; }
     const int* vw = out_widths ? dvw.as<int>() : nullptr;
-    if (!force_simt && conv_tc_eligible(in, o, g)) {
+    // force_simt: 0 = the engine's choice (mma.sync stream for narrow 1x1, else tcgen05, else CUDA cores), 1 = CUDA cores,
+    // 2 = skip the narrow-1x1 kernel (tcgen05 where eligible)
+    if (!force_simt && launch_pwconv_mma(in, o, dw.as<__half>(), db.as<float>(), g, e, nullptr, vw)) {
+      cuda_check(cudaDeviceSynchronize(), "pwconv_mma");
+    } else if (force_simt != 1 && conv_tc_eligible(in, o, g)) {
       ConvTcPlan plan = make_conv_tc_plan(in, o, dw.as<__half>(), g);
       launch_conv_tc(plan, db.as<float>(), e, nullptr, vw);
       cuda_check(cudaDeviceSynchronize(), "conv_tc");

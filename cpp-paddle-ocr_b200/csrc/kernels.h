@@ -44,6 +44,10 @@ bool conv_tc_eligible(const TV& in, const TV& out, const ConvGeom& g);
 ConvTcPlan make_conv_tc_plan(const TV& in, const TV& out, const __half* w, const ConvGeom& g);
 void free_conv_tc_plan(ConvTcPlan* p);
 void launch_conv_tc(const ConvTcPlan& p, const float* bias, const Epi& e, cudaStream_t s, const int* vw = nullptr);
+// Narrow 1x1 convolutions (<= 64 input channels) on mma.sync, streaming over the pixels (pwconv.cu); false = shape not
+// covered, nothing launched.  w: fp16 [cout_pad][cin_pad] as plan.cpp packs it.
+bool launch_pwconv_mma(const TV& in, const TV& out, const __half* w, const float* bias, const ConvGeom& g, const Epi& e,
+                       cudaStream_t s, const int* vw = nullptr);
 // w_bias: fp32 [taps][cp] weights + [cp] bias; w_half: the same weights as fp16 [taps][cp] (FHFMA kernel), or
 // nullptr to multiply with the fp32 weights (conversion + FFMA: slower, one rounding less)
 void launch_dwconv(const TV& in, const TV& out, const float* w_bias, const __half* w_half, const ConvGeom& g,

@@ -240,8 +240,9 @@ int b200ocr_kernel_dwconv(int device, const float* x, int n, int c, int h, int w
                           const int* out_widths, float* out, int* out_h, int* out_w);
 /* Dense convolution = Paddle conv2d (stride 1, "same" padding, odd kh x kw; + folded bias, activation 0 none / 1 relu /
  * 2 hard-swish / 3 swish, scalar affine, optional residual [n,cout,h,w] added after the affine): x [n,cin,h,w], filt
- * [cout][cin][kh][kw].  Takes the tcgen05 implicit-GEMM kernel when the shape is eligible (cin >= 8), the CUDA-core
- * kernel otherwise or when force_simt != 0.  out_widths as above.  out [n,cout,h,w]. */
+ * [cout][cin][kh][kw].  force_simt = 0: the engine's choice (the mma.sync pixel stream for 1x1 filters with <= 48 input
+ * and <= 64 output channels, else the tcgen05 implicit-GEMM kernel when the shape is eligible (cin >= 8), else the CUDA-core kernel);
+ * 1: the CUDA-core kernel; 2: as 0 without the narrow-1x1 kernel.  out_widths as above.  out [n,cout,h,w]. */
 int b200ocr_kernel_conv(int device, const float* x, int n, int cin, int h, int w, const float* filt, const float* bias,
                         int cout, int kh, int kw, int act, float post_scale, float post_shift, const float* residual,
                         const int* out_widths, int force_simt, float* out);

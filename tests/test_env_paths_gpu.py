@@ -64,6 +64,7 @@ VARIANTS = [
     ({"B200OCR_OLD_STEM": "1"}, False),
     ({"B200OCR_TMA_STORE": "1"}, True),           # same accumulators, stored through shared memory + TMA
     ({"B200OCR_CONV_PERSIST_MIN": "1000000"}, True),  # never the persistent convolution kernel
+    ({"B200OCR_NO_PWCONV": "1"}, False),          # narrow 1x1 convolutions on tcgen05 instead of the mma.sync stream
 ]
 
 

@@ -147,7 +147,8 @@ def test_conv_matches_torch(n, cin, cout, h, w, kh, kw, simt):
     act = int(rng.integers(0, 4))
     s2, t2 = (0.95, 0.03) if act == 2 else (1.0, 0.0)
     res = _h(rng.standard_normal((n, cout, h, w))) if (cin + cout) % 3 == 0 else None
-    got = b200ocr.kernel_conv(x, filt, bias, act, s2, t2, residual=res, force_simt=simt)
+    # 2 = not the narrow-1x1 mma.sync kernel (tested further down): this test is about the tcgen05 path
+    got = b200ocr.kernel_conv(x, filt, bias, act, s2, t2, residual=res, force_simt=1 if simt else 2)
     ref = _ref_conv(x, filt, bias, act, s2, t2, res)
     tol = 2e-3 * float(np.abs(ref).max()) + 2e-3
     assert float(np.abs(got - ref).max()) <= tol, (float(np.abs(got - ref).max()), tol)
@@ -167,4 +168,46 @@ def test_conv_ragged_rows_equal_dense_rows_bitwise():
         for i, wd in enumerate(widths):
             alone = b200ocr.kernel_conv(x[i:i + 1, :, :, :wd], filt, bias, 2, 1.03, -0.02)
             assert np.array_equal(got[i, :, :, :wd], alone[0]), (cin, cout, kh, kw, i)
+            assert not got[i, :, :, wd:].any()
+
+# ---- narrow 1x1 convolutions (pwconv.cu: mma.sync stream over the pixels; the engine takes it for C_in <= 48 and
+# C_out <= 64, the wider outputs below go to the tcgen05 kernel unless B200OCR_PWCONV_MAX_COUT raises the limit)
+@pytest.mark.parametrize("n,cin,cout,h,w", [
+    (3, 8, 8, 24, 96), (2, 8, 24, 13, 37), (2, 8, 32, 5, 7), (3, 16, 32, 14, 193), (2, 16, 40, 12, 48), (2, 16, 88, 6, 24),
+    (2, 16, 104, 6, 24), (2, 24, 8, 12, 48), (2, 32, 8, 12, 48), (2, 32, 16, 6, 24), (2, 32, 48, 20, 32), (2, 32, 200, 3, 12),
+    (2, 40, 16, 6, 24), (2, 48, 16, 6, 24), (2, 48, 48, 20, 33), (2, 48, 96, 10, 16), (1, 12, 96, 10, 16), (1, 18, 96, 5, 8),
+    (1, 42, 96, 5, 8), (1, 16, 32, 1, 1), (1, 16, 32, 1, 17),
+])
+def test_narrow_pointwise_conv_matches_torch(n, cin, cout, h, w):
+    import b200ocr
+    rng = np.random.default_rng(cin * 11 + cout * 5 + h + w)
+    x = _h(rng.standard_normal((n, cin, h, w)))
+    filt = _h(rng.standard_normal((cout, cin, 1, 1)) / np.sqrt(cin))
+    bias = rng.standard_normal(cout).astype(np.float32) * 0.2
+    act = int(rng.integers(0, 4))
+    s2, t2 = (0.95, 0.03) if act == 2 else (1.0, 0.0)
+    res = _h(rng.standard_normal((n, cout, h, w))) if (cin + cout) % 3 == 0 else None
+    got = b200ocr.kernel_conv(x, filt, bias, act, s2, t2, residual=res)
+    ref = _ref_conv(x, filt, bias, act, s2, t2, res)
+    tol = 2e-3 * float(np.abs(ref).max()) + 2e-3
+    assert float(np.abs(got - ref).max()) <= tol, (float(np.abs(got - ref).max()), tol)
+    # and it agrees with the CUDA-core kernel (same fp16 operands, fp32 accumulation) to output rounding
+    simt = b200ocr.kernel_conv(x, filt, bias, act, s2, t2, residual=res, force_simt=True)
+    assert float(np.abs(got - simt).max()) <= tol
+
+
+def test_narrow_pointwise_conv_ragged_rows_equal_dense_rows_bitwise():
+    import b200ocr
+    rng = np.random.default_rng(12)
+    for (cin, cout, h, w) in [(16, 32, 14, 61), (32, 64, 7, 50), (8, 24, 3, 33)]:
+        widths = [w, w // 2 + 3, 9, w - 1]
+        x = _h(rng.standard_normal((len(widths), cin, h, w)))
+        for i, wd in enumerate(widths):
+            x[i, :, :, wd:] = 0
+        filt = _h(rng.standard_normal((cout, cin, 1, 1)) / np.sqrt(cin))
+        bias = rng.standard_normal(cout).astype(np.float32) * 0.2
+        got = b200ocr.kernel_conv(x, filt, bias, 2, 1.03, -0.02, out_widths=widths)
+        for i, wd in enumerate(widths):
+            alone = b200ocr.kernel_conv(x[i:i + 1, :, :, :wd], filt, bias, 2, 1.03, -0.02)
+            assert np.array_equal(got[i, :, :, :wd], alone[0]), (cin, cout, i)
             assert not got[i, :, :, wd:].any()
