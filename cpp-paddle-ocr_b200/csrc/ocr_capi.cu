@@ -502,6 +502,14 @@ int b200ocr_pool_status(b200ocr_pool_t pool, char** json) {
     const double up = std::chrono::duration<double>(std::chrono::steady_clock::now() - pool->t_start).count();
     size_t queued = 0;
     for (auto& d : pool->devs) { std::lock_guard<std::mutex> lk(d->mu); queued += d->queue.size(); }
+    long long st[4] = {0, 0, 0, 0};
+    for (auto& d : pool->devs)
+      for (auto& w : d->workers) {
+        long long t[4];
+        w->stage_totals(t);
+        for (int i = 0; i < 4; ++i) st[i] += t[i];
+      }
+    auto per_image = [&](int i) { return st[3] > 0 ? double(st[i]) / 1e3 / double(st[3]) : 0.0; };
     // compact, keys in alphabetical order like jsoncpp writes them
     std::string o = "{\"average_processing_time_ms\":" + json_double(avg_ms) +
                     ",\"batches\":" + std::to_string(pool->batches.load()) +
@@ -509,6 +517,8 @@ int b200ocr_pool_status(b200ocr_pool_t pool, char** json) {
                     ",\"idle_workers\":" + std::to_string(b200ocr_pool_idle_count(pool)) +
                     ",\"queued_requests\":" + std::to_string(queued) +
                     ",\"running\":" + (pool->running.load() ? "true" : "false") +
+                    ",\"stage_ms_per_image\":{\"cls\":" + json_double(per_image(1)) + ",\"det\":" + json_double(per_image(0)) +
+                    ",\"rec\":" + json_double(per_image(2)) + "}" +
                     ",\"successful_requests\":" + std::to_string(pool->successful_requests.load()) +
                     ",\"total_requests\":" + std::to_string(pool->total_requests.load()) +
                     ",\"uptime_s\":" + json_double(up) +

@@ -589,6 +589,14 @@ void Worker::run_device(const std::vector<DevImg>& dimgs, std::vector<std::vecto
   std::vector<std::vector<std::string>> texts;
   std::vector<std::vector<float>> scores;
   rec_->run(dimgs, calls, &texts, &scores, stream_, trace ? &t_rec : nullptr);
+  {
+    // det waits for its boxes, cls is only enqueued (its GPU time is waited for inside rec): host wall time per stage
+    const double ms_end = ms_since(t_begin);
+    stage_us_[0] += (long long)(ms_det * 1e3);
+    stage_us_[1] += (long long)((ms_cls - ms_roi) * 1e3);
+    stage_us_[2] += (long long)((ms_end - ms_cls) * 1e3);
+    images_ += nb;
+  }
   if (trace) {
     auto v = [](const std::vector<double>& t, int i) { return int(t.size()) > i ? t[i] : 0.0; };
     fprintf(stderr, "[b200ocr trace] worker %d: %d images, %zu rois | det %.2f (pre %.2f net %.2f post+sync %.2f) roi %.2f "

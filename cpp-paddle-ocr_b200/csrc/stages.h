@@ -12,6 +12,7 @@
 // launch when they share the padded width the reference would have used).
 #pragma once
 #include <array>
+#include <atomic>
 #include <memory>
 #include <string>
 #include <vector>
@@ -163,6 +164,12 @@ class Worker {
   int worker_id() const { return worker_id_; }
   int device() const { return device_; }
   long launches() const;
+  // cumulative host wall time (us) this worker spent in det / cls / rec and the images it processed: the per-stage
+  // times the reference measures (`times`, ocr_worker.cpp:233-289) and then drops, kept for the pool's status
+  void stage_totals(long long out[4]) const {
+    for (int i = 0; i < 3; ++i) out[i] = stage_us_[i].load();
+    out[3] = images_.load();
+  }
   DetStage& det() { return *det_; }
   RecStage& rec() { return *rec_; }
   ClsStage* cls() { return cls_.get(); }
@@ -176,6 +183,7 @@ class Worker {
   void run_device(const std::vector<DevImg>& dimgs, std::vector<std::vector<WordOut>>* words);
   ImageBatch batch_;
   DevBuf copy_;
+  std::atomic<long long> stage_us_[3] = {{0}, {0}, {0}}, images_{0};
 };
 
 // jsoncpp-compatible compact writer pieces (StreamWriterBuilder, indentation "", emitUTF8 true)

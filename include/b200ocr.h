@@ -173,7 +173,10 @@ int b200ocr_pool_worker_count(b200ocr_pool_t pool);
 /* Service counters as one compact JSON object (free with b200ocr_free); the reference's getStatusInfo
  * (src/ocr_ipc_service.cpp:438-448) plus what it declares but never updates:
  * {"average_processing_time_ms","batches","failed_requests","idle_workers","queued_requests","running",
- *  "successful_requests","total_requests","uptime_s","workers"}; the average is submission -> completion. */
+ *  "stage_ms_per_image":{"cls","det","rec"},"successful_requests","total_requests","uptime_s","workers"}; the average
+ * is submission -> completion; stage_ms_per_image is the workers' host wall time per image by stage (the `times` the
+ * reference's stages report and its worker drops; det includes the wait for its boxes, cls is enqueue only, rec
+ * includes the wait for cls + rec). */
 int b200ocr_pool_status(b200ocr_pool_t pool, char** json);
 int b200ocr_pool_idle_count(b200ocr_pool_t pool);
 
