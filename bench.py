@@ -176,8 +176,16 @@ def run_ours(args):
     models = make_synth_weights.ensure_models()
 
     B, K, W = args.batch, args.steps, args.warmup
-    NW = max(1, args.workers)
-    NWH = max(1, args.e2e_workers)
+    # Every worker is a host thread that spins on its stream between launches: more workers than host cores per GPU
+    # cost more than they hide.  Measured on one B200 with 16 host cores: 1 / 2 / 3 / 4 workers = 4928 / 5425 / 5676 /
+    # 5595 images/s; at 8 GPUs the same 16 cores leave two per GPU.
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    auto = min(3, max(1, cores // max(1, world)))
+    NW = args.workers if args.workers > 0 else auto
+    NWH = args.e2e_workers if args.e2e_workers > 0 else auto
     # Several workers per GPU (own stream + networks each, like the reference pool's workers), every one fed its share
     # of the step's batch from its own thread: while one waits on the host between its two sync points, the others keep
     # the GPU busy.  Results per image are identical to a single worker's.  The device-resident measurement uses NW
@@ -341,8 +349,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
-    ap.add_argument("--workers", type=int, default=3, help="workers (streams) per GPU sharing a step's batch")
-    ap.add_argument("--e2e-workers", type=int, default=3, help="workers per GPU in the host-buffer (e2e) measurement")
+    ap.add_argument("--workers", type=int, default=0,
+                    help="workers (streams) per GPU sharing a step's batch; 0 = min(3, host cores // GPUs)")
+    ap.add_argument("--e2e-workers", type=int, default=0,
+                    help="workers per GPU in the host-buffer (e2e) measurement; 0 = same rule")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-images", type=int, default=24, help="size of the cpu_baseline sample")
     ap.add_argument("--ref-images", type=int, default=16, help="images per step of the reference arm")
