@@ -307,3 +307,36 @@ def test_oracle_worker_on_reference_fixtures(models_dir, golden_dir):
             assert len(word["box"]) == 4 and 0.0 <= word["confidence"] <= 1.0
     e = json.loads(w.process(9, np.zeros((0, 0, 3), np.uint8)))
     assert e["success"] is False and e["error"] == "Empty image data provided"
+
+
+# ---- the JPEG decode oracle is pinned against the library the reference decodes with
+def test_jpeg_oracle_equals_cv2_imdecode_bitwise(golden_dir):
+    """oracle/jpeg_decode.py (libjpeg's ISLOW IDCT, fancy upsampling, YCbCr tables restated) against cv2.imdecode =
+    OpenCV + libjpeg-turbo, which is what the reference's cv::imread / cv::imdecode call
+    (src/ocr_ipc_service.cpp:336-344): the reference's own test image, then seeded images at several qualities,
+    chroma samplings (4:2:0 / 4:2:2 / 4:4:4 / grey), odd sizes and restart intervals."""
+    import cv2
+    import synth_data
+    from oracle import jpeg_decode
+    data = open(os.path.join(golden_dir, "card-jd.jpg"), "rb").read()
+    assert np.array_equal(jpeg_decode.decode(data), cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR))
+    rng = np.random.default_rng(0)
+    imgs = [synth_data.card(0)[:120, :201], rng.integers(0, 256, (37, 53, 3), dtype=np.uint8),
+            rng.integers(0, 256, (1, 1, 3), dtype=np.uint8), synth_data.card(1)[100:117, :300]]
+    samplings = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+                 cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
+    n = 0
+    for k, im in enumerate(imgs):
+        for q in (30, 90, 100):
+            for sf in samplings:
+                rst = (k + q) % 3  # 0 = no restart markers
+                ok, buf = cv2.imencode(".jpg", im, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf,
+                                                    cv2.IMWRITE_JPEG_RST_INTERVAL, rst])
+                assert ok
+                assert np.array_equal(jpeg_decode.decode(buf.tobytes()), cv2.imdecode(buf, cv2.IMREAD_COLOR)), (k, q, sf, rst)
+                n += 1
+        ok, buf = cv2.imencode(".jpg", cv2.cvtColor(im, cv2.COLOR_BGR2GRAY), [cv2.IMWRITE_JPEG_QUALITY, 80])
+        assert np.array_equal(jpeg_decode.decode(buf.tobytes()), cv2.imdecode(buf, cv2.IMREAD_COLOR))
+    assert n == 36
+    with pytest.raises(ValueError):
+        jpeg_decode.decode(b"\x89PNG\r\n")
