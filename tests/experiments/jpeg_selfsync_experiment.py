@@ -7,7 +7,7 @@ falls onto true code boundaries, and once its (bit position, block-in-MCU, coeff
 state it stays correct.  This script measures, against the sequential decode of oracle/jpeg_decode.py's tables, how many
 bits a speculative decoder needs before it is synchronised, for every chunk start of an image:
 
-    python tools/jpeg_selfsync_experiment.py [file.jpg ...]        (default: tests/golden/card-jd.jpg + synthetic cards)
+    python tests/experiments/jpeg_selfsync_experiment.py [file.jpg ...]        (default: tests/golden/card-jd.jpg + synthetic cards)
 """
 import os
 import struct
@@ -15,7 +15,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 from oracle import jpeg_decode as J  # noqa: E402
