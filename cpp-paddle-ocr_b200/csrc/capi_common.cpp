@@ -11,6 +11,7 @@
 namespace b200ocr {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
+std::string json_quote(const std::string& s);  // stages.cu
 }  // namespace b200ocr
 
 extern "C" {
@@ -29,7 +30,7 @@ int b200ocr_model_params_json(const char* pdmodel_path, char** json) {
     for (const std::string& n : prog.param_names()) {
       if (!first) os << ",";
       first = false;
-      os << "{\"name\":\"" << n << "\",\"dims\":[";
+      os << "{\"name\":" << b200ocr::json_quote(n) << ",\"dims\":[";
       const auto& d = prog.vars.at(n).dims;
       for (size_t i = 0; i < d.size(); ++i) os << (i ? "," : "") << d[i];
       os << "]}";

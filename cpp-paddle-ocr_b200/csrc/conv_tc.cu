@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <stdexcept>
 
 namespace b200ocr {
 
@@ -529,11 +530,11 @@ EncodeTiledFn encode_fn() {
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
         qres != cudaDriverEntryPointSuccess || !p) {
-      fprintf(stderr, "b200ocr: cuTensorMapEncodeTiled is unavailable (driver too old?)\n");
-      abort();
+      return;  // reported below: the library never exits the host process (capi_util.h)
     }
     fn = reinterpret_cast<EncodeTiledFn>(p);
   });
+  if (!fn) throw std::runtime_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
   return fn;
 }
 
@@ -544,9 +545,10 @@ void encode(CUtensorMap* tm, void* base, int rank, const cuuint64_t* dims, const
                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    fprintf(stderr, "b200ocr: cuTensorMapEncodeTiled failed with %d (rank %d dims %llu %llu box %u %u)\n", int(r),
-            rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
-    abort();
+    char msg[200];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed with %d (rank %d dims %llu %llu box %u %u)", int(r),
+             rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    throw std::runtime_error(msg);
   }
 }
 

@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <stdexcept>
+#include <string>
 
 namespace b200ocr {
 
@@ -251,11 +253,11 @@ EncodeTiledFn encode_fn() {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) {
-      fprintf(stderr, "b200ocr: cuTensorMapEncodeTiled is unavailable\n");
-      abort();
+      return;
     }
     fn = reinterpret_cast<EncodeTiledFn>(p);
   });
+  if (!fn) throw std::runtime_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
   return fn;
 }
 void encode2d(CUtensorMap* tm, const void* base, cuuint64_t d0, cuuint64_t d1, cuuint64_t stride1_bytes, cuuint32_t b0,
@@ -267,7 +269,7 @@ void encode2d(CUtensorMap* tm, const void* base, cuuint64_t d0, cuuint64_t d1, c
   CUresult r = encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { fprintf(stderr, "b200ocr: tensor map encode failed (%d)\n", int(r)); abort(); }
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with " + std::to_string(int(r)));
 }
 
 }  // namespace

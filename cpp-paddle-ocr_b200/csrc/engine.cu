@@ -499,7 +499,13 @@ void Net::run(cudaStream_t stream, int thresh_u8) {
     if (I.graph) { cudaGraphExecDestroy(I.graph); I.graph = nullptr; }
     cudaGraph_t g = nullptr;
     cuda_check(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal), "begin capture");
-    record(I, stream, thresh_u8);
+    try {
+      record(I, stream, thresh_u8);
+    } catch (...) {  // never leave the stream in capture mode
+      cudaStreamEndCapture(stream, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
     cuda_check(cudaStreamEndCapture(stream, &g), "end capture");
     cuda_check(cudaGraphInstantiate(&I.graph, g, 0), "graph instantiate");
     cudaGraphDestroy(g);

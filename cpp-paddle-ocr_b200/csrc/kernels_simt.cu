@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstdlib>
+#include <stdexcept>
+#include <string>
 
 namespace b200ocr {
 
@@ -1342,7 +1344,7 @@ void launch_dwconv(const TV& in, const TV& out, const float* wb, const __half* w
   const int grid = grid_for(total);
   if (g.kh == 3 && g.kw == 3) dwconv_kernel<3, 3><<<grid, kThreads, 0, s>>>(in, out, wb, g, e, vw);
   else if (g.kh == 5 && g.kw == 5) dwconv_kernel<5, 5><<<grid, kThreads, 0, s>>>(in, out, wb, g, e, vw);
-  else abort();
+  else throw std::runtime_error("depthwise convolution: only 3x3 and 5x5 filters are implemented");
 }
 
 // pooled [S][cp] + hidden [S][cmid] + scratch: [2][S][cmid] (scalar path) or [parts][S][cmid | c] with
@@ -1447,24 +1449,33 @@ void launch_attention(const TV& qkv, const TV& out, int heads, int hd, float sca
   if (launch_attention_mma(qkv, out, heads, hd, scale, s, vw)) return;
   const int T = qkv.h * qkv.w;
   const size_t smem = (size_t(2) * T * hd + size_t(4) * T) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    configured = smem;
+  if (smem > 227 * 1024)
+    throw std::runtime_error("attention: a text line of " + std::to_string(T) +
+                             " tokens does not fit in shared memory (limit ~1700 tokens = a crop ~13600 px wide "
+                             "at rec height 48)");
+  static size_t configured[64] = {0};  // cudaFuncSetAttribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > 48 * 1024 && (dev >= 64 || smem > configured[dev])) {
+    if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+      throw std::runtime_error("attention: cannot opt in to " + std::to_string(smem) + " bytes of shared memory");
+    if (dev < 64) configured[dev] = smem;
   }
   attention_kernel<<<qkv.n * heads, 128, smem, s>>>(qkv, out, heads, hd, scale, vw);
+  if (cudaPeekAtLastError() != cudaSuccess)
+    throw std::runtime_error(std::string("attention launch: ") + cudaGetErrorString(cudaGetLastError()));
 }
 
 void launch_dbhead(const TV& in, const float* blk, int cmid, float* prob, uint8_t* bitmap, int thresh_u8,
                    cudaStream_t s) {
   const long npix = long(in.n) * in.h * in.w;
-  if (in.c != 24 || cmid != 24) abort();
+  if (in.c != 24 || cmid != 24) throw std::runtime_error("DB head: only the 24 -> 24 -> 1 head of the shipped det graph is implemented");
   dbhead_kernel<24, 24><<<int((npix + 127) / 128), 128, 0, s>>>(in, blk, prob, bitmap, thresh_u8);
 }
 
 void launch_fc_softmax(const float* partial, int splits, int hw, int n, int cin, int cout, const float* blk,
                        float* out, cudaStream_t s) {
-  if (cout > 8) abort();
+  if (cout > 8) throw std::runtime_error("cls head: at most 8 classes");
   fc_softmax_kernel<<<n, 32, 0, s>>>(partial, splits, 1.f / float(hw), cin, cout, blk, out);
 }
 

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <deque>
 #include <map>
+#include <set>
 #include <mutex>
 #include <thread>
 
@@ -100,6 +101,8 @@ struct b200ocr_pool {
   std::mutex res_mu;
   std::condition_variable res_cv;
   std::map<long long, std::string> results;
+  std::set<long long> outstanding;   // issued and not yet consumed by b200ocr_pool_wait (guarded by res_mu)
+  int waiters = 0;                   // threads inside b200ocr_pool_wait (guarded by res_mu)
   int max_batch = 64;
   // status counters (reference OCRIPCService::getStatusInfo, src/ocr_ipc_service.cpp:438-448 -- whose success / time
   // counters are declared but never updated; these are)
@@ -151,6 +154,11 @@ struct b200ocr_pool {
 
   ~b200ocr_pool() {
     running = false;
+    {  // waiters return B200OCR_ERR_RUNTIME instead of touching a destroyed condition variable
+      std::unique_lock<std::mutex> lk(res_mu);
+      res_cv.notify_all();
+      res_cv.wait(lk, [&] { return waiters == 0; });
+    }
     for (auto& d : devs) {
       { std::lock_guard<std::mutex> lk(d->mu); }
       d->cv.notify_all();
@@ -479,20 +487,36 @@ int b200ocr_pool_submit(b200ocr_pool_t pool, int request_id, const b200ocr_image
       if (load < best_load) { best_load = load; best = (start + k) % nd; }
     }
     auto& d = *pool->devs[best];
+    { std::lock_guard<std::mutex> lk(pool->res_mu); pool->outstanding.insert(r->ticket); }
     { std::lock_guard<std::mutex> lk(d.mu); d.queue.push_back(r); }
     d.cv.notify_one();
     *ticket = r->ticket;
   });
 }
 
-int b200ocr_pool_wait(b200ocr_pool_t pool, long long ticket, char** json) {
+int b200ocr_pool_wait_for(b200ocr_pool_t pool, long long ticket, int timeout_ms, char** json) {
   return capi_guard([&] {
     if (!pool || !json) throw std::invalid_argument("null argument");
+    *json = nullptr;
     std::unique_lock<std::mutex> lk(pool->res_mu);
-    pool->res_cv.wait(lk, [&] { return pool->results.count(ticket) != 0; });
-    *json = dup_string(pool->results[ticket]);
-    pool->results.erase(ticket);
+    if (!pool->outstanding.count(ticket)) throw std::invalid_argument("unknown or already consumed ticket");
+    struct Count {
+      b200ocr_pool* p;
+      explicit Count(b200ocr_pool* q) : p(q) { ++p->waiters; }
+      ~Count() { --p->waiters; p->res_cv.notify_all(); }
+    } count(pool);
+    auto ready = [&] { return pool->results.count(ticket) != 0 || !pool->running; };
+    if (timeout_ms < 0) pool->res_cv.wait(lk, ready);
+    else if (!pool->res_cv.wait_for(lk, std::chrono::milliseconds(timeout_ms), ready)) return;  // *json stays NULL
+    auto it = pool->results.find(ticket);
+    if (it == pool->results.end()) throw std::runtime_error("the pool is shutting down");
+    *json = dup_string(it->second);
+    pool->results.erase(it);
+    pool->outstanding.erase(ticket);
   });
+}
+int b200ocr_pool_wait(b200ocr_pool_t pool, long long ticket, char** json) {
+  return b200ocr_pool_wait_for(pool, ticket, -1, json);
 }
 int b200ocr_pool_status(b200ocr_pool_t pool, char** json) {
   return capi_guard([&] {

@@ -276,7 +276,7 @@ void load_params(const std::string& path, PdProgram* prog) {
   std::vector<uint8_t> buf = read_file(path);
   size_t pos = 0;
   auto need = [&](size_t n) {
-    if (pos + n > buf.size()) throw std::runtime_error(path + ": truncated parameter stream");
+    if (n > buf.size() - pos) throw std::runtime_error(path + ": truncated parameter stream");  // no wrap-around
   };
   for (const std::string& name : prog->param_names()) {
     // u32 version | u64 lod_level (+ levels) | u32 tensor version | i32 desc_len | TensorDesc | data
@@ -309,7 +309,11 @@ void load_params(const std::string& path, PdProgram* prog) {
     if (dims != v.dims)
       throw std::runtime_error(path + ": parameter " + name + " dims do not match the graph");
     size_t n = 1;
-    for (int64_t d : dims) n *= (size_t)d;
+    for (int64_t d : dims) {
+      if (d <= 0) throw std::runtime_error(path + ": parameter " + name + " has a non-positive dimension");
+      if ((uint64_t)d > buf.size() / 4 / n) throw std::runtime_error(path + ": truncated parameter stream");
+      n *= (size_t)d;
+    }
     need(n * 4);
     std::vector<float> data(n);
     memcpy(data.data(), &buf[pos], n * 4);

@@ -767,6 +767,18 @@ struct Builder {
       }
     }
     if (plan.input < 0 || plan.output < 0) throw std::runtime_error("plan: graph has no feed/fetch");
+    // shapes the sm_100a kernels do not implement are rejected here, so that *_create fails with a message instead
+    // of the first forward pass
+    for (const Layer& L : plan.layers) {
+      auto bad = [&](const std::string& why) {
+        throw std::runtime_error("plan: layer " + L.name + ": " + why + " (not implemented by the sm_100a kernels)");
+      };
+      if (L.kind == LKind::DwConv && !((L.kh == 3 && L.kw == 3) || (L.kh == 5 && L.kw == 5)))
+        bad("depthwise filter " + std::to_string(L.kh) + "x" + std::to_string(L.kw) + ", only 3x3 and 5x5");
+      if (L.kind == LKind::DbHead && (L.cin != 24 || L.cmid != 24))
+        bad("DB head " + std::to_string(L.cin) + " -> " + std::to_string(L.cmid) + ", only 24 -> 24");
+      if (L.kind == LKind::FcSoftmax && L.cout > 8) bad("classifier head with more than 8 classes");
+    }
     const Layer& last = plan.layers.back();
     plan.kind = last.kind == LKind::DbHead ? "det" : last.kind == LKind::FcSoftmax ? "cls"
               : last.kind == LKind::CtcHead ? "rec" : "generic";

@@ -618,33 +618,55 @@ void Worker::process_resident(const int* request_ids, const std::vector<DevImg>&
   json->assign(n, std::string());
   const auto t_start = Clock::now();
   std::vector<std::vector<WordOut>> words(n);
-  std::string error;
-  try {
-    for (int b0 = 0; b0 < n; b0 += opt_.max_batch) {
-      const int nb = std::min(opt_.max_batch, n - b0);
-      std::vector<DevImg> dimgs(resident.begin() + b0, resident.begin() + b0 + nb);
-      if (cls_) {  // rotations are in place: work on a copy
-        size_t total = 0;
-        for (auto& d : dimgs) total += (size_t(d.rows) * d.stride + 255) & ~size_t(255);
-        copy_.ensure(total);
-        size_t off = 0;
-        for (auto& d : dimgs) {
-          uint8_t* dst = copy_.as<uint8_t>() + off;
-          cuda_check(cudaMemcpyAsync(dst, d.p, size_t(d.rows) * d.stride, cudaMemcpyDeviceToDevice, stream_), "batch copy");
-          off += (size_t(d.rows) * d.stride + 255) & ~size_t(255);
-          d.p = dst;
+  std::vector<std::string> errors(n);
+  auto run_range = [&](int b0, int nb) {
+    std::vector<DevImg> dimgs(resident.begin() + b0, resident.begin() + b0 + nb);
+    if (cls_) {  // rotations are in place: work on a copy
+      size_t total = 0;
+      for (auto& d : dimgs) total += (size_t(d.rows) * d.stride + 255) & ~size_t(255);
+      copy_.ensure(total);
+      size_t off = 0;
+      for (auto& d : dimgs) {
+        uint8_t* dst = copy_.as<uint8_t>() + off;
+        cuda_check(cudaMemcpyAsync(dst, d.p, size_t(d.rows) * d.stride, cudaMemcpyDeviceToDevice, stream_), "batch copy");
+        off += (size_t(d.rows) * d.stride + 255) & ~size_t(255);
+        d.p = dst;
+      }
+    }
+    std::vector<std::vector<WordOut>> w;
+    run_device(dimgs, &w);
+    for (int i = 0; i < nb; ++i) words[b0 + i] = std::move(w[i]);
+  };
+  for (int b0 = 0; b0 < n; b0 += opt_.max_batch) {
+    const int nb = std::min(opt_.max_batch, n - b0);
+    try {
+      run_range(b0, nb);
+    } catch (const std::exception& e) {
+      // The reference handles one request at a time, so a failure there is isolated (src/ocr_worker.cpp:192-206).
+      // Keep that: the images of the failed sub-batch are retried one by one and only the offender reports the error.
+      recover_after_failure();
+      if (nb == 1) { errors[b0] = e.what(); continue; }
+      for (int i = b0; i < b0 + nb; ++i) {
+        try {
+          run_range(i, 1);
+        } catch (const std::exception& e1) {
+          recover_after_failure();
+          words[i].clear();
+          errors[i] = e1.what();
         }
       }
-      std::vector<std::vector<WordOut>> w;
-      run_device(dimgs, &w);
-      for (int i = 0; i < nb; ++i) words[b0 + i] = std::move(w[i]);
     }
-  } catch (const std::exception& e) {
-    error = e.what();
   }
   const double ms = ms_since(t_start);
   for (int i = 0; i < n; ++i)
-    (*json)[i] = result_json(request_ids[i], worker_id_, error.empty(), resident[i].cols, resident[i].rows, ms, words[i], error);
+    (*json)[i] = result_json(request_ids[i], worker_id_, errors[i].empty(), resident[i].cols, resident[i].rows, ms, words[i],
+                             errors[i]);
+}
+
+// After an exception inside a batch: drain the stream and drop the (non-sticky) CUDA error so that the retries start clean.
+void Worker::recover_after_failure() {
+  cudaStreamSynchronize(stream_);
+  cudaGetLastError();
 }
 
 void Worker::process_batch(const int* request_ids, const HostImage* imgs, int n, std::vector<std::string>* json) {
@@ -662,16 +684,30 @@ void Worker::process_batch(const int* request_ids, const HostImage* imgs, int n,
   if (live.empty()) return;
   std::vector<std::string> errors(live.size());
   std::vector<std::vector<WordOut>> words(live.size());
-  try {
-    for (size_t b0 = 0; b0 < live.size(); b0 += size_t(opt_.max_batch)) {
-      const int nb = int(std::min(live.size() - b0, size_t(opt_.max_batch)));
-      batch_.upload(live_imgs.data() + b0, nb, stream_);
-      std::vector<std::vector<WordOut>> w;
-      run_device(batch_.images(), &w);
-      for (int i = 0; i < nb; ++i) words[b0 + i] = std::move(w[i]);
+  auto run_range = [&](size_t b0, int nb) {
+    batch_.upload(live_imgs.data() + b0, nb, stream_);
+    std::vector<std::vector<WordOut>> w;
+    run_device(batch_.images(), &w);
+    for (int i = 0; i < nb; ++i) words[b0 + i] = std::move(w[i]);
+  };
+  for (size_t b0 = 0; b0 < live.size(); b0 += size_t(opt_.max_batch)) {
+    const int nb = int(std::min(live.size() - b0, size_t(opt_.max_batch)));
+    try {
+      run_range(b0, nb);
+    } catch (const std::exception& e) {
+      // failures stay isolated per request, as in the reference (see process_resident)
+      recover_after_failure();
+      if (nb == 1) { errors[b0] = e.what(); continue; }
+      for (size_t i = b0; i < b0 + size_t(nb); ++i) {
+        try {
+          run_range(i, 1);
+        } catch (const std::exception& e1) {
+          recover_after_failure();
+          words[i].clear();
+          errors[i] = e1.what();
+        }
+      }
     }
-  } catch (const std::exception& e) {
-    for (auto& s : errors) s = e.what();
   }
   const double ms = ms_since(t_start);
   for (size_t k = 0; k < live.size(); ++k) {

@@ -181,6 +181,7 @@ class Worker {
   std::unique_ptr<ClsStage> cls_;
   std::unique_ptr<RecStage> rec_;
   void run_device(const std::vector<DevImg>& dimgs, std::vector<std::vector<WordOut>>* words);
+  void recover_after_failure();
   ImageBatch batch_;
   DevBuf copy_;
   std::atomic<long long> stage_us_[3] = {{0}, {0}, {0}}, images_{0};

@@ -167,8 +167,13 @@ int b200ocr_pool_create(const char* model_dir, int n_devices, const int* devices
                         int enable_cls, int max_batch, b200ocr_pool_t* out);
 void b200ocr_pool_destroy(b200ocr_pool_t pool);
 int b200ocr_pool_submit(b200ocr_pool_t pool, int request_id, const b200ocr_image* img, long long* ticket);
-/* Blocks until the request is done; *json is the worker's result line (free with b200ocr_free). */
+/* Blocks until the request is done; *json is the worker's result line (free with b200ocr_free).  A ticket that was
+ * never issued or was already consumed returns B200OCR_ERR_INVALID; b200ocr_pool_destroy wakes pending waiters, which
+ * return B200OCR_ERR_RUNTIME. */
 int b200ocr_pool_wait(b200ocr_pool_t pool, long long ticket, char** json);
+/* Same with a time limit: returns B200OCR_OK with *json == NULL when `timeout_ms` (>= 0) elapsed first; the ticket stays
+ * valid.  timeout_ms < 0 waits forever. */
+int b200ocr_pool_wait_for(b200ocr_pool_t pool, long long ticket, int timeout_ms, char** json);
 int b200ocr_pool_worker_count(b200ocr_pool_t pool);
 /* Service counters as one compact JSON object (free with b200ocr_free); the reference's getStatusInfo
  * (src/ocr_ipc_service.cpp:438-448) plus what it declares but never updates:

@@ -23,9 +23,10 @@ def reference_test_image():
     return img
 
 
-def card(seed: int, width=1024, height=640, out=None, boxes=None):
+def card(seed: int, width=1024, height=640, out=None, boxes=None, lines=None):
     """S-card: light background, 8-12 horizontal text lines, scales 0.6-1.2.
-    `boxes` (optional list) receives (x0, y0, x1, y1) of every rendered line."""
+    `boxes` (optional list) receives (x0, y0, x1, y1) of every rendered line, `lines` (optional list) its
+    (text, x, y, font, scale, thickness)."""
     rng = np.random.default_rng(seed)
     img = out if out is not None else np.empty((height, width, 3), np.uint8)
     img[:] = rng.integers(225, 256, 3, dtype=np.uint8)
@@ -38,6 +39,8 @@ def card(seed: int, width=1024, height=640, out=None, boxes=None):
         color = tuple(int(c) for c in rng.integers(0, 90, 3))
         font, thick = _FONTS[int(rng.integers(0, len(_FONTS)))], int(rng.integers(1, 3))
         cv2.putText(img, text, (x, y), font, scale, color, thick, cv2.LINE_AA)
+        if lines is not None:
+            lines.append((text, x, y, font, scale, thick))
         if boxes is not None:
             (tw, th), base = cv2.getTextSize(text, font, scale, thick)
             boxes.append((x, y - th, min(x + tw, width - 1), y + base // 2))
@@ -47,8 +50,9 @@ def card(seed: int, width=1024, height=640, out=None, boxes=None):
     return img
 
 
-def page(seed: int, size=2048, lines=220):
-    """S-page: 2048x2048, >= 200 lines in 3 columns, widths 80..900 px."""
+def page(seed: int, size=2048, lines=220, info=None):
+    """S-page: 2048x2048, >= 200 lines in 3 columns, widths 80..900 px.  `info` (optional list) receives
+    (text, x, y, font, scale, thickness) of every rendered line."""
     rng = np.random.default_rng(seed)
     img = np.full((size, size, 3), 250, np.uint8)
     cols = [30, 710, 1390]
@@ -58,20 +62,26 @@ def page(seed: int, size=2048, lines=220):
         for _ in range(per):
             scale = float(rng.uniform(0.5, 0.9))
             text = _line(rng, int(rng.integers(1, 7)))
-            cv2.putText(img, text, (cx, y), _FONTS[int(rng.integers(0, len(_FONTS)))], scale, (20, 20, 20), 1, cv2.LINE_AA)
+            font = _FONTS[int(rng.integers(0, len(_FONTS)))]
+            cv2.putText(img, text, (cx, y), font, scale, (20, 20, 20), 1, cv2.LINE_AA)
+            if info is not None:
+                info.append((text, cx, y, font, scale, 1))
             y += int(rng.integers(24, 29))
             if y > size - 10:
                 break
     return img
 
 
-def rec_crops(n: int, height=48, width=320, seed=0):
-    """S-rec: n text-line crops of height x width u8 with rendered text."""
+def rec_crops(n: int, height=48, width=320, seed=0, texts=None):
+    """S-rec: n text-line crops of height x width u8 with rendered text (`texts`: optional list receiving it)."""
     rng = np.random.default_rng(seed)
     out = np.empty((n, height, width, 3), np.uint8)
     for i in range(n):
         out[i] = rng.integers(215, 256, 3, dtype=np.uint8)
-        cv2.putText(out[i], _line(rng, 3), (4, int(height * 0.72)), _FONTS[i % 4], height / 44.0, (10, 10, 10), 2, cv2.LINE_AA)
+        text = _line(rng, 3)
+        cv2.putText(out[i], text, (4, int(height * 0.72)), _FONTS[i % 4], height / 44.0, (10, 10, 10), 2, cv2.LINE_AA)
+        if texts is not None:
+            texts.append(text)
     return out
 
 
