@@ -1,15 +1,23 @@
-"""Headline benchmark: OCR images/s for the full det -> cls -> rec path (BASELINE.json metric, config 4:
-synthetic 1024x640 card images), one process per GPU, images sharded across ranks, no collective on the data path.
+"""Headline benchmark: OCR images/s of the det -> cls -> rec path (BASELINE.json metric), one process per GPU, inputs
+sharded across ranks, no collective on the data path.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (through the C ABI)
-    python bench.py --impl reference ...                      # the reference's CPU path, restated (oracle/), on host cores
+    python bench.py --gpus N --steps K --warmup W [--config c4|c2|c3|c5]    # this repo's CUDA path (through the C ABI)
+    python bench.py --impl reference ...                                     # the reference's CPU path, restated (oracle/)
 
-A step = one pass of the hot path over one batch of `--batch` images per GPU.
-  value : images/s with the batch already resident in HBM (b200ocr_worker_process_resident), CUDA events on the
-          worker's stream around the K timed steps, max over ranks.
-  e2e   : images/s through b200ocr_worker_process_batch with PINNED HOST buffers: H2D of the images and D2H of the
-          boxes / decoded ids inside the timed region.
-Prints ONE JSON line (rank 0).
+--config (BASELINE.json `configs`; default c4 = the configuration the metric is quoted on):
+  c4  full det->cls->rec on synthetic 1024x640 card images, worker defaults          (64 images / GPU / step)
+  c2  recognition-only: 48x320 text-line crops through CRNN/SVTR + CTC greedy decode  (4096 crops / GPU / step)
+  c3  detection-only: cards at limit_side_len 960 -> [*,3,608,960] DB forward + DBPostProcess (64 images / GPU / step)
+  c5  dense 2048x2048 pages (200+ lines) through det(960)->cls->rec                   (8 pages / GPU / step)
+
+A step = one pass of the hot path over one batch of inputs per GPU.
+  value : units/s with the batch already resident in HBM (b200ocr_*_resident calls), CUDA events on the first
+          handle's stream around the K timed steps, max over ranks.
+  e2e   : units/s through the reference-facing call with PINNED HOST buffers: H2D of the inputs and D2H of the boxes /
+          decoded ids inside the timed region.
+Inputs: by default every warm-up and timed step gets inputs NO earlier step has seen (so per-shape plan / CUDA-graph
+caches are only as warm as they would be on a real stream); --recycle rotates 4 pre-seen batches instead (round-1
+behaviour; the delta is recorded in profiles/).  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 import argparse
@@ -27,7 +35,20 @@ for p in (ROOT, os.path.join(ROOT, "cpp-paddle-ocr_b200"), os.path.join(ROOT, "t
 
 METRIC = "OCR images/sec (det+cls+rec)"
 UNIT = "images/s"
-WORKLOAD = "C4: full det->cls->rec on synthetic 1024x640 card images (cv2.putText, 8-12 lines each), worker defaults"
+WEIGHTS = "cls: shipped; det, rec: synthetic-trained on this repo's generators (reference det/rec weights absent)"
+CONFIGS = {
+    "c4": dict(workload="C4: full det->cls->rec on synthetic 1024x640 card images (cv2.putText, 8-12 lines each), worker defaults",
+               batch=64, unit_name="images", cpu_sample=24, ref_per_step=16),
+    "c2": dict(workload="C2: recognition-only, synthetic 48x320 text-line crops through CRNN/SVTR forward + CTC greedy decode "
+                        "(CRNNRecognizer::Run, rec_batch_num 6)",
+               batch=4096, unit_name="crops", cpu_sample=192, ref_per_step=128),
+    "c3": dict(workload="C3: detection-only, synthetic 1024x640 cards at limit_side_len 960 ([n,3,608,960]) through DB forward + "
+                        "DBPostProcess (DBDetector::Run: threshold, contours, box score, unclip)",
+               batch=64, unit_name="images", cpu_sample=24, ref_per_step=16),
+    "c5": dict(workload="C5: dense synthetic 2048x2048 pages with 200+ text lines each through det(limit 960)->cls->rec "
+                        "(variable-width rec packing)",
+               batch=8, unit_name="pages", cpu_sample=8, ref_per_step=8),
+}
 
 
 def peaks():
@@ -74,57 +95,82 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_cards(n, seed0, pinned):
+# ---------------------------------------------------------------------------------------------- synthetic inputs
+def make_inputs(cfg, n, seed0, pinned):
+    """n inputs of configuration `cfg` as one array [n, H, W, 3] (pinned host memory when asked)."""
     import numpy as np
     import synth_data
-    import b200ocr
-    arr = b200ocr.pinned_array((n, 640, 1024, 3)) if pinned else np.empty((n, 640, 1024, 3), np.uint8)
-    for i in range(n):
-        synth_data.card(seed0 + i, out=arr[i])
+    shape = {"c4": (640, 1024), "c3": (640, 1024), "c2": (48, 320), "c5": (2048, 2048)}[cfg]
+    if pinned:
+        import b200ocr
+        arr = b200ocr.pinned_array((n,) + shape + (3,))
+    else:
+        arr = np.empty((n,) + shape + (3,), np.uint8)
+    if cfg == "c2":
+        arr[:] = synth_data.rec_crops(n, 48, 320, seed=seed0)
+    elif cfg == "c5":
+        for i in range(n):
+            arr[i] = synth_data.page(seed0 + i)
+    else:
+        for i in range(n):
+            synth_data.card(seed0 + i, out=arr[i])
     return arr
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
-def _ref_worker_init(models, enable_cls, threads):
-    global _W
+def _ref_worker_init(models, cfg, threads):
+    global _W, _CFG
     import torch
     torch.set_num_threads(threads)
     import cv2
     cv2.setNumThreads(1)
-    from oracle.pipeline import OracleWorker
-    _W = OracleWorker(os.getpid() % 1000, models, enable_cls=enable_cls)
+    from oracle.pipeline import OracleDetector, OracleRecognizer, OracleWorker
+    _CFG = cfg
+    if cfg == "c2":
+        _W = OracleRecognizer(os.path.join(models, "rec"), os.path.join(models, "rec", "ppocr_keys_v1.txt"), 6, 48, 320)
+    elif cfg == "c3":
+        _W = OracleDetector(os.path.join(models, "det"), "max", 960, 0.3, 0.5, 2.0, "fast", False)
+    else:
+        _W = OracleWorker(os.getpid() % 1000, models, enable_cls=True, limit_side_len=960 if cfg == "c5" else 512)
 
 
 def _ref_worker_run(seed):
-    import synth_data
+    """One unit of work for one pool worker: an image (c3/c4/c5) or one CRNNRecognizer::Run call of 6 crops (c2)."""
     t0 = time.perf_counter()
-    line = _W.process(seed, synth_data.card(seed))
-    return time.perf_counter() - t0, line.count('"text"')
+    if _CFG == "c2":
+        crops = make_inputs("c2", 6, seed, False)
+        texts, _ = _W.run(list(crops))
+        return time.perf_counter() - t0, sum(1 for t in texts if t), 6
+    img = make_inputs(_CFG, 1, seed, False)[0]
+    n = len(_W.run(img)) if _CFG == "c3" else _W.process(seed, img).count('"text"')
+    return time.perf_counter() - t0, n, 1
 
 
-def cpu_reference(models, n_images, seed0, enable_cls=True, workers=None, steps=1, warmup_steps=0):
+def cpu_reference(models, cfg, n_units, seed0, workers=None, steps=1, warmup_steps=0):
     """The reference's cpu_worker_pool arrangement (src/cpu_worker_pool.cpp, src/ocr_worker.cpp:16-18): W worker
     processes with private det/cls/rec instances, 2 intra-op threads each, fed from one queue.  The pool is created and
     warmed once (model load and first-call costs stay outside the timed steps, as they do for the GPU arm)."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     workers = workers or max(1, cores // 2)
+    per_task = 6 if cfg == "c2" else 1
+    tasks = max(1, n_units // per_task)
     ctx = mp.get_context("spawn")
     runs = []
-    with ctx.Pool(workers, initializer=_ref_worker_init, initargs=(models, enable_cls, 2)) as pool:
-        pool.map(_ref_worker_run, [seed0 - 1 - k for k in range(workers)], chunksize=1)
+    with ctx.Pool(workers, initializer=_ref_worker_init, initargs=(models, cfg, 2)) as pool:
+        pool.map(_ref_worker_run, [seed0 - 100 * (k + 1) for k in range(workers)], chunksize=1)
         for s in range(warmup_steps + steps):
             t0 = time.perf_counter()
-            res = pool.map(_ref_worker_run, [seed0 + s * n_images + i for i in range(n_images)], chunksize=1)
+            res = pool.map(_ref_worker_run, [seed0 + (s * tasks + i) * 10 for i in range(tasks)], chunksize=1)
             dt = time.perf_counter() - t0
             if s >= warmup_steps:
                 runs.append((dt, res))
     total_s = sum(dt for dt, _ in runs)
     lat = sorted(r[0] for _, res in runs for r in res)
-    n_total = n_images * len(runs)
+    n_total = sum(r[2] for _, res in runs for r in res)
     return {"value": n_total / total_s, "seconds": total_s, "seconds_per_step": total_s / len(runs), "workers": workers,
-            "threads": workers * 2, "cores": cores, "p50_ms": lat[len(lat) // 2] * 1e3,
-            "words_per_image": sum(r[1] for _, res in runs for r in res) / n_total}
+            "threads": workers * 2, "cores": cores, "p50_ms": lat[len(lat) // 2] * 1e3, "units": n_total,
+            "words_per_unit": sum(r[1] for _, res in runs for r in res) / n_total}
 
 
 def run_reference(args):
@@ -133,15 +179,17 @@ def run_reference(args):
         return
     import make_synth_weights
     models = make_synth_weights.ensure_models()
-    per_step = args.ref_images
-    r = cpu_reference(models, per_step, 5000, True, steps=args.steps, warmup_steps=args.warmup)
+    C = CONFIGS[args.config]
+    per_step = args.ref_units or C["ref_per_step"]
+    r = cpu_reference(models, args.config, per_step, 5000, steps=args.steps, warmup_steps=args.warmup)
     value = r["value"]
-    sample = f"{per_step} S-card images per step x {args.steps} steps, {r['workers']} workers x 2 threads (cpu_worker_pool layout)"
+    sample = (f"{r['units'] // args.steps} {C['unit_name']} per step x {args.steps} steps, {r['workers']} workers x 2 threads "
+              f"(cpu_worker_pool layout)")
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "images_per_step": per_step, "enable_cls": True,
-                      "weights": "cls: shipped; det: synthetic-trained; rec: seeded random (reference det/rec weights absent)",
+           "config": {"workload": C["workload"], "units": C["unit_name"], "units_per_step": r["units"] // args.steps, "enable_cls": True,
+                      "weights": WEIGHTS,
                       "note": "reference CPU path restated (torch-CPU fp32 graphs + cv2 + reference Clipper); Paddle Inference itself is not installable here"},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": sample,
                             "p50_ms": r["p50_ms"], "host_cores": r["cores"]},
@@ -151,6 +199,46 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------- this repo's arm
+class Arm:
+    """One configuration: how a handle (worker / stage) is built and how it runs a share of a step's batch."""
+
+    def __init__(self, cfg, models, local, n_handles, rank):
+        import b200ocr
+        self.cfg = cfg
+        label = f"{models}/rec/ppocr_keys_v1.txt"
+        if cfg == "c4":
+            self.handles = [b200ocr.Worker(rank * 8 + k, models, gpu_id=local, enable_cls=True) for k in range(n_handles)]
+        elif cfg == "c5":
+            self.handles = [b200ocr.Worker(rank * 8 + k, models, gpu_id=local, enable_cls=True, limit_side_len=960)
+                            for k in range(n_handles)]
+        elif cfg == "c2":
+            self.handles = [b200ocr.Recognizer(f"{models}/rec", label, gpu_id=local, rec_batch_num=6, rec_img_h=48, rec_img_w=320)
+                            for _ in range(n_handles)]
+        else:
+            self.handles = [b200ocr.Detector(f"{models}/det", gpu_id=local, limit_type="max", limit_side_len=960,
+                                             det_db_thresh=0.3, det_db_box_thresh=0.5, det_db_unclip_ratio=2.0,
+                                             det_db_score_mode="fast") for _ in range(n_handles)]
+
+    def launches(self):
+        return sum(int(h.launches) for h in self.handles)
+
+    def run_resident(self, k, ids, dev_batch):
+        h = self.handles[k]
+        if self.cfg in ("c4", "c5"):
+            return sum(o.count('"text"') for o in h.process_resident(ids, dev_batch))
+        if self.cfg == "c2":
+            return sum(1 for t in h.run_resident(dev_batch)[0] if t)
+        return sum(len(b) for b in h.run_resident(dev_batch))
+
+    def run_host(self, k, ids, prepared):
+        h = self.handles[k]
+        if self.cfg in ("c4", "c5"):
+            return sum(o.count('"text"') for o in h.process_batch(ids, prepared))
+        if self.cfg == "c2":
+            return sum(1 for t in h.run(prepared)[0] if t)
+        return sum(len(b) for b in h.run_batch(prepared))
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -175,10 +263,12 @@ def run_ours(args):
         dist.barrier()
     models = make_synth_weights.ensure_models()
 
-    B, K, W = args.batch, args.steps, args.warmup
-    # Every worker is a host thread that spins on its stream between launches: more workers than host cores per GPU
-    # cost more than they hide.  Measured on one B200 with 16 host cores: 1 / 2 / 3 / 4 workers = 4928 / 5425 / 5676 /
-    # 5595 images/s; at 8 GPUs the same 16 cores leave two per GPU.
+    cfg = args.config
+    C = CONFIGS[cfg]
+    B, K, W = (args.batch or C["batch"]), args.steps, args.warmup
+    # Every handle is a host thread that waits on its stream between launches: more handles than host cores per GPU
+    # cost more than they hide.  Measured on one B200 with 16 host cores (C4): 1 / 2 / 3 / 4 workers = 4928 / 5425 /
+    # 5676 / 5595 images/s; at 8 GPUs the same 16 cores leave two per GPU.
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
@@ -186,21 +276,34 @@ def run_ours(args):
     auto = min(3, max(1, cores // max(1, world)))
     NW = args.workers if args.workers > 0 else auto
     NWH = args.e2e_workers if args.e2e_workers > 0 else auto
-    # Several workers per GPU (own stream + networks each, like the reference pool's workers), every one fed its share
+    NW, NWH = min(NW, B), min(NWH, B)
+    # Several handles per GPU (own stream + networks each, like the reference pool's workers), every one fed its share
     # of the step's batch from its own thread: while one waits on the host between its two sync points, the others keep
-    # the GPU busy.  Results per image are identical to a single worker's.  The device-resident measurement uses NW
-    # workers; the host-buffer (e2e) measurement uses NWH (one more hides the H2D upload of a share behind the compute
-    # of the others).
-    workers = [b200ocr.Worker(rank * 8 + k, models, gpu_id=local, enable_cls=True) for k in range(max(NW, NWH))]
-    worker = workers[0]
-    n_sets = min(K, 4) if K > 0 else 1
-    # distinct images per rank and per set; each set is B x 1.97 MB (>= L2 at B = 64), sets rotate between steps
-    host_sets = [make_cards(B, sharding.card_seed(rank, s, 0), pinned=True) for s in range(n_sets)]
-    host_parts = [[list(h[k::NWH]) for k in range(NWH)] for h in host_sets]
-    dev_parts = [[b200ocr.DeviceBatch(list(h[k::NW]), device=local) for k in range(NW)] for h in host_sets]
+    # the GPU busy.  Results per unit are identical to a single handle's.
+    arm = Arm(cfg, models, local, max(NW, NWH), rank)
+    first = arm.handles[0]
+
+    # ---- inputs.  distinct (default): 2 priming batches + (W + K) batches per measurement, every one rendered from its
+    # own seeds; recycle: 4 batches per measurement, each primed before timing (round-1 behaviour)
+    n_prime = 2
+    n_sets = (W + K) if not args.recycle else min(max(K, 1), 4)
+    set_seed = lambda meas, s: sharding.card_seed(rank, 0, 0) + 100_003 * meas + 5_000 * s   # noqa: E731
+    t_gen = time.perf_counter()
+    prime_sets = [make_inputs(cfg, B, set_seed(2, s), pinned=True) for s in range(n_prime)]
+    res_sets = [make_inputs(cfg, B, set_seed(0, s), pinned=True) for s in range(n_sets)]
+    host_sets = [make_inputs(cfg, B, set_seed(1, s), pinned=True) for s in range(n_sets)]
+    gen_s = time.perf_counter() - t_gen
+
+    def split(arr, nw):
+        return [list(arr[k::nw]) for k in range(nw)]
+
+    dev_parts = [[b200ocr.DeviceBatch(part, device=local) for part in split(h, NW)] for h in res_sets]
+    prime_dev = [[b200ocr.DeviceBatch(part, device=local) for part in split(h, NW)] for h in prime_sets]
+    host_parts = [[b200ocr.prepare_images(part) for part in split(h, NWH)] for h in host_sets]
+    prime_host = [[b200ocr.prepare_images(part) for part in split(h, NWH)] for h in prime_sets]
     ids_dev = [list(range(k, B, NW)) for k in range(NW)]
     ids_host = [list(range(k, B, NWH)) for k in range(NWH)]
-    stream = torch.cuda.ExternalStream(worker.stream, device=torch.device("cuda", local))
+    stream = torch.cuda.ExternalStream(first.stream, device=torch.device("cuda", local))
 
     def barrier():
         torch.cuda.synchronize()
@@ -208,12 +311,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_steps(fn, nw, first, count):
-        """`nw` workers run `count` steps each on their own thread; returns the number of words found"""
+    def run_steps(fn, nw, sets):
+        """`nw` handles run the given step batches, each on its own thread; returns the number of words / boxes found"""
         words = [0] * nw
         def body(k):
-            for s in range(first, first + count):
-                words[k] += fn(k, s)
+            for parts in sets:
+                words[k] += fn(k, parts[k])
         if nw == 1:
             body(0)
         else:
@@ -224,50 +327,53 @@ def run_ours(args):
                 t.join()
         return sum(words)
 
-    def timed(fn, nw):
-        # setup, not warm-up: every distinct input set goes through once so that each worker's activation arenas, CUDA
-        # graphs and pinned staging buffers have reached their final size (growing one means cudaFree + cudaMalloc,
-        # which stalls the whole device) before the W warm-up and K timed steps
-        run_steps(fn, nw, 0, 2 * n_sets)  # twice: the second run of a shape captures its CUDA graph
-        run_steps(fn, nw, 0, W)
+    def timed(fn, nw, prime, sets):
+        # setup, not warm-up: the priming batches go through twice so that every handle's activation arenas and pinned
+        # staging buffers have reached their working size (growing one means cudaFree + cudaMalloc, which stalls the
+        # whole device) and the shapes that do repeat (det) have their CUDA graph
+        run_steps(fn, nw, prime + prime)
+        if args.recycle:
+            run_steps(fn, nw, sets + sets)
+            warm, meas = [sets[s % n_sets] for s in range(W)], [sets[(W + s) % n_sets] for s in range(K)]
+        else:
+            warm, meas = sets[:W], sets[W:W + K]
+        run_steps(fn, nw, warm)
         barrier()
-        l0 = sum(w.launches for w in workers)
+        l0 = arm.launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
-        words = run_steps(fn, nw, W, K)
-        torch.cuda.synchronize()  # every worker has synchronised its own stream by now
+        words = run_steps(fn, nw, meas)
+        torch.cuda.synchronize()  # every handle has synchronised its own stream by now
         e1.record(stream)         # ... so this stamps the end of all work
         barrier()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
-        return sharding.reduce_run(dist, "cuda", ms, wall * 1e3, sum(w.launches for w in workers) - l0, words)
+        return sharding.reduce_run(dist, "cuda", ms, wall * 1e3, arm.launches() - l0, words)
 
-    def step_resident(k, s):
-        out = workers[k].process_resident(ids_dev[k], dev_parts[s % n_sets][k])
-        return sum(o.count('"text"') for o in out)
+    def step_resident(k, part):
+        return arm.run_resident(k, ids_dev[k], part)
 
-    def step_host(k, s):
-        out = workers[k].process_batch(ids_host[k], host_parts[s % n_sets][k])
-        return sum(o.count('"text"') for o in out)
+    def step_host(k, part):
+        return arm.run_host(k, ids_host[k], part)
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_dev, wall_dev, launches, words = timed(step_resident, NW)
+    ms_dev, wall_dev, launches, words = timed(step_resident, NW, prime_dev, dev_parts)
     clocks = sampler.stop() if sampler else None
-    ms_e2e, wall_e2e, _, _ = timed(step_host, NWH)
-    total_images = B * K * world
-    value = total_images / (ms_dev / 1e3)
-    e2e = total_images / (max(ms_e2e, wall_e2e) / 1e3)
+    ms_e2e, wall_e2e, _, _ = timed(step_host, NWH, prime_host, host_parts)
+    total_units = B * K * world
+    value = total_units / (ms_dev / 1e3)
+    e2e = total_units / (max(ms_e2e, wall_e2e) / 1e3)
 
-    # ---- roofline of the dominant kernel.  Every fused layer of the three networks is launched on its own between two
-    # CUDA events on the worker's stream (L2 flushed before each timed launch) at the largest forward pass of the last
-    # step (det: its batch; cls: all crops; rec: the chunk with the most columns -- each runs about once per worker and
+    # ---- roofline of the dominant kernel.  Every fused layer of the networks is launched on its own between two CUDA
+    # events on the handle's stream (L2 flushed before each timed launch) at the largest forward pass of the last step
+    # (det: its batch; cls: all crops; rec: the chunk with the most columns -- each runs about once per handle and
     # step, so the sums are comparable).  "Dominant" = the (network, kernel family) with the largest summed time;
     # achieved = the family's algorithmic bytes (or FLOPs) / its summed launch time.
     roof = None
     if rank == 0 and not args.no_roofline:
         hbm, tf_burst, tf_sust, which = peaks()
-        prof = worker.profile(warmup=2, reps=5)
+        prof = first.profile(warmup=2, reps=5)
         fam = {}
         for net, d in prof.items():
             for r in d["layers"]:
@@ -284,12 +390,6 @@ def run_ours(args):
         else:
             roof = {"bound": "hbm", "achieved": top["bytes"] / sec / 1e9, "peak": hbm, "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
-        roof["traffic"] = None
-        # the timed shape changes with the input, so no ncu capture matches it launch for launch; the captures that exist
-        # (ncu --set full, committed) are named here instead
-        roof["traffic_reference"] = ("profiles/r01_ncu_conv_tc_persist.txt: 240->240 1x1 layer at [160,7,100,240]: dram read "
-                                     "53.9 MB = its algorithmic input (53.8 MB), dram write 5.5 MB of 53.8 MB (the output stays "
-                                     "in the 126 MB L2); profiles/r01_ncu_dwconv_v3_static.txt: 5x5 depthwise, read 53.8 MB")
         names = {"Conv": "conv_tc_persist_kernel / conv_tc_kernel (tcgen05 implicit GEMM)" if tc else "conv_simt / stem kernels",
                  "DwConv": "dwconv_tile_kernel", "CtcHead": "ctc_head_tc_kernel", "Attn": "attention_mma_kernel"}
         roof["kernel"] = f"{net}:{kind}: {names.get(kind, kind)}"
@@ -300,39 +400,60 @@ def run_ours(args):
         roof["algorithmic_flops_per_launch"] = top["flops"] / top["n"]
         roof["arithmetic_intensity_flop_per_byte"] = ai
         roof["timed_shape"] = prof[net]["shape"]
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same family at the same shape, from a committed
+        # `ncu --set full` capture of this command (profiles/r02_traffic.json: {"<config>": {"kernel", "shape", "traffic"}})
+        roof["traffic"] = None
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if os.path.exists(tpath):
+            t = json.load(open(tpath)).get(cfg)
+            if t and t.get("family") == f"{net}:{kind}" and list(t.get("shape", [])) == list(prof[net]["shape"]):
+                roof["traffic"] = t["traffic_bytes_per_launch"]
+                roof["traffic_source"] = t.get("source")
+            elif t:
+                roof["traffic_note"] = (f"capture in {t.get('source')} is for {t.get('family')} at {t.get('shape')}: "
+                                        f"{t.get('traffic_bytes_per_launch')} B per launch")
         t = top["top"]
         roof["slowest_layer"] = {"name": t["name"], "us": t["ms"] * 1e3, "GB/s": t["bytes"] / t["ms"] / 1e6,
                                  "TFLOP/s": t["flops"] / t["ms"] / 1e9}
         roof["net_ms_at_timed_shape"] = {n: sum(r["ms"] for r in d["layers"]) for n, d in prof.items()}
         roof["family_share_of_net"] = top["ms"] / roof["net_ms_at_timed_shape"][net]
 
-    # p50 latency of ONE image through the reference-facing call (b200ocr_worker_process: host image in, JSON out)
+    # p50 latency of ONE unit through the reference-facing call (host input in, result out)
     lat = []
-    for i in range(0 if args.no_latency else 40):
+    single = [b200ocr.prepare_images([host_sets[0][i % B]] if cfg != "c2" else list(host_sets[0][(i * 6) % B:(i * 6) % B + 6]))
+              for i in range(0 if args.no_latency else 40)]
+    for i, prep in enumerate(single):
         t0 = time.perf_counter()
-        worker.process(i, host_sets[0][i % B])
+        arm.run_host(0, [i] * len(prep), prep)
         lat.append((time.perf_counter() - t0) * 1e3)
     lat = sorted(lat[8:])
     p50_single = lat[len(lat) // 2] if lat else None
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        r = cpu_reference(models, args.cpu_images, 7000, True, steps=1, warmup_steps=0)
+        n_cpu = args.cpu_units or C["cpu_sample"]
+        r = cpu_reference(models, cfg, n_cpu, 7000, steps=1, warmup_steps=0)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
-               "sample": f"{args.cpu_images} S-card images of the same generator through the restated reference CPU path "
+               "sample": f"{r['units']} {C['unit_name']} of the same generator through the restated reference CPU path "
                          f"(oracle/: torch-CPU fp32 + cv2 + reference Clipper), {r['workers']} workers x 2 threads",
-               "p50_ms": r["p50_ms"], "host_cores": r["cores"], "words_per_image": r["words_per_image"]}
+               "p50_ms": r["p50_ms"], "host_cores": r["cores"], "words_per_unit": r["words_per_unit"]}
 
     if rank == 0:
-        bytes_in = B * 640 * 1024 * 3
+        bytes_in = int(res_sets[0].nbytes)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
                "data": "synthetic",
-               "config": {"workload": WORKLOAD, "images_per_gpu_per_step": B, "workers_per_gpu": NW, "workers_per_gpu_e2e": NWH, "enable_cls": True,
-                          "words_per_image": words / max(1, total_images),
-                          "weights": "cls: shipped; det: synthetic-trained; rec: seeded random (reference det/rec weights absent)",
-                          "prime_passes": 2 * n_sets, "l2": f"inputs rotate through {n_sets} distinct batches of {bytes_in / 1e6:.0f} MB each (>= L2)",
-                          "p50_latency_ms_per_batch": ms_dev / K, "p50_latency_ms_single_image": p50_single},
+               "config": {"workload": C["workload"], "name": cfg, "units": C["unit_name"], "units_per_gpu_per_step": B,
+                          "workers_per_gpu": NW, "workers_per_gpu_e2e": NWH, "enable_cls": True,
+                          "words_per_unit": words / max(1, total_units), "weights": WEIGHTS,
+                          "inputs": ("recycled: 4 batches, each seen before timing" if args.recycle else
+                                     f"distinct: every warm-up / timed step renders {B} inputs no earlier step has seen "
+                                     f"({(n_prime + 2 * n_sets) * B} per rank, {gen_s:.1f} s to render)"),
+                          "l2": f"every step's batch is {bytes_in / 1e6:.0f} MB of u8 pixels"
+                                + (" (>= the 126 MB L2)" if bytes_in >= 126e6 else "; activations written between two reads of "
+                                   "any buffer exceed the 126 MB L2"),
+                          "p50_latency_ms_per_batch": ms_dev / K,
+                          "p50_latency_ms_single": p50_single},
                "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": bytes_in,
                        "d2h_bytes_per_step": int(words / max(1, K * world) * (24 * 8 + 8) + B * 4), "ms_per_step": ms_e2e / K},
@@ -348,17 +469,19 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="units per GPU per step; 0 = the configuration's default")
+    ap.add_argument("--recycle", action="store_true", help="rotate 4 pre-seen batches instead of distinct inputs per step")
     ap.add_argument("--workers", type=int, default=0,
-                    help="workers (streams) per GPU sharing a step's batch; 0 = min(3, host cores // GPUs)")
+                    help="handles (streams) per GPU sharing a step's batch; 0 = min(3, host cores // GPUs)")
     ap.add_argument("--e2e-workers", type=int, default=0,
-                    help="workers per GPU in the host-buffer (e2e) measurement; 0 = same rule")
+                    help="handles per GPU in the host-buffer (e2e) measurement; 0 = same rule")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-images", type=int, default=24, help="size of the cpu_baseline sample")
-    ap.add_argument("--ref-images", type=int, default=16, help="images per step of the reference arm")
+    ap.add_argument("--cpu-units", type=int, default=0, help="size of the cpu_baseline sample; 0 = the configuration's default")
+    ap.add_argument("--ref-units", type=int, default=0, help="units per step of the reference arm; 0 = the configuration's default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-layer profile pass (clean ncu launch lists)")
-    ap.add_argument("--no-latency", action="store_true", help="skip the single-image latency loop (clean ncu launch lists)")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-unit latency loop (clean ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

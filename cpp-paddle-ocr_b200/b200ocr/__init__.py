@@ -216,9 +216,25 @@ def as_image(a: np.ndarray) -> Image:
     return Image(a.ctypes.data, a.shape[0], a.shape[1], a.strides[0])
 
 
+class Prepared:
+    """A list of images already turned into the C ABI's b200ocr_image array (prepare_images): passing it instead of
+    the list keeps the per-call Python cost out of a timed loop."""
+
+    def __init__(self, arrs):
+        self.keep = [a if (a is None or a.size == 0 or a.strides[1:] == (3, 1)) else np.ascontiguousarray(a) for a in arrs]
+        self.arr = (Image * len(self.keep))(*[as_image(a) for a in self.keep])
+
+    def __len__(self):
+        return len(self.keep)
+
+
+def prepare_images(arrs) -> Prepared:
+    return arrs if isinstance(arrs, Prepared) else Prepared(arrs)
+
+
 def _images(arrs):
-    keep = [a if (a is None or a.size == 0 or a.strides[1:] == (3, 1)) else np.ascontiguousarray(a) for a in arrs]
-    return (Image * len(keep))(*[as_image(a) for a in keep]), keep
+    p = prepare_images(arrs)
+    return p.arr, p.keep
 
 
 def pinned_array(shape, dtype=np.uint8) -> np.ndarray:
@@ -333,13 +349,32 @@ class Recognizer(_Handle):
         return [_take_string(C.c_void_p(t)) for t in texts], scores
 
 
+class WorkerParams(C.Structure):
+    _fields_ = [("limit_type", C.c_char_p), ("limit_side_len", C.c_int), ("det_db_thresh", C.c_double),
+                ("det_db_box_thresh", C.c_double), ("det_db_unclip_ratio", C.c_double), ("det_db_score_mode", C.c_char_p),
+                ("use_dilation", C.c_int), ("cls_batch_num", C.c_int), ("rec_batch_num", C.c_int), ("rec_img_h", C.c_int),
+                ("rec_img_w", C.c_int), ("max_batch", C.c_int)]
+
+
+_sig("b200ocr_worker_create_ex", C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, _P(WorkerParams), _P(C.c_void_p))
+
+
 class Worker(_Handle):
     """OCRWorker::processRequest + result JSON (reference src/ocr_worker.cpp:133-311)."""
     _destroy = staticmethod(lib.b200ocr_worker_destroy)
 
-    def __init__(self, worker_id, model_dir, gpu_id=0, enable_cls=False):
+    def __init__(self, worker_id, model_dir, gpu_id=0, enable_cls=False, **params):
+        """`params`: b200ocr_worker_params overrides (limit_side_len=960, rec_img_h=48, ...); none = the reference's."""
         self._h = C.c_void_p()
-        check(lib.b200ocr_worker_create(worker_id, model_dir.encode(), 1, gpu_id, int(enable_cls), C.byref(self._h)))
+        if not params:
+            check(lib.b200ocr_worker_create(worker_id, model_dir.encode(), 1, gpu_id, int(enable_cls), C.byref(self._h)))
+            return
+        wp = WorkerParams()
+        for k, v in params.items():
+            if k not in {f[0] for f in WorkerParams._fields_}:
+                raise TypeError(f"unknown worker parameter {k}")
+            setattr(wp, k, v.encode() if isinstance(v, str) else v)
+        check(lib.b200ocr_worker_create_ex(worker_id, model_dir.encode(), gpu_id, int(enable_cls), C.byref(wp), C.byref(self._h)))
 
     def process(self, request_id, img) -> str:
         arr, keep = _images([img])
@@ -427,6 +462,65 @@ class DeviceBatch(_Handle):
         self.n = len(imgs)
         self._h = C.c_void_p()
         check(lib.b200ocr_batch_upload(device, arr, self.n, C.byref(self._h)))
+
+
+_sig("b200ocr_det_run_resident", C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, _P(C.c_double))
+_sig("b200ocr_rec_run_resident", C.c_int, C.c_void_p, C.c_void_p, _P(C.c_void_p), C.c_void_p, _P(C.c_double))
+_sig("b200ocr_det_stream", C.c_void_p, C.c_void_p)
+_sig("b200ocr_rec_stream", C.c_void_p, C.c_void_p)
+_sig("b200ocr_det_launches", C.c_longlong, C.c_void_p)
+_sig("b200ocr_rec_launches", C.c_longlong, C.c_void_p)
+_sig("b200ocr_pool_wait_for", C.c_int, C.c_void_p, C.c_longlong, C.c_int, _P(C.c_void_p))
+
+
+def _det_run_resident(self, batch: DeviceBatch, cap=1000):
+    boxes = np.zeros((batch.n, cap, 4, 2), np.int32)
+    counts = np.zeros(batch.n, np.int32)
+    times = (C.c_double * 3)()
+    check(lib.b200ocr_det_run_resident(self._h, batch._h, boxes.ctypes.data, cap, counts.ctypes.data, times))
+    self.times = list(times)
+    return [boxes[i, :min(int(counts[i]), cap)].copy() for i in range(batch.n)]
+
+
+def _rec_run_resident(self, batch: DeviceBatch):
+    texts = (C.c_void_p * batch.n)()
+    scores = np.zeros(batch.n, np.float32)
+    times = (C.c_double * 3)()
+    check(lib.b200ocr_rec_run_resident(self._h, batch._h, texts, scores.ctypes.data, times))
+    self.times = list(times)
+    return [_take_string(C.c_void_p(t)) for t in texts], scores
+
+
+_sig("b200ocr_det_profile", C.c_int, C.c_void_p, C.c_int, C.c_int, _P(C.c_void_p))
+_sig("b200ocr_rec_profile", C.c_int, C.c_void_p, C.c_int, C.c_int, _P(C.c_void_p))
+
+
+def _stage_profile(fn):
+    def profile(self, warmup=2, reps=5):
+        p = C.c_void_p()
+        check(fn(self._h, warmup, reps, C.byref(p)))
+        return json.loads(_take_string(p))
+    return profile
+
+
+Detector.profile = _stage_profile(lib.b200ocr_det_profile)
+Recognizer.profile = _stage_profile(lib.b200ocr_rec_profile)
+Detector.run_resident = _det_run_resident
+Recognizer.run_resident = _rec_run_resident
+Detector.stream = property(lambda self: lib.b200ocr_det_stream(self._h))
+Recognizer.stream = property(lambda self: lib.b200ocr_rec_stream(self._h))
+Detector.launches = property(lambda self: int(lib.b200ocr_det_launches(self._h)))
+Recognizer.launches = property(lambda self: int(lib.b200ocr_rec_launches(self._h)))
+
+
+def _pool_wait_for(self, ticket, timeout_ms):
+    """None when the time limit elapsed first (the ticket stays valid)."""
+    p = C.c_void_p()
+    check(lib.b200ocr_pool_wait_for(self._h, ticket, int(timeout_ms), C.byref(p)))
+    return _take_string(p) if p.value else None
+
+
+Pool.wait_for = _pool_wait_for
 
 
 def _worker_process_resident(self, request_ids, batch: DeviceBatch):
@@ -530,3 +624,25 @@ def kernel_conv(x, filt, bias, act=0, post_scale=1.0, post_shift=0.0, residual=N
                                   post_scale, post_shift, None if res is None else res.ctypes.data,
                                   None if wd is None else wd.ctypes.data, int(force_simt), out.ctypes.data))
     return out
+
+
+_sig("b200ocr_kernel_ctc_head", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+
+
+def kernel_ctc_head(feat, w, bias, force_simt=False, device=0):
+    """feat [n,t,cin], w [cin,ncls], bias [ncls] -> (idx [n,t], prob [n,t], collapsed ids per row, scores [n])."""
+    feat = np.ascontiguousarray(feat, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    bias = np.ascontiguousarray(bias, np.float32)
+    n, t, cin = feat.shape
+    assert w.shape[0] == cin and bias.shape[0] == w.shape[1]
+    idx = np.empty((n, t), np.int32)
+    prob = np.empty((n, t), np.float32)
+    col = np.empty((n, t), np.int32)
+    lens = np.empty(n, np.int32)
+    scores = np.empty(n, np.float32)
+    check(lib.b200ocr_kernel_ctc_head(device, feat.ctypes.data, n, t, cin, w.ctypes.data, bias.ctypes.data, w.shape[1],
+                                      1 if force_simt else 0, idx.ctypes.data, prob.ctypes.data, col.ctypes.data,
+                                      lens.ctypes.data, scores.ctypes.data))
+    return idx, prob, [col[i, :lens[i]].copy() for i in range(n)], scores

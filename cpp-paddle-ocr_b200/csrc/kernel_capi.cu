@@ -173,4 +173,50 @@ int b200ocr_kernel_conv(int device, const float* x, int n, int cin, int h, int w
   });
 }
 
+int b200ocr_kernel_ctc_head(int device, const float* feat, int n, int t, int cin, const float* w, const float* bias,
+                            int ncls, int force_simt, int32_t* idx, float* prob, int32_t* collapsed, int32_t* lens,
+                            float* scores) {
+  return capi_guard([&] {
+    if (!feat || !w || !bias || !idx || !prob || n < 1 || t < 1 || cin < 1 || ncls < 2) throw std::invalid_argument("bad argument");
+    cuda_check(cudaSetDevice(device), "cudaSetDevice");
+    // exactly what plan.cpp builds for the rec head: fp16 [ncls_pad16][cin_pad64] K-major rows, padded classes biased
+    // to -30000, and the same bias pre-multiplied by log2(e) for the tcgen05 kernel
+    const int pitch = round_up(cin, 8), cin_pad = round_up(cin, 64), ncls_pad = round_up(ncls, 16);
+    std::vector<uint16_t> hf(size_t(n) * t * pitch, 0);
+    for (size_t r = 0; r < size_t(n) * t; ++r)
+      for (int c = 0; c < cin; ++c) hf[r * pitch + c] = f32_to_f16_bits(feat[r * cin + c]);
+    std::vector<uint16_t> hw(size_t(ncls_pad) * cin_pad, 0);
+    for (int co = 0; co < ncls; ++co)
+      for (int ci = 0; ci < cin; ++ci) hw[size_t(co) * cin_pad + ci] = f32_to_f16_bits(w[size_t(ci) * ncls + co]);
+    std::vector<float> hb(ncls_pad, -30000.f), hb2(ncls_pad);
+    for (int co = 0; co < ncls; ++co) hb[co] = bias[co];
+    for (int co = 0; co < ncls_pad; ++co) hb2[co] = hb[co] * 1.4426950408889634f;
+    const size_t rows = size_t(n) * t;
+    DevMem df(hf.size() * 2), dw(hw.size() * 2), db(hb.size() * 4), db2(hb2.size() * 4), di(rows * 4), dp(rows * 4),
+        dc(rows * 4), dl(size_t(n) * 4), ds(size_t(n) * 4);
+    cuda_check(cudaMemcpy(df.p, hf.data(), hf.size() * 2, cudaMemcpyHostToDevice), "upload");
+    cuda_check(cudaMemcpy(dw.p, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice), "upload");
+    cuda_check(cudaMemcpy(db.p, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice), "upload");
+    cuda_check(cudaMemcpy(db2.p, hb2.data(), hb2.size() * 4, cudaMemcpyHostToDevice), "upload");
+    cuda_check(cudaMemset(di.p, 0xff, rows * 4), "memset");
+    cuda_check(cudaMemset(dp.p, 0xff, rows * 4), "memset");
+    TV f;
+    f.p = df.as<__half>(); f.n = n; f.h = 1; f.w = t; f.c = cin; f.pitch = pitch;
+    if (!force_simt && ctc_tc_eligible(f, cin_pad))
+      launch_ctc_head_tc(f, dw.as<__half>(), db2.as<float>(), cin_pad, ncls, ncls_pad, di.as<int>(), dp.as<float>(), nullptr);
+    else if (force_simt)
+      launch_ctc_head_simt(f, dw.as<__half>(), db.as<float>(), cin_pad, ncls, ncls_pad, di.as<int>(), dp.as<float>(), nullptr);
+    else
+      throw std::runtime_error("shape not eligible for the tcgen05 CTC head");
+    cuda_check(cudaGetLastError(), "ctc head launch");
+    launch_ctc_collapse(di.as<int>(), dp.as<float>(), n, t, dc.as<int>(), dl.as<int>(), ds.as<float>(), nullptr);
+    cuda_check(cudaDeviceSynchronize(), "ctc head");
+    cuda_check(cudaMemcpy(idx, di.p, rows * 4, cudaMemcpyDeviceToHost), "download");
+    cuda_check(cudaMemcpy(prob, dp.p, rows * 4, cudaMemcpyDeviceToHost), "download");
+    if (collapsed) cuda_check(cudaMemcpy(collapsed, dc.p, rows * 4, cudaMemcpyDeviceToHost), "download");
+    if (lens) cuda_check(cudaMemcpy(lens, dl.p, size_t(n) * 4, cudaMemcpyDeviceToHost), "download");
+    if (scores) cuda_check(cudaMemcpy(scores, ds.p, size_t(n) * 4, cudaMemcpyDeviceToHost), "download");
+  });
+}
+
 }  // extern "C"

@@ -355,6 +355,44 @@ int b200ocr_rec_run(b200ocr_rec_t r, const b200ocr_image* imgs, int n, char** re
   });
 }
 
+// ---- device-resident forms of the stage calls (inputs uploaded once with b200ocr_batch_upload)
+int b200ocr_det_run_resident(b200ocr_det_t d, b200ocr_batch_t batch, int32_t* boxes, int cap, int* counts, double times[3]) {
+  return capi_guard([&] {
+    if (!d || !batch || !counts || (cap > 0 && !boxes)) throw std::invalid_argument("null argument");
+    if (batch->device != d->device) throw std::invalid_argument("batch and detector live on different devices");
+    cuda_check(cudaSetDevice(d->device), "cudaSetDevice");
+    const auto& dev = batch->b.images();
+    std::vector<std::vector<Box>> res;
+    std::vector<double> t;
+    d->st->run(dev, &res, d->stream, &t);
+    for (size_t i = 0; i < dev.size(); ++i) {
+      counts[i] = int(res[i].size());
+      for (int k = 0; k < counts[i] && k < cap; ++k) memcpy(boxes + (i * size_t(cap) + k) * 8, res[i][k].data(), 32);
+    }
+    if (times) for (int k = 0; k < 3; ++k) times[k] = t[k];
+  });
+}
+int b200ocr_rec_run_resident(b200ocr_rec_t r, b200ocr_batch_t batch, char** rec_texts, float* rec_text_scores,
+                             double times[3]) {
+  return capi_guard([&] {
+    if (!r || !batch || !rec_texts || !rec_text_scores) throw std::invalid_argument("null argument");
+    if (batch->device != r->device) throw std::invalid_argument("batch and recognizer live on different devices");
+    cuda_check(cudaSetDevice(r->device), "cudaSetDevice");
+    const auto& dev = batch->b.images();
+    std::vector<std::vector<Roi>> calls(1, full_rois(dev));
+    std::vector<std::vector<std::string>> texts;
+    std::vector<std::vector<float>> scores;
+    std::vector<double> t;
+    r->st->run(dev, calls, &texts, &scores, r->stream, &t);
+    for (size_t i = 0; i < dev.size(); ++i) { rec_texts[i] = dup_string(texts[0][i]); rec_text_scores[i] = scores[0][i]; }
+    if (times) for (int k = 0; k < 3; ++k) times[k] = t[k];
+  });
+}
+void* b200ocr_det_stream(b200ocr_det_t d) { return d ? d->stream : nullptr; }
+void* b200ocr_rec_stream(b200ocr_rec_t r) { return r ? r->stream : nullptr; }
+long long b200ocr_det_launches(b200ocr_det_t d) { return d ? d->st->launches : 0; }
+long long b200ocr_rec_launches(b200ocr_rec_t r) { return r ? r->st->launches : 0; }
+
 // ---- worker
 int b200ocr_worker_create(int worker_id, const char* model_dir, int use_gpu, int gpu_id, int enable_cls,
                           b200ocr_worker_t* out) {
@@ -365,6 +403,34 @@ int b200ocr_worker_create(int worker_id, const char* model_dir, int use_gpu, int
     auto h = std::make_unique<b200ocr_worker>();
     WorkerOptions o;
     o.enable_cls = enable_cls != 0;
+    h->w = std::make_unique<Worker>(worker_id, model_dir, gpu_id, o);
+    *out = h.release();
+  });
+}
+int b200ocr_worker_create_ex(int worker_id, const char* model_dir, int gpu_id, int enable_cls,
+                             const b200ocr_worker_params* p, b200ocr_worker_t* out) {
+  return capi_guard([&] {
+    if (!model_dir || !out) throw std::invalid_argument("null argument");
+    need_device(gpu_id);
+    auto h = std::make_unique<b200ocr_worker>();
+    WorkerOptions o;
+    o.enable_cls = enable_cls != 0;
+    if (p) {
+      if (p->limit_type) o.det_limit_type = p->limit_type;
+      if (o.det_limit_type != "max" && o.det_limit_type != "min") throw std::invalid_argument("limit_type must be max or min");
+      if (p->limit_side_len > 0) o.det_limit_side_len = p->limit_side_len;
+      if (p->det_db_thresh > 0) o.det_db_thresh = p->det_db_thresh;
+      if (p->det_db_box_thresh > 0) o.det_db_box_thresh = p->det_db_box_thresh;
+      if (p->det_db_unclip_ratio > 0) o.det_db_unclip_ratio = p->det_db_unclip_ratio;
+      if (p->det_db_score_mode) o.det_db_score_mode = p->det_db_score_mode;
+      if (o.det_db_score_mode != "fast" && o.det_db_score_mode != "slow") throw std::invalid_argument("det_db_score_mode must be fast or slow");
+      o.use_dilation = p->use_dilation != 0;
+      if (p->cls_batch_num > 0) o.cls_batch_num = p->cls_batch_num;
+      if (p->rec_batch_num > 0) o.rec_batch_num = p->rec_batch_num;
+      if (p->rec_img_h > 0) o.rec_img_h = p->rec_img_h;
+      if (p->rec_img_w > 0) o.rec_img_w = p->rec_img_w;
+      if (p->max_batch > 0) o.max_batch = p->max_batch;
+    }
     h->w = std::make_unique<Worker>(worker_id, model_dir, gpu_id, o);
     *out = h.release();
   });
@@ -434,6 +500,31 @@ int b200ocr_worker_profile(b200ocr_worker_t w, int warmup, int reps, char** json
     if (k.cls()) o += ",\"cls\":" + timed(k.cls()->net(), k.cls()->prof_n, k.cls()->prof_h, k.cls()->prof_w, -1);
     o += ",\"rec\":" + timed(k.rec().net(), k.rec().prof_n, k.rec().prof_h, k.rec().prof_w, -1) + "}";
     *json = dup_string(o);
+  });
+}
+
+// per-layer profile of a stage's network at the largest forward pass of its last run
+static std::string stage_profile(Net& net, int n, int h, int wd, int thresh, cudaStream_t s, int warmup, int reps) {
+  if (n <= 0) throw std::runtime_error("profile before the first run");
+  net.prepare(n, h, wd, nullptr, s);
+  char shape[96];
+  snprintf(shape, sizeof shape, "{\"shape\":[%d,%d,%d],\"layers\":", n, h, wd);
+  return std::string(shape) + profile_json(net, s, warmup, reps, thresh) + "}";
+}
+int b200ocr_det_profile(b200ocr_det_t d, int warmup, int reps, char** json) {
+  return capi_guard([&] {
+    if (!d || !json || reps < 1) throw std::invalid_argument("bad argument");
+    cuda_check(cudaSetDevice(d->device), "cudaSetDevice");
+    *json = dup_string("{\"det\":" + stage_profile(d->st->net(), d->st->prof_n, d->st->prof_h, d->st->prof_w, 51, d->stream,
+                                                    warmup, reps) + "}");
+  });
+}
+int b200ocr_rec_profile(b200ocr_rec_t r, int warmup, int reps, char** json) {
+  return capi_guard([&] {
+    if (!r || !json || reps < 1) throw std::invalid_argument("bad argument");
+    cuda_check(cudaSetDevice(r->device), "cudaSetDevice");
+    *json = dup_string("{\"rec\":" + stage_profile(r->st->net(), r->st->prof_n, r->st->prof_h, r->st->prof_w, -1, r->stream,
+                                                    warmup, reps) + "}");
   });
 }
 

@@ -527,16 +527,17 @@ Worker::Worker(int worker_id, const std::string& model_dir, int device, const Wo
   cuda_check(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate");
   // reference src/ocr_worker.cpp:21-63
   DetParams dp;
-  dp.limit_type = "max";
-  dp.limit_side_len = 512;
-  dp.det_db_thresh = 0.2;
-  dp.det_db_box_thresh = 0.4;
-  dp.det_db_unclip_ratio = 1.8;
-  dp.det_db_score_mode = "fast";
-  dp.use_dilation = false;
+  dp.limit_type = opt.det_limit_type;
+  dp.limit_side_len = opt.det_limit_side_len;
+  dp.det_db_thresh = opt.det_db_thresh;
+  dp.det_db_box_thresh = opt.det_db_box_thresh;
+  dp.det_db_unclip_ratio = opt.det_db_unclip_ratio;
+  dp.det_db_score_mode = opt.det_db_score_mode;
+  dp.use_dilation = opt.use_dilation;
   det_ = std::make_unique<DetStage>(model_dir + "/det", device, dp);
-  if (opt.enable_cls) cls_ = std::make_unique<ClsStage>(model_dir + "/cls", device, 8, 0.98f);
-  rec_ = std::make_unique<RecStage>(model_dir + "/rec", device, model_dir + "/rec/ppocr_keys_v1.txt", 16, 28, 192);
+  if (opt.enable_cls) cls_ = std::make_unique<ClsStage>(model_dir + "/cls", device, opt.cls_batch_num, float(opt.cls_thresh));
+  rec_ = std::make_unique<RecStage>(model_dir + "/rec", device, model_dir + "/rec/ppocr_keys_v1.txt", opt.rec_batch_num,
+                                    opt.rec_img_h, opt.rec_img_w);
   // tuning knobs (launch granularity only; results do not depend on them)
   if (const char* v = getenv("B200OCR_DET_MAX_BATCH")) det_->max_batch = std::max(1, atoi(v));
   if (const char* v = getenv("B200OCR_CLS_MAX_BATCH")) { if (cls_) cls_->max_batch = std::max(1, atoi(v)); }

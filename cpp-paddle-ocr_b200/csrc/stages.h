@@ -148,6 +148,16 @@ struct WordOut { std::string text; float confidence; Box box; };
 struct WorkerOptions {
   bool enable_cls = false;
   int max_batch = 64;  // images processed together by process_batch
+  // Stage hyper-parameters; the defaults are what the reference OCRWorker hard-codes (src/ocr_worker.cpp:21-63).
+  // b200ocr_worker_create_ex overrides them (a dense 2048x2048 page needs limit_side_len 960 to keep its lines legible).
+  std::string det_limit_type = "max";
+  int det_limit_side_len = 512;
+  double det_db_thresh = 0.2, det_db_box_thresh = 0.4, det_db_unclip_ratio = 1.8;
+  std::string det_db_score_mode = "fast";
+  bool use_dilation = false;
+  int cls_batch_num = 8;
+  double cls_thresh = 0.98;
+  int rec_batch_num = 16, rec_img_h = 28, rec_img_w = 192;
 };
 
 // Same hyper-parameters as the reference OCRWorker constructor (src/ocr_worker.cpp:21-63).

@@ -140,6 +140,19 @@ int b200ocr_rec_run(b200ocr_rec_t rec, const b200ocr_image* imgs, int n, char** 
 typedef struct b200ocr_worker* b200ocr_worker_t;
 int b200ocr_worker_create(int worker_id, const char* model_dir, int use_gpu, int gpu_id, int enable_cls,
                           b200ocr_worker_t* out);
+/* The same worker with other stage hyper-parameters than the ones src/ocr_worker.cpp:21-63 hard-codes: fields that are
+ * 0 / NULL keep the reference's value (limit "max" 512, thresh 0.2, box_thresh 0.4, unclip 1.8, "fast", no dilation,
+ * cls batch 8, rec batch 16 at 28x192, 64 images per device batch).  Dense 2048x2048 pages (BASELINE config 5) use
+ * limit_side_len 960: at 512 their text lines shrink to 6 px. */
+typedef struct b200ocr_worker_params {
+  const char* limit_type;
+  int limit_side_len;
+  double det_db_thresh, det_db_box_thresh, det_db_unclip_ratio;
+  const char* det_db_score_mode;
+  int use_dilation, cls_batch_num, rec_batch_num, rec_img_h, rec_img_w, max_batch;
+} b200ocr_worker_params;
+int b200ocr_worker_create_ex(int worker_id, const char* model_dir, int gpu_id, int enable_cls,
+                             const b200ocr_worker_params* params, b200ocr_worker_t* out);
 void b200ocr_worker_destroy(b200ocr_worker_t w);
 int b200ocr_worker_process(b200ocr_worker_t w, int request_id, const b200ocr_image* img, char** json);
 /* Throughput form: n requests through the GPU together (results are per image, identical to n process() calls). */
@@ -155,6 +168,21 @@ int b200ocr_worker_process_resident(b200ocr_worker_t w, b200ocr_batch_t batch, c
 void* b200ocr_worker_stream(b200ocr_worker_t w);
 /* kernels launched by this worker so far */
 long long b200ocr_worker_launches(b200ocr_worker_t w);
+
+/* Stage calls on device-resident inputs (b200ocr_batch_upload; every image of the batch is one input of the call) --
+ * what bench.py's device-resident figures for the detection-only / recognition-only configurations time.  Outputs as
+ * in b200ocr_det_run_batch / b200ocr_rec_run.  The *_stream accessors return the stage's cudaStream_t. */
+int b200ocr_det_run_resident(b200ocr_det_t det, b200ocr_batch_t batch, int32_t* boxes, int cap, int* counts, double times[3]);
+int b200ocr_rec_run_resident(b200ocr_rec_t rec, b200ocr_batch_t batch, char** rec_texts, float* rec_text_scores,
+                             double times[3]);
+void* b200ocr_det_stream(b200ocr_det_t det);
+void* b200ocr_rec_stream(b200ocr_rec_t rec);
+long long b200ocr_det_launches(b200ocr_det_t det);
+long long b200ocr_rec_launches(b200ocr_rec_t rec);
+/* Per-fused-layer device time of the stage's network at the largest forward pass of its last run, in the format of
+ * b200ocr_worker_profile: {"det":{"shape":[n,h,w],"layers":[...]}} / {"rec":{...}}; free with b200ocr_free. */
+int b200ocr_det_profile(b200ocr_det_t det, int warmup, int reps, char** json);
+int b200ocr_rec_profile(b200ocr_rec_t rec, int warmup, int reps, char** json);
 
 /* ------------------------------------------------------------------ per-device worker pool
  * Replaces PaddleOCR::GPUWorkerPool (include/paddle_ocr/gpu_worker_pool.h:14-31, src/gpu_worker_pool.cpp:8-59), which
@@ -258,6 +286,15 @@ int b200ocr_kernel_conv(int device, const float* x, int n, int cin, int h, int w
  * valid (may be NULL): tokens per sequence, keys beyond it are ignored and queries beyond it give zeros. */
 int b200ocr_kernel_attention(int device, const float* qkv, int n, int t, int heads, int head_dim, float scale,
                              const int* valid, float* out);
+/* Recognizer head + greedy decode (reference src/ocr_rec.cpp:97-128) on its own: feat [n][t][cin] (values are rounded to
+ * fp16 like the activations the networks hold), w [cin][ncls] (Paddle linear layout, rounded to fp16), bias [ncls] ->
+ * idx [n][t] arg-max class (first maximum wins), prob [n][t] soft-max probability of that class, then the blank / repeat
+ * collapse: collapsed [n][t] label ids (first lens[i] entries of a row valid), scores [n] mean probability of the kept
+ * steps (0 when nothing is kept).  force_simt = 0: the tcgen05 kernel (error when the shape is not eligible), 1: the
+ * CUDA-core kernel.  collapsed / lens / scores may be NULL. */
+int b200ocr_kernel_ctc_head(int device, const float* feat, int n, int t, int cin, const float* w, const float* bias,
+                            int ncls, int force_simt, int32_t* idx, float* prob, int32_t* collapsed, int32_t* lens,
+                            float* scores);
 
 #ifdef __cplusplus
 }

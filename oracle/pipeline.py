@@ -112,9 +112,10 @@ def result_json(request_id, worker_id, success, width, height, ms, words, error=
 class OracleWorker:
     """Hyper-parameters of the reference OCRWorker constructor (src/ocr_worker.cpp:21-63)."""
 
-    def __init__(self, worker_id, model_dir, enable_cls=False):
+    def __init__(self, worker_id, model_dir, enable_cls=False, limit_side_len=512):
+        """`limit_side_len` other than the reference's 512 = b200ocr_worker_create_ex (dense pages, BASELINE config 5)."""
         self.worker_id = worker_id
-        self.det = OracleDetector(os.path.join(model_dir, "det"), "max", 512, 0.2, 0.4, 1.8, "fast", False)
+        self.det = OracleDetector(os.path.join(model_dir, "det"), "max", limit_side_len, 0.2, 0.4, 1.8, "fast", False)
         self.cls = OracleClassifier(os.path.join(model_dir, "cls"), 8) if enable_cls else None
         self.rec = OracleRecognizer(os.path.join(model_dir, "rec"), os.path.join(model_dir, "rec", "ppocr_keys_v1.txt"),
                                     16, 28, 192)

@@ -31,12 +31,9 @@ def run():
     for g, r in zip(got_boxes, ref_boxes):
         assert np.abs(np.asarray(g) - np.asarray(r)).max() <= 1, (g, r)
     ref_words, raw = oracle.process_words(img, det_boxes=got_boxes, want_raw=True)
-    same = 0
     for w, (t, s, _b), (_idx, mx, second) in zip(res["words"], ref_words, raw):
-        if w["text"] == t:
-            same += 1
-            assert abs(w["confidence"] - s) < 6e-2, (w, s)
-        else:  # fp16 vs fp32: a label may only differ where the oracle's own top-2 gap is tiny (random rec weights)
-            assert (mx - second).min() < 6e-2, (w["text"], t)
-    print(f"smoke ok: {len(got_boxes)} boxes, {same}/{len(ref_words)} lines identical to the oracle, "
+        assert w["text"] == t, (w["text"], t)  # every recognised string identical to the oracle's: N / N or fail
+        # confidence within the 1e-2 contract, except in a line where the oracle itself has a near-tie step
+        assert abs(w["confidence"] - s) < 1e-2 or (mx - second).min() < 1e-2, (w, s)
+    print(f"smoke ok: {len(got_boxes)} boxes, {len(ref_words)}/{len(ref_words)} lines identical to the oracle, "
           f"{worker.launches} kernel launches, {b200ocr.version()}")

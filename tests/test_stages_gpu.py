@@ -2,8 +2,7 @@
 C ABI.  Each stage is compared GIVEN IDENTICAL UPSTREAM DATA (north_star): the oracle's later stages are fed the GPU's
 boxes / crops so that an fp16-vs-fp32 flip in one stage does not hide or fake a mismatch in the next.
 
-Tolerances: probability maps / softmax within 1e-2; boxes within 1 px; decoded label indices identical except where
-the oracle's own top-2 softmax margin is below 1e-2 (fp16 storage, fp32 accumulation vs fp32).
+Tolerances: probability maps / softmax within 1e-2; boxes within 1 px; recognised strings identical.
 """
 import json
 import os
@@ -14,16 +13,22 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-# mean of per-step max-softmax values: each step is within the 1e-2 probability tolerance where the softmax is
-# saturated (real text); the seeded random rec weights put most steps at mid-range probabilities, where a 2e-3
-# relative logit error (fp16 activations through ~55 layers; per-layer error grows smoothly from 4e-4 to 3e-3 of the
-# tensor scale, no single bad layer) moves a probability by up to ~5e-2 (measured: tools/diag_rec_precision.py max
-# 0.028 / p99 0.015 / mean 0.003 on S-rec crops, tools/diag_rec_stage.py max 0.055 on detector crops); about one
-# step in a hundred flips its arg-max, so a line of 25-70 steps differs from the oracle in 30-50 % of the cases --
-# every such line must contain a step whose oracle top-2 gap is inside the tolerance.  det probability maps and the
-# cls softmax (trained / shipped weights) stay within 1e-2.
-SCORE_TOL = 6e-2
-MARGIN_TOL = 6e-2  # a different arg-max is accepted only where the oracle's own top-2 gap is below this
+# Contract (north star): probabilities within 1e-2, recognised strings identical.  The rec weights are fitted to this
+# repository's generators (tools/train_synth_rec.py) so that the soft-max is saturated on the test inputs, as a trained
+# model's is on real text.  What is left of fp16-vs-fp32: an arg-max may differ at a step where the ORACLE's own top-2
+# probabilities are closer than the 1e-2 tolerance (a near tie: either answer is inside the contract); such a step can
+# move a line's confidence (the mean over the emitted steps) by more than 1e-2, so lines containing one are exempt from
+# the confidence check -- never from the string check.
+SCORE_TOL = 1e-2
+MARGIN_TOL = 1e-2
+
+
+def _check_line(text, conf, ref_text, ref_conf, raw):
+    """identical string always; confidence within SCORE_TOL unless the oracle itself has a near-tie step in this line"""
+    assert text == ref_text, (text, ref_text, float((raw[1] - raw[2]).min()))
+    near_tie = bool(((raw[1] - raw[2]) < MARGIN_TOL).any())
+    assert near_tie or abs(conf - ref_conf) < SCORE_TOL, (text, conf, ref_conf)
+    return not near_tie
 
 
 @pytest.fixture(scope="module")
@@ -96,15 +101,8 @@ def test_recognizer_matches_oracle(models_dir, images, oracle, h, w, batch):
     crops = crops[:40]
     texts, scores = rec.run(crops)
     rt, rs, raw = orec.run(crops, want_raw=True)
-    same = 0
-    for i in range(len(crops)):
-        if texts[i] == rt[i]:
-            same += 1
-            assert abs(scores[i] - rs[i]) < SCORE_TOL
-        else:  # only allowed when some time step of the oracle has a top-2 margin below the tolerance
-            idx, mx, second = raw[i]
-            assert (mx - second).min() < MARGIN_TOL, (texts[i], rt[i])
-    assert same >= 0.4 * len(crops), (same, len(crops))
+    checked = sum(_check_line(texts[i], scores[i], rt[i], rs[i], raw[i]) for i in range(len(crops)))
+    assert checked >= 0.8 * len(crops), (checked, len(crops))  # near-tie lines are the exception
     assert rec.run([])[0] == []
 
 
@@ -126,15 +124,9 @@ def test_worker_json_matches_oracle(models_dir, images, oracle):
         # oracle fed with the GPU's boxes: cls + in-place rotation + rec + zip must agree
         ref, raw = oracle.process_words(im, det_boxes=[wd["box"] for wd in d["words"]], want_raw=True)
         assert len(ref) == len(d["words"])
-        agree = 0
-        for wd, (text, score, box), (idx, mx, second) in zip(d["words"], ref, raw):
+        for wd, (text, score, box), r3 in zip(d["words"], ref, raw):
             assert wd["box"] == [list(map(int, p)) for p in box]
-            if wd["text"] == text:
-                agree += 1
-                assert abs(wd["confidence"] - score) < SCORE_TOL
-            else:  # a different label only where the oracle's own top-2 margin is inside the tolerance
-                assert (mx - second).min() < MARGIN_TOL, (wd["text"], text)
-        assert agree >= 0.4 * len(ref), (agree, len(ref))
+            _check_line(wd["text"], wd["confidence"], text, score, r3)
         # the line is byte-for-byte what the reference's jsoncpp writer would print for these values
         rebuilt = result_json(rid, 5, True, im.shape[1], im.shape[0], d["processing_time_ms"],
                               [(wd["text"], wd["confidence"], wd["box"]) for wd in d["words"]])
@@ -180,3 +172,24 @@ def test_pool_dispatch_and_results(models_dir, images):
         time.sleep(0.01)
     assert pool.idle_count == pool.worker_count
     pool.close()
+
+
+def test_recognised_strings_identical_on_the_test_set(models_dir, images, oracle):
+    """card-jd, the reference's own test image and 24 S-cards (>= 200 lines) through the worker: every recognised
+    string equals the oracle's (fed with the GPU's boxes, so that cls + rotation + rec see identical upstream data)."""
+    import b200ocr
+    import synth_data
+    w = b200ocr.Worker(2, models_dir, enable_cls=True)
+    imgs = images[:2] + [synth_data.card(3000 + i) for i in range(24)]
+    lines = w.process_batch(list(range(len(imgs))), imgs)
+    n = conf_checked = 0
+    for im, line in zip(imgs, lines):
+        d = json.loads(line)
+        assert d["success"]
+        ref, raw = oracle.process_words(im, det_boxes=[wd["box"] for wd in d["words"]], want_raw=True)
+        assert len(ref) == len(d["words"])
+        for wd, (text, score, _box), r3 in zip(d["words"], ref, raw):
+            conf_checked += _check_line(wd["text"], wd["confidence"], text, score, r3)
+            n += 1
+    assert n >= 200, n
+    assert conf_checked >= 0.8 * n, (conf_checked, n)

@@ -3,9 +3,10 @@
   models/cls : the shipped graph + the shipped (real) weights
   models/det, models/rec : the shipped graphs + SYNTHETIC weights, because the reference
       mount lacks models/{det,rec}/inference.pdiparams (.MISSING_LARGE_BLOBS).
-      rec: seeded random.  det: tests/golden/models/det/inference.pdiparams, which tools/train_synth_det.py
-      fitted (from the seeded random initialisation) to the synthetic card generator so that the detector
-      finds the rendered text lines; without that file the seeded random det weights are used.
+      tests/golden/models/{det,rec}/inference.pdiparams, which tools/train_synth_det.py / tools/train_synth_rec.py
+      fitted (from the seeded random initialisation) to the synthetic generators so that the detector finds the
+      rendered text lines and the recognizer reads them with a saturated soft-max; without those files the seeded
+      random weights are used.
 
 Parameter names / shapes come from the product's own .pdmodel reader (b200ocr_model_params_json),
 the records are written in the `.pdiparams` layout.  If real det/rec weights are
@@ -87,7 +88,6 @@ def _is_synth(path, params, model) -> bool:
 
 
 def ensure_models(verbose=False) -> str:
-    import b200ocr  # the product library lists the parameters; no oracle code involved
     for m in ("det", "cls", "rec"):
         os.makedirs(os.path.join(DST, m), exist_ok=True)
         src_model = os.path.join(SRC, m, "inference.pdmodel")
@@ -100,6 +100,9 @@ def ensure_models(verbose=False) -> str:
             if not os.path.exists(dst_w) or open(dst_w, "rb").read() != open(src_w, "rb").read():
                 shutil.copyfile(src_w, dst_w)
             continue
+        # only reached when tests/golden/models/<m>/inference.pdiparams is missing (all three are committed): the
+        # product's own .pdmodel reader lists the parameters for the seeded fallback weights
+        import b200ocr
         params = b200ocr.model_params(src_model)
         expect = sum(16 + 4 + 2 + sum(1 + len(_varint(int(d))) for d in dims) + 4 * int(np.prod(dims))
                      for _n, dims in params)

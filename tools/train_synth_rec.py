@@ -153,8 +153,7 @@ def build_data(n_cards, n_random, n_pages, n_rec, verbose=True):
     # card-jd: content outside the generators' alphabet -> fixed pseudo labels (dictionary entries 100..)
     jd = cv2.imread(os.path.join(ROOT, "tests", "golden", "card-jd.jpg"))
     n0 = len(items)
-    for d in (det, det960):
-        add(jd, None, d, "jd")
+    add(jd, None, det, "jd")  # (one detector only: a second pass would find the same regions and label them differently)
     labels = ops.read_dict(os.path.join(GOLDEN, "rec", "ppocr_keys_v1.txt"))
     for i in range(n0, len(items)):
         c, rr, _l, src = items[i]
@@ -243,8 +242,13 @@ def main():
     ap.add_argument("--batch", type=int, default=48)
     ap.add_argument("--threads", type=int, default=8)
     ap.add_argument("--lr", type=float, default=2e-3)
+    ap.add_argument("--wd", type=float, default=1e-4)
     ap.add_argument("--device", default="cpu")
     ap.add_argument("--init", default="")
+    ap.add_argument("--entropy", type=float, default=0.0,
+                    help="weight of a per-step entropy penalty: makes the net commit to ONE alignment, so that the steps "
+                         "at character boundaries (where CTC is indifferent) stop sitting at p ~ 0.5")
+    ap.add_argument("--jd-repeat", type=int, default=1, help="oversampling of the card-jd crops")
     ap.add_argument("--out", default=os.path.join(GOLDEN, "rec", "inference.pdiparams"))
     a = ap.parse_args()
     torch.set_num_threads(a.threads)
@@ -254,6 +258,8 @@ def main():
         if a.build_data:
             return
     items = load_data()
+    if a.jd_repeat > 1:
+        items = items + [it_ for it_ in items if it_[3] == "jd"] * (a.jd_repeat - 1)
     print(f"{len(items)} crops", flush=True)
     dev = torch.device(a.device)
     prog = load_program(os.path.join(GOLDEN, "rec", "inference.pdmodel"))
@@ -276,7 +282,7 @@ def main():
     for it_ in items:
         for ch in it_[2]:
             assert ch in lab2idx, repr(ch)
-    opt = torch.optim.AdamW(train, lr=a.lr, weight_decay=1e-4)
+    opt = torch.optim.AdamW(train, lr=a.lr, weight_decay=a.wd)
 
     def lr_at(p):  # linear warm-up over the first 8 %, cosine to 2 % of the peak
         return a.lr * (p / 0.08 if p < 0.08 else 0.02 + 0.98 * 0.5 * (1 + np.cos(np.pi * (p - 0.08) / 0.92)))
@@ -309,6 +315,9 @@ def main():
                                                 torch.full((len(ls),), T, dtype=torch.long), tl, blank=0,
                                                 reduction="none", zero_infinity=True)
         loss = (loss_all * keep.to(loss_all.device)).sum() / max(int(keep.sum()), 1) / max(T, 1) * 10.0
+        if a.entropy > 0:
+            ent = -(logp.exp() * logp).sum(-1).mean()
+            loss = loss + a.entropy * 10.0 * ent
         opt.zero_grad(set_to_none=True)
         loss.backward()
         torch.nn.utils.clip_grad_norm_(train, 5.0)
