@@ -646,3 +646,63 @@ def kernel_ctc_head(feat, w, bias, force_simt=False, device=0):
                                       1 if force_simt else 0, idx.ctypes.data, prob.ctypes.data, col.ctypes.data,
                                       lens.ctypes.data, scores.ctypes.data))
     return idx, prob, [col[i, :lens[i]].copy() for i in range(n)], scores
+
+
+# ---------------------------------------------------------------- encoded inputs (device JPEG decode)
+class Blob(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("size", C.c_size_t)]
+
+
+_sig("b200ocr_worker_process_encoded", C.c_int, C.c_void_p, _P(C.c_int), _P(Blob), C.c_int, _P(C.c_void_p))
+_sig("b200ocr_worker_last_encoded_h2d_bytes", C.c_longlong, C.c_void_p)
+_sig("b200ocr_jpeg_decode", C.c_int, C.c_int, C.c_void_p, C.c_size_t, _P(C.c_int), _P(C.c_int), C.c_void_p)
+_sig("b200ocr_pool_submit_encoded", C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, _P(C.c_longlong))
+
+
+def _blob_array(files):
+    """files: bytes / bytearray / uint8 arrays -> (Blob array, keep-alive list)"""
+    keep = [np.frombuffer(f, np.uint8) if isinstance(f, (bytes, bytearray, memoryview)) else np.ascontiguousarray(f, np.uint8)
+            for f in files]
+    arr = (Blob * len(keep))(*[Blob(k.ctypes.data if k.size else None, k.size) for k in keep])
+    return arr, keep
+
+
+class PreparedBlobs:
+    def __init__(self, files):
+        self.arr, self.keep = _blob_array(files)
+
+    def __len__(self):
+        return len(self.keep)
+
+
+def jpeg_decode(data, device=0) -> np.ndarray:
+    """Baseline JPEG bytes -> uint8 [h, w, 3] BGR, decoded on the GPU (bit-identical to cv2.imdecode)."""
+    buf = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(data, np.uint8)
+    r, c = C.c_int(), C.c_int()
+    check(lib.b200ocr_jpeg_decode(device, buf.ctypes.data, buf.size, C.byref(r), C.byref(c), None))
+    out = np.empty((r.value, c.value, 3), np.uint8)
+    check(lib.b200ocr_jpeg_decode(device, buf.ctypes.data, buf.size, C.byref(r), C.byref(c), out.ctypes.data))
+    return out
+
+
+def _worker_process_encoded(self, request_ids, files):
+    p = files if isinstance(files, PreparedBlobs) else PreparedBlobs(files)
+    n = len(p)
+    ids = (C.c_int * n)(*request_ids)
+    out = (C.c_void_p * n)()
+    check(lib.b200ocr_worker_process_encoded(self._h, ids, p.arr, n, out))
+    return [_take_string(C.c_void_p(t)) for t in out]
+
+
+Worker.process_encoded = _worker_process_encoded
+Worker.last_encoded_h2d_bytes = property(lambda self: int(lib.b200ocr_worker_last_encoded_h2d_bytes(self._h)))
+
+
+def _pool_submit_encoded(self, request_id, data) -> int:
+    buf = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(data, np.uint8)
+    t = C.c_longlong()
+    check(lib.b200ocr_pool_submit_encoded(self._h, request_id, buf.ctypes.data if buf.size else None, buf.size, C.byref(t)))
+    return t.value
+
+
+Pool.submit_encoded = _pool_submit_encoded

@@ -1,0 +1,420 @@
+// Device half of the JPEG decoder (see jpeg.h): Huffman decoding, ISLOW inverse DCT, fancy upsampling + YCbCr -> BGR.
+// Integer arithmetic throughout, restating libjpeg's jdhuff.c / jidctint.c / jdsample.c / jdcolor.c the way
+// oracle/jpeg_decode.py does; results are bit-identical to cv2.imdecode.
+#include "jpeg.h"
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "stages.h"
+
+namespace b200ocr {
+
+namespace {
+
+__constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// ------------------------------------------------------------------------------------------------ entropy decoding
+// MSB-first bit reader over an entropy-coded segment: 0xFF00 is un-stuffed, any other marker feeds zero bits without
+// advancing (libjpeg's behaviour at the end of a segment; oracle/jpeg_decode.py::_Bits).
+struct BitReader {
+  const uint8_t* d;       // 4-byte aligned; readable up to 8 bytes past `end` (the batch buffer is padded)
+  int p, end;
+  uint64_t acc;
+  int n;
+  int pad;                // zero bits appended after the end of the data (they sit at the tail of acc)
+  __device__ __forceinline__ void fill() {
+    if (n > 32) return;
+    if (p + 4 <= end) {
+      // four bytes at once when none of them is 0xFF (no stuffing, no marker): two aligned words, funnel-shifted
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(d) + (p >> 2);
+      const uint32_t le = __funnelshift_r(__ldg(w), __ldg(w + 1), (p & 3) * 8);
+      const uint32_t inv = ~le;
+      if (((inv - 0x01010101u) & ~inv & 0x80808080u) == 0) {
+        acc = (acc << 32) | __byte_perm(le, 0, 0x0123);
+        n += 32;
+        p += 4;
+        return;
+      }
+    }
+    while (n <= 56) {
+      uint32_t b = 0;
+      if (p < end) {
+        b = d[p];
+        if (b == 0xFF) {
+          const uint32_t nx = p + 1 < end ? d[p + 1] : 0xD9u;
+          if (nx == 0) p += 2; else { b = 0; pad += 8; }
+        } else {
+          ++p;
+        }
+      } else {
+        pad += 8;
+      }
+      acc = (acc << 8) | b;
+      n += 8;
+    }
+  }
+  __device__ __forceinline__ uint32_t peek(int k) const { return uint32_t(acc >> (n - k)) & ((1u << k) - 1u); }
+  __device__ __forceinline__ void skip(int k) { n -= k; }
+  __device__ __forceinline__ int receive_extend(int s) {   // F.2.2.1 / F.2.2.4
+    if (s == 0) return 0;
+    const int v = int(peek(s));
+    skip(s);
+    return v >= (1 << (s - 1)) ? v : v - (1 << s) + 1;
+  }
+};
+
+__device__ __forceinline__ int decode_symbol(BitReader& br, const JpegHuffLut& t) {
+  const uint32_t look = br.peek(9);
+  const uint32_t e = t.fast[look];
+  if (e) {
+    br.skip(int(e >> 8));
+    return int(e & 255u);
+  }
+  // codes longer than 9 bits (F.2.2.3)
+  for (int len = 10; len <= 16; ++len) {
+    const int code = int(br.peek(len));
+    if (code <= t.maxcode[len]) {
+      br.skip(len);
+      return t.vals[(code + t.valoff[len]) & 255];
+    }
+  }
+  br.skip(16);  // invalid code: libjpeg warns and returns 0
+  return 0;
+}
+
+constexpr int kHuffThreads = 64;
+
+// One CTA per image: its six look-up tables are staged in shared memory, then every thread decodes restart intervals
+// (thread t takes intervals t, t + 64, ...).  Files without restart markers have one interval: one thread decodes
+// the whole image while the CTA's other threads idle -- the kernel is latency-bound per image and meant to run
+// beside other work (a batch of images = that many busy threads on as many SMs).
+__global__ void __launch_bounds__(kHuffThreads)
+jpeg_huffman_kernel(const JpegImage* __restrict__ imgs, const JpegSeg* __restrict__ segs, const uint8_t* __restrict__ bytes,
+                    int16_t* __restrict__ coef) {
+  __shared__ JpegHuffLut lut[6];
+  const JpegImage& im = imgs[blockIdx.x];
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(im.lut);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(lut);
+    const int words = int(sizeof(JpegHuffLut) * 2 * im.ncomp / 4);
+    for (int i = threadIdx.x; i < words; i += kHuffThreads) dst[i] = src[i];
+  }
+  __shared__ long long s_off[3];
+  __shared__ int s_bw[3], s_hs[3], s_vs[3];
+  if (threadIdx.x < im.ncomp) {
+    s_off[threadIdx.x] = im.comp[threadIdx.x].coef_off;
+    s_bw[threadIdx.x] = im.comp[threadIdx.x].bw;
+    s_hs[threadIdx.x] = im.comp[threadIdx.x].hs;
+    s_vs[threadIdx.x] = im.comp[threadIdx.x].vs;
+  }
+  __syncthreads();
+  const int ncomp = im.ncomp, mcux = im.mcux, nseg = im.seg_count, seg0 = im.seg_begin;
+  const uint8_t* data = bytes + im.data_off;
+  for (int si = threadIdx.x; si < nseg; si += kHuffThreads) {
+    const JpegSeg sg = segs[seg0 + si];
+    BitReader br;
+    br.d = data;
+    br.p = sg.begin; br.end = sg.end; br.acc = 0; br.n = 0; br.pad = 0;
+    int pred[3] = {0, 0, 0};
+    int my = sg.mcu0 / mcux, mx = sg.mcu0 - my * mcux;
+    for (int m = 0; m < sg.nmcu; ++m) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (c >= ncomp) break;
+        const JpegHuffLut& tdc = lut[2 * c];
+        const JpegHuffLut& tac = lut[2 * c + 1];
+        const int hs = s_hs[c], vs = s_vs[c], bw = s_bw[c];
+        for (int by = 0; by < vs; ++by)
+          for (int bx = 0; bx < hs; ++bx) {
+            int16_t* blk = coef + (s_off[c] + (long long)(my * vs + by) * bw + (mx * hs + bx)) * 64;
+            br.fill();
+            const int t = decode_symbol(br, tdc) & 15;
+            br.fill();
+            pred[c] += br.receive_extend(t);
+            blk[0] = int16_t(pred[c]);
+            int k = 1;
+            while (k < 64) {
+              br.fill();
+              const int rs = decode_symbol(br, tac);
+              const int r = rs >> 4, s = rs & 15;
+              if (s == 0) {
+                if (r != 15) break;
+                k += 16;
+                continue;
+              }
+              k += r;
+              const int v = br.receive_extend(s);
+              if (k < 64) blk[c_zigzag[k]] = int16_t(v);
+              ++k;
+            }
+          }
+      }
+      if (++mx == mcux) { mx = 0; ++my; }
+      // Out of data (jdhuff.c `insufficient_data`): the MCU in which the decoder ran past the end of the segment is
+      // completed with zero bits, the MCUs after it are not decoded at all (their coefficients stay zero: mid grey).
+      if (br.pad > br.n) break;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ inverse DCT
+// jidctint.c (JDCT_ISLOW): CONST_BITS 13, PASS1_BITS 2
+__device__ __forceinline__ void idct8(const int x[8], int out[8], int shift) {
+  constexpr int F0298 = 2446, F0390 = 3196, F0541 = 4433, F0765 = 6270, F0899 = 7373, F1175 = 9633, F1501 = 12299,
+                F1847 = 15137, F1961 = 16069, F2053 = 16819, F2562 = 20995, F3072 = 25172;
+  int z2 = x[2], z3 = x[6];
+  int z1 = (z2 + z3) * F0541;
+  const int tmp2 = z1 - z3 * F1847;
+  const int tmp3 = z1 + z2 * F0765;
+  const int tmp0 = (x[0] + x[4]) << 13;
+  const int tmp1 = (x[0] - x[4]) << 13;
+  const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  int t0 = x[7], t1 = x[5], t2 = x[3], t3 = x[1];
+  z1 = t0 + t3; z2 = t1 + t2; z3 = t0 + t2;
+  int z4 = t1 + t3;
+  const int z5 = (z3 + z4) * F1175;
+  t0 *= F0298; t1 *= F2053; t2 *= F3072; t3 *= F1501;
+  z1 *= -F0899; z2 *= -F2562;
+  z3 = z3 * -F1961 + z5;
+  z4 = z4 * -F0390 + z5;
+  t0 += z1 + z3; t1 += z2 + z4; t2 += z2 + z3; t3 += z1 + z4;
+  const int rnd = 1 << (shift - 1);
+  out[0] = (tmp10 + t3 + rnd) >> shift; out[7] = (tmp10 - t3 + rnd) >> shift;
+  out[1] = (tmp11 + t2 + rnd) >> shift; out[6] = (tmp11 - t2 + rnd) >> shift;
+  out[2] = (tmp12 + t1 + rnd) >> shift; out[5] = (tmp12 - t1 + rnd) >> shift;
+  out[3] = (tmp13 + t0 + rnd) >> shift; out[4] = (tmp13 - t0 + rnd) >> shift;
+}
+
+constexpr int kIdctThreads = 256;  // 32 blocks of 8x8 per CTA, 8 threads each
+
+// image of a batch-wide block number: binary search over the images' first blocks
+__device__ __forceinline__ int find_image(const JpegImage* imgs, int n, long long b) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (imgs[mid].block_begin <= b) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kIdctThreads)
+jpeg_idct_kernel(const JpegImage* __restrict__ imgs, int n_images, long long total_blocks, const int16_t* __restrict__ coef,
+                 uint8_t* __restrict__ planes) {
+  __shared__ int ws[kIdctThreads / 8][8][9];
+  const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
+  const long long b = (long long)blockIdx.x * (kIdctThreads / 8) + g;
+  const bool live = b < total_blocks;
+  int comp = 0;
+  long long local = 0;
+  const JpegImage* im = nullptr;
+  if (live) {
+    im = &imgs[find_image(imgs, n_images, b)];
+    local = b - im->block_begin;  // == index into the coefficient buffer relative to comp[0].coef_off
+    for (int c = im->ncomp - 1; c > 0; --c)
+      if (local >= im->comp[c].coef_off - im->comp[0].coef_off) { comp = c; break; }
+  }
+  int row[8], v[8];
+  if (live) {
+    // thread j: row j of the block, dequantised
+    const JpegComp& cp = im->comp[comp];
+    const int4 raw = *reinterpret_cast<const int4*>(coef + (im->comp[0].coef_off + local) * 64 + j * 8);
+    const int16_t* r16 = reinterpret_cast<const int16_t*>(&raw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ws[g][j][k] = int(r16[k]) * int(cp.q[j * 8 + k]);
+  }
+  __syncwarp();
+  if (live) {
+    // pass 1: column j
+#pragma unroll
+    for (int k = 0; k < 8; ++k) row[k] = ws[g][k][j];
+    idct8(row, v, 13 - 2);
+  }
+  __syncwarp();
+  if (live) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ws[g][k][j] = v[k];
+  }
+  __syncwarp();
+  if (live) {
+    // pass 2: row j
+#pragma unroll
+    for (int k = 0; k < 8; ++k) row[k] = ws[g][j][k];
+    idct8(row, v, 13 + 2 + 3);
+    const JpegComp& cp = im->comp[comp];
+    const long long cb = local - (cp.coef_off - im->comp[0].coef_off);
+    const int by = int(cb / cp.bw), bx = int(cb - (long long)by * cp.bw);
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      lo |= uint32_t(min(max(v[k] + 128, 0), 255)) << (8 * k);
+      hi |= uint32_t(min(max(v[k + 4] + 128, 0), 255)) << (8 * k);
+    }
+    uint8_t* dst = planes + cp.plane_off + (long long)(by * 8 + j) * (cp.bw * 8) + bx * 8;
+    *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ upsampling + colour
+// jdsample.c fancy upsampling of one chroma sample at full-resolution position (y, x); the component's last real
+// row / column is replicated as context.
+__device__ __forceinline__ int chroma_at(const uint8_t* __restrict__ p, int pitch, int cw, int ch, int fh, int fv, int y, int x) {
+  if (fh == 1) return p[(long long)y * pitch + x];
+  const int cx = x >> 1;
+  const int xo = (x & 1) ? min(cx + 1, cw - 1) : max(cx - 1, 0);
+  if (fv == 1) {
+    const uint8_t* r = p + (long long)y * pitch;
+    return (x & 1) ? (3 * r[cx] + r[xo] + 2) >> 2 : (3 * r[cx] + r[xo] + 1) >> 2;
+  }
+  const int cy = y >> 1;
+  const int yo = (y & 1) ? min(cy + 1, ch - 1) : max(cy - 1, 0);
+  const uint8_t* r0 = p + (long long)cy * pitch;
+  const uint8_t* r1 = p + (long long)yo * pitch;
+  const int cs = 3 * r0[cx] + r1[cx], co = 3 * r0[xo] + r1[xo];
+  return (x & 1) ? (3 * cs + co + 7) >> 4 : (3 * cs + co + 8) >> 4;
+}
+
+__global__ void __launch_bounds__(256)
+jpeg_color_kernel(const JpegImage* __restrict__ imgs, const uint8_t* __restrict__ planes, uint8_t* __restrict__ out) {
+  const JpegImage& im = imgs[blockIdx.z];
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= im.width || y >= im.height) return;
+  const JpegComp& c0 = im.comp[0];
+  const int Y = planes[c0.plane_off + (long long)y * (c0.bw * 8) + x];
+  int b = Y, g = Y, r = Y;
+  if (im.ncomp == 3) {
+    const JpegComp& c1 = im.comp[1];
+    const JpegComp& c2 = im.comp[2];
+    const int fh = im.hmax / c1.hs, fv = im.vmax / c1.vs;
+    const int cb = chroma_at(planes + c1.plane_off, c1.bw * 8, c1.cw, c1.ch, fh, fv, y, x) - 128;
+    const int cr = chroma_at(planes + c2.plane_off, c2.bw * 8, c2.cw, c2.ch, fh, fv, y, x) - 128;
+    // jdcolor.c, SCALEBITS 16: FIX(1.40200) = 91881, FIX(1.77200) = 116130, FIX(0.71414) = 46802, FIX(0.34414) = 22554
+    r = Y + ((91881 * cr + 32768) >> 16);
+    b = Y + ((116130 * cb + 32768) >> 16);
+    g = Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+    r = min(max(r, 0), 255); g = min(max(g, 0), 255); b = min(max(b, 0), 255);
+  }
+  uint8_t* o = out + im.out_off + (long long)y * im.out_stride + 3 * x;
+  o[0] = uint8_t(b); o[1] = uint8_t(g); o[2] = uint8_t(r);
+}
+
+}  // namespace
+
+void launch_jpeg_decode(const JpegImage* imgs_dev, const JpegImage* imgs_host, int n_images, const JpegSeg* segs_dev,
+                        int n_segs, const uint8_t* bytes_dev, int16_t* coef_dev, size_t coef_bytes, uint8_t* planes_dev,
+                        uint8_t* out_dev, cudaStream_t s) {
+  (void)n_segs;
+  if (n_images < 1) return;
+  // only the non-zero coefficients are written by the entropy decoder
+  if (cudaMemsetAsync(coef_dev, 0, coef_bytes, s) != cudaSuccess) throw std::runtime_error("jpeg: cudaMemsetAsync failed");
+  jpeg_huffman_kernel<<<n_images, kHuffThreads, 0, s>>>(imgs_dev, segs_dev, bytes_dev, coef_dev);
+  const JpegImage& last = imgs_host[n_images - 1];
+  const long long total_blocks = last.block_begin + last.nblocks;
+  const int per = kIdctThreads / 8;
+  jpeg_idct_kernel<<<unsigned((total_blocks + per - 1) / per), kIdctThreads, 0, s>>>(imgs_dev, n_images, total_blocks, coef_dev,
+                                                                                    planes_dev);
+  int wmax = 0, hmax = 0;
+  for (int i = 0; i < n_images; ++i) { wmax = std::max(wmax, imgs_host[i].width); hmax = std::max(hmax, imgs_host[i].height); }
+  dim3 grid((wmax + 63) / 64, (hmax + 3) / 4, n_images);
+  jpeg_color_kernel<<<grid, 256, 0, s>>>(imgs_dev, planes_dev, out_dev);
+  const cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("jpeg decode launch: ") + cudaGetErrorString(cudaGetLastError()));
+}
+
+// ------------------------------------------------------------------------------------------------ batch front end
+struct JpegBatch::Impl {
+  DevBuf meta, coef, planes, out;
+  DevBuf stage{true};
+  cudaEvent_t copied = nullptr;
+  bool pending = false;
+};
+
+JpegBatch::JpegBatch() : impl_(new Impl) {}
+JpegBatch::~JpegBatch() {
+  if (impl_->copied) cudaEventDestroy(impl_->copied);
+  delete impl_;
+}
+
+int JpegBatch::decode(const uint8_t* const* data, const size_t* sizes, int n, cudaStream_t s, std::vector<DevImg>* out,
+                      std::vector<std::string>* why) {
+  out->assign(size_t(n), DevImg());
+  why->assign(size_t(n), std::string());
+  h2d_bytes_ = 0;
+  std::vector<JpegImage> imgs;
+  std::vector<JpegSeg> segs;
+  std::vector<int> index;
+  std::vector<std::pair<size_t, size_t>> ecs;
+  imgs.reserve(size_t(n));
+  auto a256 = [](size_t x) { return (x + 255) & ~size_t(255); };
+  size_t bytes_total = 0, coef_blocks = 0, plane_bytes = 0, out_bytes = 0;
+  for (int i = 0; i < n; ++i) {
+    JpegImage im;
+    std::vector<JpegSeg> sg;
+    size_t b = 0, e = 0;
+    if (!data[i] || sizes[i] == 0) { (*why)[i] = "Empty image data provided"; continue; }
+    if (!jpeg_parse(data[i], sizes[i], &im, &b, &e, &sg, &(*why)[i])) continue;
+    im.data_off = (long long)bytes_total;
+    im.data_len = int(e - b);
+    bytes_total += (size_t(im.data_len) + 16 + 15) & ~size_t(15);  // 4-byte aligned start, readable past the end
+    im.seg_begin = int(segs.size());
+    im.seg_count = int(sg.size());
+    for (auto& x : sg) { x.image = int(imgs.size()); segs.push_back(x); }
+    im.block_begin = (long long)coef_blocks;
+    for (int c = 0; c < im.ncomp; ++c) {
+      im.comp[c].coef_off = (long long)coef_blocks;
+      coef_blocks += size_t(im.comp[c].bw) * im.comp[c].bh;
+      im.comp[c].plane_off = (long long)plane_bytes;
+      plane_bytes += a256(size_t(im.comp[c].bw) * 8 * im.comp[c].bh * 8);
+    }
+    im.nblocks = (long long)coef_blocks - im.block_begin;
+    im.out_off = (long long)out_bytes;
+    im.out_stride = (long long)im.width * 3;
+    out_bytes += a256(size_t(im.width) * im.height * 3);
+    imgs.push_back(im);
+    index.push_back(i);
+    ecs.emplace_back(b, e);
+  }
+  const int m = int(imgs.size());
+  if (m == 0) return 0;
+  Impl& I = *impl_;
+  if (!I.copied) cuda_check(cudaEventCreateWithFlags(&I.copied, cudaEventDisableTiming), "cudaEventCreate");
+  if (I.pending) { cuda_check(cudaEventSynchronize(I.copied), "jpeg staging reuse"); I.pending = false; }
+  const size_t off_segs = a256(sizeof(JpegImage) * size_t(m));
+  const size_t off_bytes = off_segs + a256(sizeof(JpegSeg) * segs.size());
+  const size_t total = off_bytes + bytes_total + 16;
+  I.stage.ensure(total);
+  I.meta.ensure(total);
+  I.coef.ensure(coef_blocks * 128);
+  I.planes.ensure(plane_bytes);
+  I.out.ensure(out_bytes);
+  uint8_t* h = I.stage.as<uint8_t>();
+  memcpy(h, imgs.data(), sizeof(JpegImage) * size_t(m));
+  memcpy(h + off_segs, segs.data(), sizeof(JpegSeg) * segs.size());
+  for (int k = 0; k < m; ++k) {
+    uint8_t* dst = h + off_bytes + imgs[k].data_off;
+    memcpy(dst, data[index[k]] + ecs[k].first, size_t(imgs[k].data_len));
+    memset(dst + imgs[k].data_len, 0, 16);
+  }
+  cuda_check(cudaMemcpyAsync(I.meta.p, h, total, cudaMemcpyHostToDevice, s), "jpeg upload");
+  cuda_check(cudaEventRecord(I.copied, s), "cudaEventRecord");
+  I.pending = true;
+  h2d_bytes_ = total;
+  const uint8_t* d = I.meta.as<uint8_t>();
+  launch_jpeg_decode(reinterpret_cast<const JpegImage*>(d), imgs.data(), m, reinterpret_cast<const JpegSeg*>(d + off_segs),
+                     int(segs.size()), d + off_bytes, I.coef.as<int16_t>(), coef_blocks * 128, I.planes.as<uint8_t>(),
+                     I.out.as<uint8_t>(), s);
+  launches += 3;
+  for (int k = 0; k < m; ++k) {
+    DevImg& o = (*out)[size_t(index[k])];
+    o.p = I.out.as<uint8_t>() + imgs[k].out_off;
+    o.rows = imgs[k].height; o.cols = imgs[k].width; o.stride = long(imgs[k].out_stride);
+  }
+  return m;
+}
+
+}  // namespace b200ocr

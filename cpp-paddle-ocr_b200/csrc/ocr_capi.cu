@@ -12,6 +12,7 @@
 #include "../../include/b200ocr.h"
 #include "capi_util.h"
 #include "stages.h"
+#include "jpeg.h"
 
 using namespace b200ocr;
 
@@ -82,6 +83,7 @@ struct b200ocr_pool {
     long long ticket;
     int request_id;
     std::vector<uint8_t> pixels;  // deep copy, like OCRRequest (reference include/paddle_ocr/ocr_worker.h:28-29)
+    bool encoded = false;         // pixels holds the encoded file (b200ocr_pool_submit_encoded)
     int rows, cols;
     std::chrono::steady_clock::time_point t_submit;
   };
@@ -121,15 +123,37 @@ struct b200ocr_pool {
         d->busy += 1;
       }
       std::vector<int> ids(take.size());
-      std::vector<HostImage> imgs(take.size());
-      for (size_t i = 0; i < take.size(); ++i) {
-        ids[i] = take[i]->request_id;
-        imgs[i].data = take[i]->pixels.empty() ? nullptr : take[i]->pixels.data();
-        imgs[i].rows = take[i]->rows; imgs[i].cols = take[i]->cols; imgs[i].step = size_t(take[i]->cols) * 3;
-      }
-      std::vector<std::string> out;
+      for (size_t i = 0; i < take.size(); ++i) ids[i] = take[i]->request_id;
+      std::vector<std::string> out(take.size());
       try {
-        w->process_batch(ids.data(), imgs.data(), int(take.size()), &out);
+        // raw and encoded requests of one batch go through the worker as two groups
+        std::vector<size_t> raw, enc;
+        for (size_t i = 0; i < take.size(); ++i) (take[i]->encoded ? enc : raw).push_back(i);
+        if (!raw.empty()) {
+          std::vector<int> rid(raw.size());
+          std::vector<HostImage> imgs(raw.size());
+          for (size_t k = 0; k < raw.size(); ++k) {
+            const Request& r = *take[raw[k]];
+            rid[k] = r.request_id;
+            imgs[k].data = r.pixels.empty() ? nullptr : r.pixels.data();
+            imgs[k].rows = r.rows; imgs[k].cols = r.cols; imgs[k].step = size_t(r.cols) * 3;
+          }
+          std::vector<std::string> o;
+          w->process_batch(rid.data(), imgs.data(), int(raw.size()), &o);
+          for (size_t k = 0; k < raw.size(); ++k) out[raw[k]] = std::move(o[k]);
+        }
+        if (!enc.empty()) {
+          std::vector<int> rid(enc.size());
+          std::vector<const uint8_t*> data(enc.size());
+          std::vector<size_t> sizes(enc.size());
+          for (size_t k = 0; k < enc.size(); ++k) {
+            const Request& r = *take[enc[k]];
+            rid[k] = r.request_id; data[k] = r.pixels.data(); sizes[k] = r.pixels.size();
+          }
+          std::vector<std::string> o;
+          w->process_encoded(rid.data(), data.data(), sizes.data(), int(enc.size()), &o);
+          for (size_t k = 0; k < enc.size(); ++k) out[enc[k]] = std::move(o[k]);
+        }
       } catch (const std::exception& e) {
         // reference src/ocr_worker.cpp:192-206: request_id, success=false, error, worker_id
         out.assign(take.size(), std::string());
@@ -483,6 +507,42 @@ int b200ocr_worker_process_resident(b200ocr_worker_t w, b200ocr_batch_t batch, c
   });
 }
 
+int b200ocr_worker_process_encoded(b200ocr_worker_t w, const int* request_ids, const b200ocr_blob* blobs, int n,
+                                   char** jsons) {
+  return capi_guard([&] {
+    if (!w || !request_ids || !blobs || !jsons || n < 0) throw std::invalid_argument("null argument");
+    std::vector<const uint8_t*> data(n);
+    std::vector<size_t> sizes(n);
+    for (int i = 0; i < n; ++i) { data[i] = blobs[i].data; sizes[i] = blobs[i].size; }
+    std::vector<std::string> out;
+    w->w->process_encoded(request_ids, data.data(), sizes.data(), n, &out);
+    for (int i = 0; i < n; ++i) jsons[i] = dup_string(out[i]);
+  });
+}
+long long b200ocr_worker_last_encoded_h2d_bytes(b200ocr_worker_t w) { return w ? (long long)w->w->last_encoded_h2d_bytes() : 0; }
+
+int b200ocr_jpeg_decode(int device, const uint8_t* data, size_t size, int* rows, int* cols, uint8_t* bgr) {
+  return capi_guard([&] {
+    if (!data || !rows || !cols) throw std::invalid_argument("null argument");
+    JpegImage im;
+    std::vector<JpegSeg> segs;
+    size_t b = 0, e = 0;
+    std::string why;
+    if (!jpeg_parse(data, size, &im, &b, &e, &segs, &why)) throw std::invalid_argument("Unsupported image encoding: " + why);
+    *rows = im.height; *cols = im.width;
+    if (!bgr) return;
+    StageBase sb;
+    sb.init(device);
+    JpegBatch jb;
+    std::vector<DevImg> out;
+    std::vector<std::string> w2;
+    jb.decode(&data, &size, 1, sb.stream, &out, &w2);
+    if (!out[0].p) throw std::runtime_error(w2[0]);
+    cuda_check(cudaMemcpyAsync(bgr, out[0].p, size_t(im.height) * im.width * 3, cudaMemcpyDeviceToHost, sb.stream), "copy");
+    cuda_check(cudaStreamSynchronize(sb.stream), "jpeg decode");
+  });
+}
+
 int b200ocr_worker_profile(b200ocr_worker_t w, int warmup, int reps, char** json) {
   return capi_guard([&] {
     if (!w || !json || reps < 1) throw std::invalid_argument("bad argument");
@@ -554,6 +614,7 @@ int b200ocr_pool_create(const char* model_dir, int n_devices, const int* devices
 }
 void b200ocr_pool_destroy(b200ocr_pool_t pool) { delete pool; }
 
+static void pool_enqueue(b200ocr_pool_t pool, const std::shared_ptr<b200ocr_pool::Request>& r);
 int b200ocr_pool_submit(b200ocr_pool_t pool, int request_id, const b200ocr_image* img, long long* ticket) {
   return capi_guard([&] {
     if (!pool || !img || !ticket) throw std::invalid_argument("null argument");
@@ -568,19 +629,39 @@ int b200ocr_pool_submit(b200ocr_pool_t pool, int request_id, const b200ocr_image
       r->pixels.resize(row * img->rows);
       for (int y = 0; y < img->rows; ++y) memcpy(r->pixels.data() + y * row, img->data + y * step, row);
     }
-    // shortest queue first; ties broken round-robin (reference src/gpu_worker_pool.cpp:46-59: idle worker, else round-robin)
-    const size_t nd = pool->devs.size(), start = pool->rr++ % nd;
-    size_t best = start, best_load = ~size_t(0);
-    for (size_t k = 0; k < nd; ++k) {
-      auto& d = *pool->devs[(start + k) % nd];
-      std::lock_guard<std::mutex> lk(d.mu);
-      const size_t load = d.queue.size() + size_t(d.busy.load()) * size_t(pool->max_batch);
-      if (load < best_load) { best_load = load; best = (start + k) % nd; }
-    }
-    auto& d = *pool->devs[best];
-    { std::lock_guard<std::mutex> lk(pool->res_mu); pool->outstanding.insert(r->ticket); }
-    { std::lock_guard<std::mutex> lk(d.mu); d.queue.push_back(r); }
-    d.cv.notify_one();
+    pool_enqueue(pool, r);
+    *ticket = r->ticket;
+  });
+}
+
+static void pool_enqueue(b200ocr_pool_t pool, const std::shared_ptr<b200ocr_pool::Request>& r) {
+  // shortest queue first; ties broken round-robin (reference src/gpu_worker_pool.cpp:46-59: idle worker, else round-robin)
+  const size_t nd = pool->devs.size(), start = pool->rr++ % nd;
+  size_t best = start, best_load = ~size_t(0);
+  for (size_t k = 0; k < nd; ++k) {
+    auto& d = *pool->devs[(start + k) % nd];
+    std::lock_guard<std::mutex> lk(d.mu);
+    const size_t load = d.queue.size() + size_t(d.busy.load()) * size_t(pool->max_batch);
+    if (load < best_load) { best_load = load; best = (start + k) % nd; }
+  }
+  auto& d = *pool->devs[best];
+  { std::lock_guard<std::mutex> lk(pool->res_mu); pool->outstanding.insert(r->ticket); }
+  { std::lock_guard<std::mutex> lk(d.mu); d.queue.push_back(r); }
+  d.cv.notify_one();
+}
+
+int b200ocr_pool_submit_encoded(b200ocr_pool_t pool, int request_id, const uint8_t* data, size_t size, long long* ticket) {
+  return capi_guard([&] {
+    if (!pool || !ticket || (!data && size)) throw std::invalid_argument("null argument");
+    auto r = std::make_shared<b200ocr_pool::Request>();
+    r->ticket = pool->next_ticket++;
+    r->request_id = request_id;
+    r->t_submit = std::chrono::steady_clock::now();
+    pool->total_requests += 1;
+    r->rows = r->cols = 0;
+    r->encoded = true;
+    if (size) r->pixels.assign(data, data + size);
+    pool_enqueue(pool, r);
     *ticket = r->ticket;
   });
 }

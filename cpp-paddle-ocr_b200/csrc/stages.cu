@@ -1,4 +1,5 @@
 #include "stages.h"
+#include "jpeg.h"
 
 #include <algorithm>
 #include <chrono>
@@ -552,7 +553,9 @@ Worker::~Worker() {
   if (stream_) cudaStreamDestroy(stream_);
 }
 
-long Worker::launches() const { return det_->launches + rec_->launches + (cls_ ? cls_->launches : 0); }
+long Worker::launches() const {
+  return det_->launches + rec_->launches + (cls_ ? cls_->launches : 0) + (jpeg_ ? jpeg_->launches : 0);
+}
 
 // det -> ROI -> (cls -> rotate) -> rec for one batch of device images (reference src/ocr_worker.cpp:228-300)
 void Worker::run_device(const std::vector<DevImg>& dimgs, std::vector<std::vector<WordOut>>* words) {
@@ -668,6 +671,78 @@ void Worker::process_resident(const int* request_ids, const std::vector<DevImg>&
 void Worker::recover_after_failure() {
   cudaStreamSynchronize(stream_);
   cudaGetLastError();
+}
+
+size_t Worker::last_encoded_h2d_bytes() const { return jpeg_ ? jpeg_->h2d_bytes() : 0; }
+
+void Worker::process_encoded(const int* request_ids, const uint8_t* const* data, const size_t* sizes, int n,
+                             std::vector<std::string>* json) {
+  cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+  json->assign(n, std::string());
+  const auto t_start = Clock::now();
+  if (!jpeg_) jpeg_ = std::make_unique<JpegBatch>();
+  std::vector<DevImg> dec;
+  std::vector<std::string> why;
+  std::vector<int> live;
+  std::vector<std::string> errors(n);
+  std::vector<std::vector<WordOut>> words(n);
+  try {
+    jpeg_->decode(data, sizes, n, stream_, &dec, &why);
+  } catch (const std::exception& e) {
+    recover_after_failure();
+    dec.assign(n, DevImg());
+    why.assign(n, e.what());
+  }
+  for (int i = 0; i < n; ++i) {
+    if (dec[i].p) live.push_back(i);
+    else errors[i] = (!data[i] || sizes[i] == 0) ? "Empty image data provided" : "Unsupported image encoding: " + why[i];
+  }
+  auto run_range = [&](size_t b0, int nb) {
+    std::vector<DevImg> dimgs(nb);
+    for (int k = 0; k < nb; ++k) dimgs[k] = dec[live[b0 + k]];
+    std::vector<std::vector<WordOut>> w;
+    run_device(dimgs, &w);   // (the classifier's in-place rotations land in the decoder's own output buffer)
+    for (int k = 0; k < nb; ++k) words[live[b0 + k]] = std::move(w[k]);
+  };
+  for (size_t b0 = 0; b0 < live.size(); b0 += size_t(opt_.max_batch)) {
+    const int nb = int(std::min(live.size() - b0, size_t(opt_.max_batch)));
+    try {
+      run_range(b0, nb);
+    } catch (const std::exception& e) {
+      recover_after_failure();
+      if (nb == 1) { errors[live[b0]] = e.what(); continue; }
+      // NOTE: a retry sees ROIs the failed pass may already have rotated; decode again for a clean retry
+      for (size_t i = b0; i < b0 + size_t(nb); ++i) {
+        try {
+          std::vector<DevImg> one;
+          std::vector<std::string> w1;
+          const int src = live[i];
+          jpeg_->decode(data + src, sizes + src, 1, stream_, &one, &w1);
+          if (!one[0].p) throw std::runtime_error(w1[0]);
+          std::vector<std::vector<WordOut>> w;
+          run_device(one, &w);
+          words[src] = std::move(w[0]);
+        } catch (const std::exception& e1) {
+          recover_after_failure();
+          words[live[i]].clear();
+          errors[live[i]] = e1.what();
+        }
+      }
+      // the single-image decodes reused the batch buffers: the images of later sub-batches are gone -> decode them again
+      if (b0 + size_t(nb) < live.size()) {
+        std::vector<DevImg> again;
+        std::vector<std::string> w2;
+        jpeg_->decode(data, sizes, n, stream_, &again, &w2);
+        for (size_t i = b0 + size_t(nb); i < live.size(); ++i) dec[live[i]] = again[live[i]];
+      }
+    }
+  }
+  const double ms = ms_since(t_start);
+  for (int i = 0; i < n; ++i) {
+    const bool ok = errors[i].empty();
+    (*json)[i] = result_json(request_ids[i], worker_id_, ok, ok || dec[i].p ? dec[i].cols : 0, ok || dec[i].p ? dec[i].rows : 0, ms,
+                             words[i], errors[i]);
+  }
 }
 
 void Worker::process_batch(const int* request_ids, const HostImage* imgs, int n, std::vector<std::string>* json) {

