@@ -11,6 +11,7 @@
 // registers, P = exp2(S - m) repacked in place as the A operand of P.V.  The number of key blocks depends only on
 // the row's own valid length, so a row of a ragged batch is bit-identical to the same row in a dense batch.
 #include "kernels.h"
+#include "pdl.h"
 
 #include <cfloat>
 #include <cstdlib>
@@ -41,6 +42,8 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 // smem: QK [Tp][kTok] halves (Q then K per token; the Q slots are reused for the output), Vt [8][16][Tp + 8]
 __global__ void __launch_bounds__(kAttnThreads)
 attention_mma_kernel(TV qkv, TV out, int heads, int hd, float scale_log2e, const int* __restrict__ vw, int Tp) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t attn_smem[];
   __half* QK = reinterpret_cast<__half*>(attn_smem);
   const int vpitch = Tp + 8;                 // +8 halves: rows of Vt land on different banks
@@ -214,7 +217,7 @@ bool launch_attention_mma(const TV& qkv, const TV& out, int heads, int hd, float
     cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured[dev] = 200 * 1024;
   }
-  attention_mma_kernel<<<qkv.n, kAttnThreads, smem, s>>>(qkv, out, heads, hd, scale * 1.4426950408889634f, vw, Tp);
+  launch_k(attention_mma_kernel, dim3(qkv.n), dim3(kAttnThreads), smem, s, qkv, out, heads, hd, scale * 1.4426950408889634f, vw, Tp);
   return true;
 }
 

@@ -10,6 +10,7 @@
 // epilogue warps read them back with tcgen05.ld, apply bias/activation/affine/residual and store
 // NHWC fp16.  Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issue, 2..5 = epilogue.
 #include "kernels.h"
+#include "pdl.h"
 
 #include <cuda.h>
 #include <cstdio>
@@ -254,6 +255,7 @@ template <int ACT>
 __global__ void __launch_bounds__(kThreadsTc)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcArgs a) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   // [barriers | tmem ptr] then 1024-aligned tiles
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -296,6 +298,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // everything above (barriers, TMEM, tensor maps) overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -358,6 +361,7 @@ __global__ void __launch_bounds__(kThreadsTc)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmC, const ConvTcArgs a, const int n_mtiles,
                        const int kt /* taps * K chunks */, const int tma_store) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* a_full = b_full + 1;
@@ -401,6 +405,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int tap = 0, it = 0; tap < a.kh * a.kw; ++tap)
         for (int kc = 0; kc < kchunks; ++kc, ++it)
           tma_load_2d(&tmB, b_full, tiles + size_t(it) * b_chunk, tap * a.cin_pad + kc * 64, nblk * a.bn);
+      pdl_wait();  // the filter block is on its way; activations only after the previous kernel has finished
       const uint32_t a_bytes = a.halo ? uint32_t(a.row_w * (a.th + a.kh - 1) * 128) : uint32_t(a.tw * a.th * a.tn * 128);
       int g = 0;
       for (int tile = blockIdx.x; tile < n_mtiles; tile += gridDim.x) {
@@ -475,6 +480,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else {
+    pdl_wait();  // residual reads / output writes: only after the previous kernel has finished
     // output staging tile behind the A ring (only with tma_store): ceil(bn / 64) chunks of 128 rows x 128 B
     uint8_t* stage = tma_store ? tiles + a_ring + size_t(a.stages) * a.a_stage : nullptr;
     const bool leader = warp == 2 && lane == 0;
@@ -752,22 +758,22 @@ void launch_conv_tc(const ConvTcPlan& p, const float* bias, const Epi& e, cudaSt
     const int nm = p.impl->n_mtiles, kt = p.impl->kt;
     const int ts = p.impl->tma_store && e.res == nullptr ? 1 : 0;
     switch (e.act) {
-      case 1: conv_tc_persist_kernel<1><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
-      case 2: conv_tc_persist_kernel<2><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
-      case 3: conv_tc_persist_kernel<3><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
-      case 4: conv_tc_persist_kernel<4><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
-      case 5: conv_tc_persist_kernel<5><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
-      default: conv_tc_persist_kernel<0><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
+      case 1: launch_k(conv_tc_persist_kernel<1>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
+      case 2: launch_k(conv_tc_persist_kernel<2>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
+      case 3: launch_k(conv_tc_persist_kernel<3>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
+      case 4: launch_k(conv_tc_persist_kernel<4>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
+      case 5: launch_k(conv_tc_persist_kernel<5>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
+      default: launch_k(conv_tc_persist_kernel<0>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, p.impl->tmC, a, nm, kt, ts); break;
     }
     return;
   }
   switch (e.act) {
-    case 1: conv_tc_kernel<1><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
-    case 2: conv_tc_kernel<2><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
-    case 3: conv_tc_kernel<3><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
-    case 4: conv_tc_kernel<4><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
-    case 5: conv_tc_kernel<5><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
-    default: conv_tc_kernel<0><<<p.impl->grid, kThreadsTc, p.impl->smem, s>>>(p.impl->tmA, p.impl->tmB, a); break;
+    case 1: launch_k(conv_tc_kernel<1>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
+    case 2: launch_k(conv_tc_kernel<2>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
+    case 3: launch_k(conv_tc_kernel<3>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
+    case 4: launch_k(conv_tc_kernel<4>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
+    case 5: launch_k(conv_tc_kernel<5>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
+    default: launch_k(conv_tc_kernel<0>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
   }
 }
 

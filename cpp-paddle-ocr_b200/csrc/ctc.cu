@@ -3,6 +3,7 @@
 // softmax is never materialised); this kernel applies the blank / repeat rule with warp ballots and
 // accumulates the score in time order in fp32, exactly like the reference's sequential loop.
 #include "kernels.h"
+#include "pdl.h"
 
 namespace b200ocr {
 
@@ -11,6 +12,8 @@ namespace {
 __global__ void __launch_bounds__(128)
 ctc_collapse_kernel(const int* __restrict__ idx, const float* __restrict__ prob, int n, int T,
                     int* __restrict__ out_idx, int* __restrict__ out_len, float* __restrict__ out_score) {
+  pdl_trigger();
+  pdl_wait();
   const int line = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (line >= n) return;
@@ -49,7 +52,7 @@ ctc_collapse_kernel(const int* __restrict__ idx, const float* __restrict__ prob,
 void launch_ctc_collapse(const int* idx, const float* prob, int n, int T, int* out_idx, int* out_len,
                          float* out_score, cudaStream_t s) {
   const int warps_per_block = 4;
-  ctc_collapse_kernel<<<(n + warps_per_block - 1) / warps_per_block, 128, 0, s>>>(idx, prob, n, T, out_idx, out_len,
+  launch_k(ctc_collapse_kernel, dim3((n + warps_per_block - 1) / warps_per_block), dim3(128), 0, s, idx, prob, n, T, out_idx, out_len,
                                                                                 out_score);
 }
 

@@ -9,6 +9,7 @@
 //   Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issue, 2..17 = epilogue (a token = one TMEM lane; the four
 //   warps of a lane quadrant split the column groups and merge their (max, arg-max, sum) through shared memory).
 #include "kernels.h"
+#include "pdl.h"
 
 #include <cuda.h>
 #include <cfloat>
@@ -94,6 +95,8 @@ struct CtcArgs {
 
 __global__ void __launch_bounds__(kCtcThreads)
 ctc_head_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const CtcArgs a) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* b_full = a_full + 1;           // [kStages]
@@ -292,7 +295,7 @@ void launch_ctc_head_tc(const TV& feat, const __half* w, const float* bias, int 
   a.bias = bias; a.vw = vw; a.idx = idx; a.prob = prob;
   const size_t smem = kABytes + size_t(kStages) * kBBytes + 1024 + 128;
   cudaFuncSetAttribute(ctc_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  ctc_head_tc_kernel<<<unsigned((rows + 127) / 128), kCtcThreads, smem, s>>>(tmA, tmB, a);
+  launch_k(ctc_head_tc_kernel, dim3(unsigned((rows + 127) / 128)), dim3(kCtcThreads), smem, s, tmA, tmB, a);
 }
 
 }  // namespace b200ocr

@@ -22,6 +22,7 @@
 // Verified against cv2.findContours on random bitmaps (same count, order, start pixels, pixel sets) in
 // tests/test_dbpost_gpu.py.  Integer / index work is bit-exact; box vertices agree within 1 px.
 #include "kernels.h"
+#include "pdl.h"
 #include "geom.h"
 
 #include <algorithm>
@@ -53,6 +54,8 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
 
 __global__ void __launch_bounds__(256)
 ccl_init_kernel(int* __restrict__ L, int* __restrict__ aux, long total) {
+  pdl_trigger();
+  pdl_wait();
   // aux: per pixel, zeroed: border-touch flag of background roots / contour flag of start pixels
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
     L[t] = int(t);  // global index; images never merge because neighbours are taken inside one image
@@ -62,6 +65,8 @@ ccl_init_kernel(int* __restrict__ L, int* __restrict__ aux, long total) {
 
 __global__ void __launch_bounds__(256)
 ccl_merge_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int n, int h, int w) {
+  pdl_trigger();
+  pdl_wait();
   const long per = long(h) * w, total = per * n;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
     const int r = int(t % per);
@@ -85,6 +90,8 @@ ccl_merge_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int n, int
 // contacts of the 8-connected foreground that are not already implied by a horizontal or vertical contact.
 __global__ void __launch_bounds__(256)
 ccl_runs_init_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int* __restrict__ aux, long total) {
+  pdl_trigger();
+  pdl_wait();
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
     const unsigned lane = threadIdx.x & 31;
     const unsigned mask = __ballot_sync(0xffffffffu, bm[t] != 0);
@@ -98,6 +105,8 @@ ccl_runs_init_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int* _
 
 __global__ void __launch_bounds__(256)
 ccl_runs_merge_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int n, int h, int w) {
+  pdl_trigger();
+  pdl_wait();
   const long per = long(h) * w, total = per * n;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
     const int r = int(t % per);
@@ -122,6 +131,8 @@ ccl_runs_merge_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int n
 // flatten + flag background components that touch the image frame (they are the "outside")
 __global__ void __launch_bounds__(256)
 ccl_flatten_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int* __restrict__ touch, int n, int h, int w) {
+  pdl_trigger();
+  pdl_wait();
   const long per = long(h) * w, total = per * n;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
     const int root = uf_find(L, int(t));
@@ -163,6 +174,8 @@ constexpr int kCandCap = 4096;
 
 __global__ void __launch_bounds__(256)
 slot_init_kernel(Slot s, long total) {
+  pdl_trigger();
+  pdl_wait();
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
     s.flag[t] = 0;
     s.x0[t] = 0x7fffffff; s.y0[t] = 0x7fffffff; s.x1[t] = -1; s.y1[t] = -1;
@@ -187,6 +200,8 @@ __device__ __forceinline__ unsigned long long prob_q32(float p) {
 __global__ void __launch_bounds__(256)
 nest_sum_kernel(const uint8_t* __restrict__ bm, const float* __restrict__ prob, const int* __restrict__ L,
                 const int* __restrict__ touch, Slot s, int n, int h, int w) {
+  pdl_trigger();
+  pdl_wait();
   const long per = long(h) * w, total = per * n;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
     const unsigned long long q = prob_q32(prob[t]);
@@ -219,6 +234,8 @@ nest_sum_kernel(const uint8_t* __restrict__ bm, const float* __restrict__ prob, 
 __global__ void __launch_bounds__(256)
 mark_kernel(const uint8_t* __restrict__ bm, const int* __restrict__ L, const int* __restrict__ touch, Slot s,
             int n, int h, int w, const float* __restrict__ prob) {
+  pdl_trigger();
+  pdl_wait();
   const long per = long(h) * w, total = per * n;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
     if (bm[t] == 0) continue;
@@ -268,6 +285,8 @@ mark_kernel(const uint8_t* __restrict__ bm, const int* __restrict__ L, const int
 __global__ void __launch_bounds__(1024)
 sort_candidates_kernel(const int* __restrict__ cand, const int* __restrict__ cand_n, int max_cand, int* __restrict__ counts,
                        int* __restrict__ list) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int key[kCandCap];
   const int img = blockIdx.x;
   const int n = cand_n[img];
@@ -298,6 +317,8 @@ sort_candidates_kernel(const int* __restrict__ cand, const int* __restrict__ can
 __global__ void __launch_bounds__(1024)
 list_kernel(const int* __restrict__ flag, int h, int w, int max_cand, int* __restrict__ counts, int* __restrict__ list,
             const int* __restrict__ cand_n) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int kPer = 8;
   __shared__ int warp_sums[32];
   __shared__ int base;
@@ -525,6 +546,8 @@ __global__ void __launch_bounds__(kBoxThreads)
 boxes_kernel(DbPostParams P, const float* __restrict__ prob, const uint8_t* __restrict__ bm,
              const int* __restrict__ L, const int* __restrict__ touch, Slot s, const int* __restrict__ counts,
              const int* __restrict__ list, const DbImageInfo* __restrict__ info, DbBox* __restrict__ boxes) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ int dyn[];  // rowmin[h], rowmax[h]
   const int img = blockIdx.y;
   const int cnt = counts[img];
@@ -536,6 +559,8 @@ boxes_kernel(DbPostParams P, const float* __restrict__ prob, const uint8_t* __re
 
 __global__ void __launch_bounds__(256)
 dilate2x2_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int n, int h, int w) {
+  pdl_trigger();
+  pdl_wait();
   // cv::dilate with a 2x2 rectangle, anchor (1,1): out(y,x) = max over rows y-1..y, cols x-1..x
   const long per = long(h) * w, total = per * n;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
@@ -550,6 +575,8 @@ dilate2x2_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int 
 
 __global__ void __launch_bounds__(256)
 threshold_kernel(const float* __restrict__ prob, long n, int thresh_u8, uint8_t* __restrict__ bm) {
+  pdl_trigger();
+  pdl_wait();
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < n; t += long(gridDim.x) * blockDim.x)
     bm[t] = (int((unsigned char)(prob[t] * 255.f)) > thresh_u8) ? 255 : 0;
 }
@@ -595,28 +622,28 @@ void launch_dbpost(const DbPostParams& p, const float* prob, const uint8_t* bitm
     s.cnt = reinterpret_cast<int*>(extra + al(px * 8));
   }
   const int g = grid_for(long(px));
-  if (p.w % 32 == 0) ccl_runs_init_kernel<<<g, 256, 0, st>>>(bitmap, L, touch, long(px));
-  else ccl_init_kernel<<<g, 256, 0, st>>>(L, touch, long(px));
-  slot_init_kernel<<<g, 256, 0, st>>>(s, long(px));
-  if (p.w % 32 == 0) ccl_runs_merge_kernel<<<g, 256, 0, st>>>(bitmap, L, p.n, p.h, p.w);
-  else ccl_merge_kernel<<<g, 256, 0, st>>>(bitmap, L, p.n, p.h, p.w);
-  ccl_flatten_kernel<<<g, 256, 0, st>>>(bitmap, L, touch, p.n, p.h, p.w);
-  mark_kernel<<<g, 256, 0, st>>>(bitmap, L, touch, s, p.n, p.h, p.w, prob);
-  if (p.score_slow) nest_sum_kernel<<<g, 256, 0, st>>>(bitmap, prob, L, touch, s, p.n, p.h, p.w);
-  sort_candidates_kernel<<<p.n, 1024, 0, st>>>(s.cand, s.cand_n, p.max_candidates, counts_dev, list);
-  list_kernel<<<p.n, 1024, 0, st>>>(s.flag, p.h, p.w, p.max_candidates, counts_dev, list, s.cand_n);
+  if (p.w % 32 == 0) launch_k(ccl_runs_init_kernel, dim3(g), dim3(256), 0, st, bitmap, L, touch, long(px));
+  else launch_k(ccl_init_kernel, dim3(g), dim3(256), 0, st, L, touch, long(px));
+  launch_k(slot_init_kernel, dim3(g), dim3(256), 0, st, s, long(px));
+  if (p.w % 32 == 0) launch_k(ccl_runs_merge_kernel, dim3(g), dim3(256), 0, st, bitmap, L, p.n, p.h, p.w);
+  else launch_k(ccl_merge_kernel, dim3(g), dim3(256), 0, st, bitmap, L, p.n, p.h, p.w);
+  launch_k(ccl_flatten_kernel, dim3(g), dim3(256), 0, st, bitmap, L, touch, p.n, p.h, p.w);
+  launch_k(mark_kernel, dim3(g), dim3(256), 0, st, bitmap, L, touch, s, p.n, p.h, p.w, prob);
+  if (p.score_slow) launch_k(nest_sum_kernel, dim3(g), dim3(256), 0, st, bitmap, prob, L, touch, s, p.n, p.h, p.w);
+  launch_k(sort_candidates_kernel, dim3(p.n), dim3(1024), 0, st, s.cand, s.cand_n, p.max_candidates, counts_dev, list);
+  launch_k(list_kernel, dim3(p.n), dim3(1024), 0, st, s.flag, p.h, p.w, p.max_candidates, counts_dev, list, s.cand_n);
   const size_t smem = size_t(2) * p.h * sizeof(int);
   const int per_image = std::min(p.max_candidates, std::max(16, (148 * 8 + p.n - 1) / p.n));
-  boxes_kernel<<<dim3(per_image, p.n), kBoxThreads, smem, st>>>(p, prob, bitmap, L, touch, s, counts_dev, list, info_dev,
+  launch_k(boxes_kernel, dim3(dim3(per_image, p.n)), dim3(kBoxThreads), smem, st, p, prob, bitmap, L, touch, s, counts_dev, list, info_dev,
                                                                  boxes_dev);
 }
 
 void launch_threshold(const float* prob, long n, int thresh_u8, uint8_t* bitmap, cudaStream_t s) {
-  threshold_kernel<<<grid_for(n), 256, 0, s>>>(prob, n, thresh_u8, bitmap);
+  launch_k(threshold_kernel, dim3(grid_for(n)), dim3(256), 0, s, prob, n, thresh_u8, bitmap);
 }
 
 void launch_dilate2x2(const uint8_t* in, uint8_t* out, int n, int h, int w, cudaStream_t s) {
-  dilate2x2_kernel<<<grid_for(long(n) * h * w), 256, 0, s>>>(in, out, n, h, w);
+  launch_k(dilate2x2_kernel, dim3(grid_for(long(n) * h * w)), dim3(256), 0, s, in, out, n, h, w);
 }
 
 }  // namespace b200ocr

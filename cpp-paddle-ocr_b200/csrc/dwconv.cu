@@ -17,6 +17,7 @@
 // Chunks narrower than 64 channels put several column strips into one warp; one pad pixel per strip width in the
 // shared-memory row keeps those strips on different banks.
 #include "kernels.h"
+#include "pdl.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -57,6 +58,8 @@ struct DwArgs {
 // offset becomes an immediate and the tile exactly covers R rows: no per-row tests), or 0 / -1 = taken from DwArgs.
 template <int K, int SH, int SW, int R, bool WF32, int RB_T, int WCL_T>
 __global__ void __launch_bounds__(kDwThreads, 4) dwconv_tile_kernel(const DwArgs a) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t dw_smem[];
   constexpr bool STATIC = RB_T > 0 && WCL_T >= 0;
   constexpr int WIN = (kS - 1) * SW + K;       // input columns one thread needs per row
@@ -239,7 +242,7 @@ void dw_launch(DwArgs& a, cudaStream_t s) {
     }
   }
   const long blocks = long(a.out.n) * a.tiles_y * a.tiles_x * a.chunks;
-  kern<<<unsigned(blocks), kDwThreads, smem, s>>>(a);
+  launch_k(kern, dim3(unsigned(blocks)), dim3(kDwThreads), smem, s, a);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -249,6 +252,8 @@ void dw_launch(DwArgs& a, cudaStream_t s) {
 // (cp.async) while tile i is multiplied -- the load -> barrier -> compute bubble of the one-tile-per-CTA kernel is gone.
 template <int K, int SH, int R>
 __global__ void __launch_bounds__(kDwThreads, 3) dwconv_persist_kernel(const DwArgs a, const int n_tiles) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t dw_smem[];
   constexpr int SW = 1, TW = 16, WIN = (kS - 1) * SW + K, IHR = (R - 1) * SH + K, IW = (TW - 1) * SW + K;
   constexpr uint32_t kTileBytes = IHR * IW * 128;
@@ -381,7 +386,7 @@ void dw_persist_launch(DwArgs& a, cudaStream_t s) {
   }
   const int n_tiles = a.out.n * a.tiles_x;
   const int per_chunk = std::max(1, std::min(n_tiles, (148 * 4 + a.chunks - 1) / a.chunks));
-  kern<<<dim3(unsigned(per_chunk), unsigned(a.chunks)), kDwThreads, smem, s>>>(a, n_tiles);
+  launch_k(kern, dim3(dim3(unsigned(per_chunk), unsigned(a.chunks))), dim3(kDwThreads), smem, s, a, n_tiles);
 }
 
 // fraction of the tile's lanes that hold real channels x real columns, for a chunk of 2^(l2+1) channels

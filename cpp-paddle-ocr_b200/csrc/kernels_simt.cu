@@ -3,6 +3,7 @@
 // variant).  All activations are NHWC fp16 with 16-byte (8-channel) vector access; accumulation
 // is fp32.  HBM/L2-bound kernels: one thread per (pixel, 8-channel group), coalesced along C.
 #include "kernels.h"
+#include "pdl.h"
 
 #include <algorithm>
 #include <cfloat>
@@ -95,6 +96,8 @@ __device__ __forceinline__ void epilogue8(float* acc, const float* bias, int c0,
 __global__ void __launch_bounds__(kThreads)
 conv_simt_kernel(TV in, TV out, const __half* __restrict__ w, const float* __restrict__ bias,
                  ConvGeom g, Epi e, const int* __restrict__ vw) {
+  pdl_trigger();
+  pdl_wait();
   const int cgs = (out.c + 7) >> 3;
   const long npix = long(out.n) * out.h * out.w;
   const long total = npix * cgs;
@@ -138,6 +141,8 @@ conv_simt_kernel(TV in, TV out, const __half* __restrict__ w, const float* __res
 template <int KH, int KW>
 __global__ void __launch_bounds__(kThreads)
 dwconv_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi e, const int* __restrict__ vw) {
+  pdl_trigger();
+  pdl_wait();
   const int cgs = (out.c + 7) >> 3;
   const int cp = g.cout_pad;
   const long total = long(out.n) * out.h * out.w * cgs;
@@ -196,6 +201,8 @@ template <int KH, int KW, int SW, int S>
 __global__ void __launch_bounds__(kThreads)
 dwconv_strip_kernel(TV in, TV out, const float* __restrict__ wb, const __half* __restrict__ wh, ConvGeom g, Epi e,
                     const int* __restrict__ vw) {
+  pdl_trigger();
+  pdl_wait();
   const int cgs = (out.c + 7) >> 3;
   const int cp = g.cout_pad;
   const int strips = (out.w + S - 1) / S;
@@ -264,6 +271,8 @@ dwconv_strip_kernel(TV in, TV out, const float* __restrict__ wb, const __half* _
 template <int KH, int KW, int SW, int S>
 __global__ void __launch_bounds__(kThreads)
 dwconv_strip_f32w_kernel(TV in, TV out, const float* __restrict__ wb, ConvGeom g, Epi e, const int* __restrict__ vw) {
+  pdl_trigger();
+  pdl_wait();
   const int cgs = (out.c + 7) >> 3;
   const int cp = g.cout_pad;
   const int strips = (out.w + S - 1) / S;
@@ -334,6 +343,8 @@ template <int COUT>
 __global__ void __launch_bounds__(kThreads)
 stem_conv_kernel(TV in, TV out, const __half* __restrict__ w, const float* __restrict__ bias, ConvGeom g, Epi e,
                  const int* __restrict__ vw) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sw[9 * 3 * COUT];
   __shared__ float sb[COUT];
   for (int i = threadIdx.x; i < 9 * 3 * COUT; i += blockDim.x) {
@@ -410,6 +421,8 @@ template <int COUT, int PX>
 __global__ void __launch_bounds__(128, PX == 4 ? 3 : 4)
 stem_conv_s2x4_kernel(TV in, TV out, const __half* __restrict__ w, const float* __restrict__ bias, ConvGeom g, Epi e,
                       const int* __restrict__ vw) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) float sw[9 * 3 * COUT];
   __shared__ float sb[COUT];
   for (int i = threadIdx.x; i < 9 * 3 * COUT; i += blockDim.x) {
@@ -579,6 +592,8 @@ __device__ __forceinline__ void gap_partial_body(TV in, float* __restrict__ part
 
 __global__ void __launch_bounds__(kThreads)
 gap_partial_kernel(TV in, float* __restrict__ partial, int splits, int cbs, int cbw) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   gap_partial_body(in, partial, splits, cbs, cbw, sm);
 }
@@ -799,6 +814,8 @@ __global__ void __launch_bounds__(kThreads)
 se_fc_kernel(const float* __restrict__ partial, int splits, float inv_hw0, int n_total, int c, int cmid,
              const float* __restrict__ blk, float slope, float offset, float* __restrict__ gate,
              const int* __restrict__ vw_in, int h) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   se_fc_body<kSeSamples>(sm, partial, splits, inv_hw0, blockIdx.x * kSeSamples, n_total, c, cmid, blk, slope, offset, gate,
                          vw_in, h);
@@ -810,6 +827,8 @@ se_fc_kernel(const float* __restrict__ partial, int splits, float inv_hw0, int n
 // one block, so the result does not depend on which block came last.
 __global__ void __launch_bounds__(kThreads)
 gap_se_kernel(TV in, float* __restrict__ partial, int splits, int cbs, int cbw, SeFuse fc) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   __shared__ int s_last;
   gap_partial_body(in, partial, splits, cbs, cbw, sm);
@@ -831,6 +850,8 @@ gap_se_kernel(TV in, float* __restrict__ partial, int splits, int cbs, int cbw, 
 
 __global__ void __launch_bounds__(kThreads)
 scale_kernel(TV in, const float* __restrict__ gate, int add_x, TV out) {
+  pdl_trigger();
+  pdl_wait();
   const int cgs = (in.c + 7) >> 3;
   const int cp = cgs * 8;
   const long hw = long(in.h) * in.w;
@@ -854,6 +875,8 @@ scale_kernel(TV in, const float* __restrict__ gate, int add_x, TV out) {
 
 // ---------------------------------------------------------------- glue
 __global__ void __launch_bounds__(kThreads) upadd_kernel(TV a, TV b, TV out) {
+  pdl_trigger();
+  pdl_wait();
   const int cgs = (a.c + 7) >> 3;
   const long total = long(a.n) * a.h * a.w * cgs;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
@@ -879,6 +902,8 @@ struct UpCatArgs {
 };
 
 __global__ void __launch_bounds__(kThreads) upcat_kernel(UpCatArgs a, TV out) {
+  pdl_trigger();
+  pdl_wait();
   const int cgs = (out.c + 7) >> 3;
   const long total = long(out.n) * out.h * out.w * cgs;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
@@ -898,6 +923,8 @@ __global__ void __launch_bounds__(kThreads) upcat_kernel(UpCatArgs a, TV out) {
 }
 
 __global__ void __launch_bounds__(kThreads) add_kernel(TV a, TV b, TV out) {
+  pdl_trigger();
+  pdl_wait();
   const int cgs = (a.c + 7) >> 3;
   const long total = long(a.n) * a.h * a.w * cgs;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
@@ -917,6 +944,8 @@ __global__ void __launch_bounds__(kThreads) add_kernel(TV a, TV b, TV out) {
 // windows are clipped to the input; avg divides by the clipped size (Paddle exclusive=true)
 __global__ void __launch_bounds__(kThreads)
 pool_kernel(TV in, TV out, int kh, int kw, int sh, int sw, int is_max, const int* __restrict__ vw) {
+  pdl_trigger();
+  pdl_wait();
   const int cgs = (in.c + 7) >> 3;
   const long total = long(out.n) * out.h * out.w * cgs;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
@@ -984,6 +1013,8 @@ constexpr int kLnTok = 4;
 template <int LPT>
 __global__ void __launch_bounds__(kThreads)
 layernorm_kernel(TV in, TV out, const float* __restrict__ gb, float eps, const int* __restrict__ vw) {
+  pdl_trigger();
+  pdl_wait();
   const long rows = long(in.n) * in.h * in.w;
   const int lane = threadIdx.x % LPT;
   const long group = (blockIdx.x * long(blockDim.x) + threadIdx.x) / LPT;
@@ -1046,6 +1077,8 @@ layernorm_kernel(TV in, TV out, const float* __restrict__ gb, float eps, const i
 // smem: K[T][d], V[T][d], P[warps][T]
 __global__ void __launch_bounds__(128)
 attention_kernel(TV qkv, TV out, int heads, int hd, float scale, const int* __restrict__ vw) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int Tfull = qkv.h * qkv.w;
   const int n = blockIdx.x / heads, head = blockIdx.x % heads;
@@ -1106,6 +1139,8 @@ template <int CIN, int CMID>
 __global__ void __launch_bounds__(128, 4)
 dbhead_kernel(TV in, const float* __restrict__ blk, float* __restrict__ prob,
               uint8_t* __restrict__ bitmap, int thresh_u8) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sw1[4 * CIN * CMID];
   __shared__ float sb1[CMID];
   __shared__ float sw2[CMID * 4];
@@ -1165,6 +1200,8 @@ dbhead_kernel(TV in, const float* __restrict__ blk, float* __restrict__ prob,
 // blk: w[cin][cout], b[cout]; one warp per image
 __global__ void fc_softmax_kernel(const float* __restrict__ partial, int splits, float inv_hw, int cin,
                                   int cout, const float* __restrict__ blk, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.x, lane = threadIdx.x;
   const int cp = (cin + 7) / 8 * 8;
   float logit[8];
@@ -1192,6 +1229,8 @@ __global__ void fc_softmax_kernel(const float* __restrict__ partial, int splits,
 __global__ void __launch_bounds__(kThreads)
 ctc_head_simt_kernel(TV feat, const __half* __restrict__ w, const float* __restrict__ bias, int cin_pad,
                      int ncls_pad, int* __restrict__ idx, float* __restrict__ prob, const int* __restrict__ vw) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int ROWS = 8;
   extern __shared__ float sm[];  // feat[ROWS][cin_pad]
   const long rows = long(feat.n) * feat.h * feat.w;
@@ -1267,6 +1306,8 @@ ctc_head_simt_kernel(TV feat, const __half* __restrict__ w, const float* __restr
 }
 
 __global__ void __launch_bounds__(kThreads) nhwc_to_nchw_f32_kernel(TV in, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long total = long(in.n) * in.c * in.h * in.w;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
     const int x = int(t % in.w);
@@ -1279,6 +1320,8 @@ __global__ void __launch_bounds__(kThreads) nhwc_to_nchw_f32_kernel(TV in, float
 
 __global__ void __launch_bounds__(kThreads)
 nchw3_to_input_kernel(const float* __restrict__ in, int n, int h, int w, __half* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long total = long(n) * h * w;
   const long hw = long(h) * w;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
@@ -1304,19 +1347,19 @@ void launch_conv_simt(const TV& in, const TV& out, const __half* w, const float*
     if (g.sh == 2 && g.sw == 2 && out.w >= 8 && e.act >= 0 && e.act <= 2 && !getenv("B200OCR_OLD_STEM")) {
       static const int px = getenv("B200OCR_STEM_PX") ? atoi(getenv("B200OCR_STEM_PX")) : 2;
       const int sg = grid_for(long(out.n) * out.h * ((out.w + px - 1) / px), 128);
-      if (out.c == 16 && px == 4) stem_conv_s2x4_kernel<16, 4><<<sg, 128, 0, s>>>(in, out, w, bias, g, e, vw);
-      else if (out.c == 16) stem_conv_s2x4_kernel<16, 2><<<sg, 128, 0, s>>>(in, out, w, bias, g, e, vw);
-      else if (px == 4) stem_conv_s2x4_kernel<8, 4><<<sg, 128, 0, s>>>(in, out, w, bias, g, e, vw);
-      else stem_conv_s2x4_kernel<8, 2><<<sg, 128, 0, s>>>(in, out, w, bias, g, e, vw);
+      if (out.c == 16 && px == 4) launch_k(stem_conv_s2x4_kernel<16, 4>, dim3(sg), dim3(128), 0, s, in, out, w, bias, g, e, vw);
+      else if (out.c == 16) launch_k(stem_conv_s2x4_kernel<16, 2>, dim3(sg), dim3(128), 0, s, in, out, w, bias, g, e, vw);
+      else if (px == 4) launch_k(stem_conv_s2x4_kernel<8, 4>, dim3(sg), dim3(128), 0, s, in, out, w, bias, g, e, vw);
+      else launch_k(stem_conv_s2x4_kernel<8, 2>, dim3(sg), dim3(128), 0, s, in, out, w, bias, g, e, vw);
       return;
     }
     const int grid = grid_for(long(out.n) * out.h * out.w);
-    if (out.c == 16) stem_conv_kernel<16><<<grid, kThreads, 0, s>>>(in, out, w, bias, g, e, vw);
-    else stem_conv_kernel<8><<<grid, kThreads, 0, s>>>(in, out, w, bias, g, e, vw);
+    if (out.c == 16) launch_k(stem_conv_kernel<16>, dim3(grid), dim3(kThreads), 0, s, in, out, w, bias, g, e, vw);
+    else launch_k(stem_conv_kernel<8>, dim3(grid), dim3(kThreads), 0, s, in, out, w, bias, g, e, vw);
     return;
   }
   const long total = long(out.n) * out.h * out.w * ((out.c + 7) / 8);
-  conv_simt_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, w, bias, g, e, vw);
+  launch_k(conv_simt_kernel, dim3(grid_for(total)), dim3(kThreads), 0, s, in, out, w, bias, g, e, vw);
 }
 
 void launch_dwconv(const TV& in, const TV& out, const float* wb, const __half* wh, const ConvGeom& g, const Epi& e,
@@ -1328,22 +1371,22 @@ void launch_dwconv(const TV& in, const TV& out, const float* wb, const __half* w
     const long st = long(out.n) * out.h * ((out.w + S - 1) / S) * ((out.c + 7) / 8);
     const int sg = grid_for(st);
     if (out.w >= 2 * S && e.res == nullptr && wh == nullptr) {
-      if (g.kh == 3 && g.kw == 3 && g.sw == 1) { dwconv_strip_f32w_kernel<3, 3, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
-      if (g.kh == 3 && g.kw == 3 && g.sw == 2) { dwconv_strip_f32w_kernel<3, 3, 2, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
-      if (g.kh == 5 && g.kw == 5 && g.sw == 1) { dwconv_strip_f32w_kernel<5, 5, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
-      if (g.kh == 5 && g.kw == 5 && g.sw == 2) { dwconv_strip_f32w_kernel<5, 5, 2, S><<<sg, kThreads, 0, s>>>(in, out, wb, g, e, vw); return; }
+      if (g.kh == 3 && g.kw == 3 && g.sw == 1) { launch_k(dwconv_strip_f32w_kernel<3, 3, 1, S>, dim3(sg), dim3(kThreads), 0, s, in, out, wb, g, e, vw); return; }
+      if (g.kh == 3 && g.kw == 3 && g.sw == 2) { launch_k(dwconv_strip_f32w_kernel<3, 3, 2, S>, dim3(sg), dim3(kThreads), 0, s, in, out, wb, g, e, vw); return; }
+      if (g.kh == 5 && g.kw == 5 && g.sw == 1) { launch_k(dwconv_strip_f32w_kernel<5, 5, 1, S>, dim3(sg), dim3(kThreads), 0, s, in, out, wb, g, e, vw); return; }
+      if (g.kh == 5 && g.kw == 5 && g.sw == 2) { launch_k(dwconv_strip_f32w_kernel<5, 5, 2, S>, dim3(sg), dim3(kThreads), 0, s, in, out, wb, g, e, vw); return; }
     }
     if (out.w >= 2 * S && e.res == nullptr && wh != nullptr) {
-      if (g.kh == 3 && g.kw == 3 && g.sw == 1) { dwconv_strip_kernel<3, 3, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, wh, g, e, vw); return; }
-      if (g.kh == 3 && g.kw == 3 && g.sw == 2) { dwconv_strip_kernel<3, 3, 2, S><<<sg, kThreads, 0, s>>>(in, out, wb, wh, g, e, vw); return; }
-      if (g.kh == 5 && g.kw == 5 && g.sw == 1) { dwconv_strip_kernel<5, 5, 1, S><<<sg, kThreads, 0, s>>>(in, out, wb, wh, g, e, vw); return; }
-      if (g.kh == 5 && g.kw == 5 && g.sw == 2) { dwconv_strip_kernel<5, 5, 2, S><<<sg, kThreads, 0, s>>>(in, out, wb, wh, g, e, vw); return; }
+      if (g.kh == 3 && g.kw == 3 && g.sw == 1) { launch_k(dwconv_strip_kernel<3, 3, 1, S>, dim3(sg), dim3(kThreads), 0, s, in, out, wb, wh, g, e, vw); return; }
+      if (g.kh == 3 && g.kw == 3 && g.sw == 2) { launch_k(dwconv_strip_kernel<3, 3, 2, S>, dim3(sg), dim3(kThreads), 0, s, in, out, wb, wh, g, e, vw); return; }
+      if (g.kh == 5 && g.kw == 5 && g.sw == 1) { launch_k(dwconv_strip_kernel<5, 5, 1, S>, dim3(sg), dim3(kThreads), 0, s, in, out, wb, wh, g, e, vw); return; }
+      if (g.kh == 5 && g.kw == 5 && g.sw == 2) { launch_k(dwconv_strip_kernel<5, 5, 2, S>, dim3(sg), dim3(kThreads), 0, s, in, out, wb, wh, g, e, vw); return; }
     }
   }
   const long total = long(out.n) * out.h * out.w * ((out.c + 7) / 8);
   const int grid = grid_for(total);
-  if (g.kh == 3 && g.kw == 3) dwconv_kernel<3, 3><<<grid, kThreads, 0, s>>>(in, out, wb, g, e, vw);
-  else if (g.kh == 5 && g.kw == 5) dwconv_kernel<5, 5><<<grid, kThreads, 0, s>>>(in, out, wb, g, e, vw);
+  if (g.kh == 3 && g.kw == 3) launch_k(dwconv_kernel<3, 3>, dim3(grid), dim3(kThreads), 0, s, in, out, wb, g, e, vw);
+  else if (g.kh == 5 && g.kw == 5) launch_k(dwconv_kernel<5, 5>, dim3(grid), dim3(kThreads), 0, s, in, out, wb, g, e, vw);
   else throw std::runtime_error("depthwise convolution: only 3x3 and 5x5 filters are implemented");
 }
 
@@ -1385,10 +1428,10 @@ void launch_gap_partial(const TV& in, float* partial, int splits, bool ragged_sa
   size_t smem = std::max(size_t(lanes) * cgs * 8 * sizeof(float), size_t(kGapStages) * kThreads * 16);
   if (fuse) {
     smem = std::max(smem, se_fc_smem_floats(1, cgs * 8, fuse->cmid) * sizeof(float));
-    gap_se_kernel<<<dim3(splits, in.n), kThreads, smem, s>>>(in, partial, splits, cbs, cbw, *fuse);
+    launch_k(gap_se_kernel, dim3(dim3(splits, in.n)), dim3(kThreads), smem, s, in, partial, splits, cbs, cbw, *fuse);
     return;
   }
-  gap_partial_kernel<<<dim3(splits, in.n), kThreads, smem, s>>>(in, partial, splits, cbs, cbw);
+  launch_k(gap_partial_kernel, dim3(dim3(splits, in.n)), dim3(kThreads), smem, s, in, partial, splits, cbs, cbw);
 }
 
 void launch_se_fc(const float* partial, int splits, int hw, int n, int c, int cmid, const float* blk,
@@ -1398,19 +1441,19 @@ void launch_se_fc(const float* partial, int splits, int hw, int n, int c, int cm
   const int S = n >= 4 * 148 ? 4 : (n >= 2 * 148 ? 2 : 1);
   const size_t smem = se_fc_smem_floats(S, cp, cmid) * sizeof(float);
   const float inv = 1.f / float(hw);
-  if (S == 4) se_fc_kernel<4><<<(n + 3) / 4, kThreads, smem, s>>>(partial, splits, inv, n, c, cmid, blk, slope, offset, gate, vw_in, h);
-  else if (S == 2) se_fc_kernel<2><<<(n + 1) / 2, kThreads, smem, s>>>(partial, splits, inv, n, c, cmid, blk, slope, offset, gate, vw_in, h);
-  else se_fc_kernel<1><<<n, kThreads, smem, s>>>(partial, splits, inv, n, c, cmid, blk, slope, offset, gate, vw_in, h);
+  if (S == 4) launch_k(se_fc_kernel<4>, dim3((n + 3) / 4), dim3(kThreads), smem, s, partial, splits, inv, n, c, cmid, blk, slope, offset, gate, vw_in, h);
+  else if (S == 2) launch_k(se_fc_kernel<2>, dim3((n + 1) / 2), dim3(kThreads), smem, s, partial, splits, inv, n, c, cmid, blk, slope, offset, gate, vw_in, h);
+  else launch_k(se_fc_kernel<1>, dim3(n), dim3(kThreads), smem, s, partial, splits, inv, n, c, cmid, blk, slope, offset, gate, vw_in, h);
 }
 
 void launch_scale(const TV& in, const float* gate, bool add_x, const TV& out, cudaStream_t s) {
   const long total = long(in.n) * in.h * in.w * ((in.c + 7) / 8);
-  scale_kernel<<<grid_for(total), kThreads, 0, s>>>(in, gate, add_x ? 1 : 0, out);
+  launch_k(scale_kernel, dim3(grid_for(total)), dim3(kThreads), 0, s, in, gate, add_x ? 1 : 0, out);
 }
 
 void launch_upadd(const TV& a, const TV& b, const TV& out, cudaStream_t s) {
   const long total = long(a.n) * a.h * a.w * ((a.c + 7) / 8);
-  upadd_kernel<<<grid_for(total), kThreads, 0, s>>>(a, b, out);
+  launch_k(upadd_kernel, dim3(grid_for(total)), dim3(kThreads), 0, s, a, b, out);
 }
 
 void launch_upcat(const TV in[4], const int shift[4], int nin, const TV& out, cudaStream_t s) {
@@ -1424,25 +1467,25 @@ void launch_upcat(const TV in[4], const int shift[4], int nin, const TV& out, cu
   }
   a.nin = nin;
   const long total = long(out.n) * out.h * out.w * ((out.c + 7) / 8);
-  upcat_kernel<<<grid_for(total), kThreads, 0, s>>>(a, out);
+  launch_k(upcat_kernel, dim3(grid_for(total)), dim3(kThreads), 0, s, a, out);
 }
 
 void launch_add(const TV& a, const TV& b, const TV& out, cudaStream_t s) {
   const long total = long(a.n) * a.h * a.w * ((a.c + 7) / 8);
-  add_kernel<<<grid_for(total), kThreads, 0, s>>>(a, b, out);
+  launch_k(add_kernel, dim3(grid_for(total)), dim3(kThreads), 0, s, a, b, out);
 }
 
 void launch_pool(const TV& in, const TV& out, int kh, int kw, int sh, int sw, bool is_max, cudaStream_t s,
                  const int* vw) {
   const long total = long(out.n) * out.h * out.w * ((out.c + 7) / 8);
-  pool_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, kh, kw, sh, sw, is_max ? 1 : 0, vw);
+  launch_k(pool_kernel, dim3(grid_for(total)), dim3(kThreads), 0, s, in, out, kh, kw, sh, sw, is_max ? 1 : 0, vw);
 }
 
 void launch_layernorm(const TV& in, const TV& out, const float* gb, float eps, cudaStream_t s, const int* vw) {
   const long rows = long(in.n) * in.h * in.w;
   const long groups = (rows + kLnTok - 1) / kLnTok;
-  if (in.c <= 128) layernorm_kernel<16><<<int((groups * 16 + kThreads - 1) / kThreads), kThreads, 0, s>>>(in, out, gb, eps, vw);
-  else layernorm_kernel<32><<<int((groups * 32 + kThreads - 1) / kThreads), kThreads, 0, s>>>(in, out, gb, eps, vw);
+  if (in.c <= 128) launch_k(layernorm_kernel<16>, dim3(int((groups * 16 + kThreads - 1) / kThreads)), dim3(kThreads), 0, s, in, out, gb, eps, vw);
+  else launch_k(layernorm_kernel<32>, dim3(int((groups * 32 + kThreads - 1) / kThreads)), dim3(kThreads), 0, s, in, out, gb, eps, vw);
 }
 
 void launch_attention(const TV& qkv, const TV& out, int heads, int hd, float scale, cudaStream_t s, const int* vw) {
@@ -1461,7 +1504,7 @@ void launch_attention(const TV& qkv, const TV& out, int heads, int hd, float sca
       throw std::runtime_error("attention: cannot opt in to " + std::to_string(smem) + " bytes of shared memory");
     if (dev < 64) configured[dev] = smem;
   }
-  attention_kernel<<<qkv.n * heads, 128, smem, s>>>(qkv, out, heads, hd, scale, vw);
+  launch_k(attention_kernel, dim3(qkv.n * heads), dim3(128), smem, s, qkv, out, heads, hd, scale, vw);
   if (cudaPeekAtLastError() != cudaSuccess)
     throw std::runtime_error(std::string("attention launch: ") + cudaGetErrorString(cudaGetLastError()));
 }
@@ -1470,30 +1513,30 @@ void launch_dbhead(const TV& in, const float* blk, int cmid, float* prob, uint8_
                    cudaStream_t s) {
   const long npix = long(in.n) * in.h * in.w;
   if (in.c != 24 || cmid != 24) throw std::runtime_error("DB head: only the 24 -> 24 -> 1 head of the shipped det graph is implemented");
-  dbhead_kernel<24, 24><<<int((npix + 127) / 128), 128, 0, s>>>(in, blk, prob, bitmap, thresh_u8);
+  launch_k(dbhead_kernel<24, 24>, dim3(int((npix + 127) / 128)), dim3(128), 0, s, in, blk, prob, bitmap, thresh_u8);
 }
 
 void launch_fc_softmax(const float* partial, int splits, int hw, int n, int cin, int cout, const float* blk,
                        float* out, cudaStream_t s) {
   if (cout > 8) throw std::runtime_error("cls head: at most 8 classes");
-  fc_softmax_kernel<<<n, 32, 0, s>>>(partial, splits, 1.f / float(hw), cin, cout, blk, out);
+  launch_k(fc_softmax_kernel, dim3(n), dim3(32), 0, s, partial, splits, 1.f / float(hw), cin, cout, blk, out);
 }
 
 void launch_ctc_head_simt(const TV& feat, const __half* w, const float* bias, int cin_pad, int ncls,
                           int ncls_pad, int* idx, float* prob, cudaStream_t s, const int* vw) {
   (void)ncls;
   const long rows = long(feat.n) * feat.h * feat.w;
-  ctc_head_simt_kernel<<<int((rows + 7) / 8), kThreads, size_t(8) * cin_pad * sizeof(float), s>>>(
+  launch_k(ctc_head_simt_kernel, dim3(int((rows + 7) / 8)), dim3(kThreads), size_t(8) * cin_pad * sizeof(float), s, 
       feat, w, bias, cin_pad, ncls_pad, idx, prob, vw);
 }
 
 void launch_nchw3_to_input(const float* in, int n, int h, int w, __half* out, cudaStream_t s) {
-  nchw3_to_input_kernel<<<grid_for(long(n) * h * w), kThreads, 0, s>>>(in, n, h, w, out);
+  launch_k(nchw3_to_input_kernel, dim3(grid_for(long(n) * h * w)), dim3(kThreads), 0, s, in, n, h, w, out);
 }
 
 void launch_nhwc_to_nchw_f32(const TV& in, float* out, cudaStream_t s) {
   const long total = long(in.n) * in.c * in.h * in.w;
-  nhwc_to_nchw_f32_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out);
+  launch_k(nhwc_to_nchw_f32_kernel, dim3(grid_for(total)), dim3(kThreads), 0, s, in, out);
 }
 
 }  // namespace b200ocr

@@ -13,6 +13,7 @@
 // to cv2.resize (tests/test_preproc_gpu.py).  HBM-bound: every source byte is read once (neighbouring
 // threads share rows through L1), every output pixel is one 16-byte store.
 #include "kernels.h"
+#include "pdl.h"
 
 namespace b200ocr {
 
@@ -105,6 +106,8 @@ __device__ __forceinline__ void store_px(__half* out, long pix, float a, float b
 __global__ void __launch_bounds__(kThreads)
 det_preprocess_kernel(const DetPreItem* __restrict__ items, int n, int dh, int dw, NormParams np,
                       __half* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long per = long(dh) * dw;
   const long total = per * n;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
@@ -123,6 +126,8 @@ det_preprocess_kernel(const DetPreItem* __restrict__ items, int n, int dh, int d
 __global__ void __launch_bounds__(kThreads)
 crop_preprocess_kernel(const CropItem* __restrict__ items, int n, int dh, int dw, NormParams np, float pad_value,
                        __half* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long per = long(dh) * dw;
   const long total = per * n;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
@@ -146,6 +151,8 @@ crop_preprocess_kernel(const CropItem* __restrict__ items, int n, int dh, int dw
 // In-place 180 degree rotation of one ROI, executed only when *label == 1.
 __global__ void __launch_bounds__(kThreads)
 rotate180_kernel(uint8_t* __restrict__ img, long stride, int x0, int y0, int w, int h, const int* __restrict__ label) {
+  pdl_trigger();
+  pdl_wait();
   if (*label != 1) return;
   const long total = long(w) * h;
   const long half = total / 2;
@@ -163,6 +170,8 @@ rotate180_kernel(uint8_t* __restrict__ img, long stride, int x0, int y0, int w, 
 // Plain resized 8-bit image (test hook for the fixed-point resize; also used by the warp path tests).
 __global__ void __launch_bounds__(kThreads)
 resize_u8_kernel(const uint8_t* __restrict__ src, int sw, int sh, long stride, int dw, int dh, uint8_t* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long total = long(dw) * dh;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
     const int dy = int(t / dw), dx = int(t - long(dy) * dw);
@@ -192,21 +201,21 @@ NormParams make_norm(const float mean[3], const float scale[3]) {
 
 void launch_det_preprocess(const DetPreItem* items_dev, int n, int dh, int dw, const NormParams& np, __half* out,
                            cudaStream_t s) {
-  det_preprocess_kernel<<<grid_for(long(n) * dh * dw), kThreads, 0, s>>>(items_dev, n, dh, dw, np, out);
+  launch_k(det_preprocess_kernel, dim3(grid_for(long(n) * dh * dw)), dim3(kThreads), 0, s, items_dev, n, dh, dw, np, out);
 }
 
 void launch_crop_preprocess(const CropItem* items_dev, int n, int dh, int dw, const NormParams& np, float pad_value,
                             __half* out, cudaStream_t s) {
-  crop_preprocess_kernel<<<grid_for(long(n) * dh * dw), kThreads, 0, s>>>(items_dev, n, dh, dw, np, pad_value, out);
+  launch_k(crop_preprocess_kernel, dim3(grid_for(long(n) * dh * dw)), dim3(kThreads), 0, s, items_dev, n, dh, dw, np, pad_value, out);
 }
 
 void launch_rotate180_if(uint8_t* img, long stride, int x0, int y0, int w, int h, const int* label_dev,
                          cudaStream_t s) {
-  rotate180_kernel<<<grid_for(long(w) * h / 2 + 1), kThreads, 0, s>>>(img, stride, x0, y0, w, h, label_dev);
+  launch_k(rotate180_kernel, dim3(grid_for(long(w) * h / 2 + 1)), dim3(kThreads), 0, s, img, stride, x0, y0, w, h, label_dev);
 }
 
 void launch_resize_u8(const uint8_t* src, int sw, int sh, long stride, int dw, int dh, uint8_t* out, cudaStream_t s) {
-  resize_u8_kernel<<<grid_for(long(dw) * dh), kThreads, 0, s>>>(src, sw, sh, stride, dw, dh, out);
+  launch_k(resize_u8_kernel, dim3(grid_for(long(dw) * dh)), dim3(kThreads), 0, s, src, sw, sh, stride, dw, dh, out);
 }
 
 }  // namespace b200ocr

@@ -12,6 +12,7 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "pdl.h"
 
 namespace b200ocr {
 namespace {
@@ -56,6 +57,8 @@ template <int K8, int TILES, int ACT>
 __global__ void __launch_bounds__(kPwThreads)
 pwconv_mma_kernel(const TV in, const TV out, const __half* __restrict__ w, const int w_stride,
                   const float* __restrict__ bias, const Epi e, const int* __restrict__ vw, const long npix) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t pw_smem[];
   constexpr int WS = K8 * 8 + 8;  // shared filter row stride (halves): rows 4 banks apart -> conflict-free b fragments
   const int nt = out.pitch >> 3;  // 8-channel output tiles
@@ -174,10 +177,10 @@ void pw_launch(const TV& in, const TV& out, const __half* w, int w_stride, const
   const long ntile = (npix + 15) / 16;
   const long want = (ntile + long(kPwWarps) * TILES - 1) / (long(kPwWarps) * TILES);
   const int grid = int(std::max<long>(1, std::min<long>(want, 148 * 2)));
-  if (e.act == 0) pwconv_mma_kernel<K8, TILES, 0><<<grid, kPwThreads, smem, s>>>(in, out, w, w_stride, bias, e, vw, npix);
-  else if (e.act == 1) pwconv_mma_kernel<K8, TILES, 1><<<grid, kPwThreads, smem, s>>>(in, out, w, w_stride, bias, e, vw, npix);
-  else if (e.act == 2) pwconv_mma_kernel<K8, TILES, 2><<<grid, kPwThreads, smem, s>>>(in, out, w, w_stride, bias, e, vw, npix);
-  else pwconv_mma_kernel<K8, TILES, -1><<<grid, kPwThreads, smem, s>>>(in, out, w, w_stride, bias, e, vw, npix);
+  if (e.act == 0) launch_k(pwconv_mma_kernel<K8, TILES, 0>, dim3(grid), dim3(kPwThreads), smem, s, in, out, w, w_stride, bias, e, vw, npix);
+  else if (e.act == 1) launch_k(pwconv_mma_kernel<K8, TILES, 1>, dim3(grid), dim3(kPwThreads), smem, s, in, out, w, w_stride, bias, e, vw, npix);
+  else if (e.act == 2) launch_k(pwconv_mma_kernel<K8, TILES, 2>, dim3(grid), dim3(kPwThreads), smem, s, in, out, w, w_stride, bias, e, vw, npix);
+  else launch_k(pwconv_mma_kernel<K8, TILES, -1>, dim3(grid), dim3(kPwThreads), smem, s, in, out, w, w_stride, bias, e, vw, npix);
 }
 
 }  // namespace
