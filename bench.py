@@ -464,6 +464,90 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------- in-process pool
+def run_pool(args):
+    """One process, one b200ocr_pool over --gpus devices (what replaces the reference's GPUWorkerPool,
+    src/gpu_worker_pool.cpp:8-59): feeder threads submit C4 cards (raw pixels, then JPEG-encoded) and collect the result
+    lines.  Wall clock around the timed stream (the pool's streams are its own; there is no single stream to put CUDA
+    events on), every device synchronised on both sides."""
+    import cv2
+    import numpy as np
+    import torch
+    import b200ocr
+    import make_synth_weights
+    models = make_synth_weights.ensure_models()
+    N = args.gpus
+    if b200ocr.device_count() < N:
+        raise SystemExit(f"--pool --gpus {N}: only {b200ocr.device_count()} devices visible")
+    B, K, W = (args.batch or 64), args.steps, args.warmup
+    cores = len(os.sched_getaffinity(0))
+    wpd = args.workers if args.workers > 0 else min(3, max(1, cores // N))
+    pool = b200ocr.Pool(models, devices=tuple(range(N)), workers_per_device=wpd, enable_cls=True, max_batch=max(8, B // wpd))
+    n_warm, n_timed = W * N * B, K * N * B
+    t0 = time.perf_counter()
+    imgs = make_inputs("c4", n_warm + n_timed, 9_000_000, pinned=False)
+    gen_s = time.perf_counter() - t0
+    n_feed = max(1, min(cores - N * wpd // 2, 2 * N, 16))
+
+    def stream(submit, items, first_id):
+        """n_feed threads: thread f submits items f, f + n_feed, ... keeping at most `window` of its requests in flight"""
+        window = max(4, 2 * N * B // n_feed)
+        words = [0] * n_feed
+        fails = [0] * n_feed
+        def body(f):
+            pending = []
+            for i in range(f, len(items), n_feed):
+                pending.append(submit(first_id + i, items[i]))
+                if len(pending) >= window:
+                    line = pool.wait(pending.pop(0))
+                    words[f] += line.count('"text"'); fails[f] += '"success":true' not in line
+            for t in pending:
+                line = pool.wait(t)
+                words[f] += line.count('"text"'); fails[f] += '"success":true' not in line
+        ts = [threading.Thread(target=body, args=(f,)) for f in range(n_feed)]
+        for t in ts: t.start()
+        for t in ts: t.join()
+        return sum(words), sum(fails)
+
+    def sync_all():
+        for d in range(N):
+            torch.cuda.synchronize(d)
+
+    def measure(submit, items):
+        stream(submit, items[:n_warm], 0)
+        stream(submit, items[:n_warm], 0)   # second pass: arenas / staging buffers at their working size
+        sync_all()
+        t0 = time.perf_counter()
+        words, fails = stream(submit, items[n_warm:], n_warm)
+        sync_all()
+        dt = time.perf_counter() - t0
+        return n_timed / dt, dt, words, fails
+
+    sampler = ClockSampler(0)
+    raw_rate, raw_s, words, fails = measure(pool.submit, imgs)
+    clocks = sampler.stop()
+    files = [cv2.imencode(".jpg", im, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes() for im in imgs]
+    enc_rate, enc_s, words_e, fails_e = measure(pool.submit_encoded, files)
+    status = pool.status()
+    out = {"metric": METRIC, "value": raw_rate, "unit": UNIT, "n_gpus": N, "steps": K, "warmup": W,
+           "ms_per_step": raw_s / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+           "data": "synthetic",
+           "config": {"workload": CONFIGS["c4"]["workload"], "name": "c4", "mode": "pool: ONE process, b200ocr_pool over all devices, "
+                      f"{n_feed} feeder threads, wall clock", "units_per_gpu_per_step": B, "workers_per_gpu": wpd, "enable_cls": True,
+                      "words_per_unit": words / n_timed, "failed": fails + fails_e, "weights": WEIGHTS,
+                      "inputs": f"distinct: {n_warm + n_timed} cards, {gen_s:.1f} s to render", "host_cores": cores,
+                      "stage_ms_per_image": status.get("stage_ms_per_image")},
+           "clocks": clocks,
+           "e2e": {"value": raw_rate, "unit": UNIT, "h2d_bytes_per_step": int(imgs[0].nbytes) * N * B, "d2h_bytes_per_step": None,
+                   "ms_per_step": raw_s / K * 1e3},
+           "e2e_encoded": {"value": enc_rate, "unit": UNIT, "input": "JPEG quality 90, decoded on the device",
+                           "bytes_per_step": int(sum(len(f) for f in files[n_warm:]) / K), "ms_per_step": enc_s / K * 1e3,
+                           "words_per_unit": words_e / n_timed},
+           "gpu_launches": None}
+    print(json.dumps(out))
+    pool.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -477,6 +561,8 @@ def main():
     ap.add_argument("--e2e-workers", type=int, default=0,
                     help="handles per GPU in the host-buffer (e2e) measurement; 0 = same rule")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pool", action="store_true",
+                    help="measure the in-process multi-GPU pool (b200ocr_pool_*) instead of one process per GPU: run WITHOUT torchrun")
     ap.add_argument("--cpu-units", type=int, default=0, help="size of the cpu_baseline sample; 0 = the configuration's default")
     ap.add_argument("--ref-units", type=int, default=0, help="units per step of the reference arm; 0 = the configuration's default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -485,6 +571,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.pool:
+        run_pool(args)
     else:
         run_ours(args)
 

@@ -4,8 +4,9 @@ The reference serves `recognize` / `status` / `shutdown` commands over a Windows
 (src/ocr_ipc_service.cpp:310-423; 1 MB request / 64 KB response limits, include/paddle_ocr/ocr_ipc_service.h:86-88).
 This module speaks the same commands, fields and error strings over a Unix stream socket, one compact JSON document
 per line in each direction (a stream socket has no message boundaries; the reference's pretty-printed envelopes would
-not survive line framing, the OCR result line itself is already compact).  Image decode is host side (cv2.imread /
-cv2.imdecode, like the reference's cv::imread / base64ToMat); the OCR itself runs on the GPU worker pool.
+not survive line framing, the OCR result line itself is already compact).  Baseline JPEG files are decoded on the GPU
+(b200ocr_pool_submit_encoded: only the encoded bytes cross PCIe); every other format goes through cv2.imdecode on the
+host like the reference's cv::imread / base64ToMat; the OCR itself runs on the GPU worker pool.
 
     python -m b200ocr.service --model-dir models --socket /tmp/b200ocr.sock --devices 0 --workers 2
 """
@@ -53,16 +54,18 @@ class Protocol:
             command = req.get("command", "") or ""
             if command == "recognize":
                 path, data = req.get("image_path", "") or "", req.get("image_data", "") or ""
-                image, error = None, ""
+                raw, error, kind = None, "", ""
                 if path:
-                    image = self._decode_path(path)
-                    if image is None or image.size == 0:
+                    kind = "path"
+                    try:
+                        with open(path, "rb") as f:
+                            raw = f.read()
+                    except OSError:
                         error = "Failed to load image from path: " + path
                 elif data:
+                    kind = "data"
                     try:
-                        image = self._decode_bytes(base64.b64decode(data, validate=True))
-                        if image is None or image.size == 0:
-                            error = "Failed to decode base64 image data"
+                        raw = base64.b64decode(data, validate=True)
                     except Exception as e:  # noqa: BLE001 (the reference catches std::exception here)
                         error = "Base64 decode error: " + str(e)
                 else:
@@ -72,6 +75,16 @@ class Protocol:
                 with self._lock:
                     rid = self._next_id
                     self._next_id += 1
+                # Device decode first: only the file's bytes cross PCIe (b200ocr_pool_submit_encoded; baseline JPEG).
+                if raw and hasattr(self.pool, "submit_encoded"):
+                    line = self.pool.wait(self.pool.submit_encoded(rid, raw))
+                    if '"Unsupported image encoding' not in line:
+                        return line
+                # Anything the device decoder does not cover (PNG, BMP, progressive JPEG, EXIF rotation ...) is decoded
+                # the reference's way -- cv::imread / cv::imdecode on the host -- and submitted as pixels.
+                image = self._decode_bytes(raw) if raw else None
+                if image is None or image.size == 0:
+                    return _err("Failed to load image from path: " + path if kind == "path" else "Failed to decode base64 image data")
                 return self.pool.wait(self.pool.submit(rid, image))   # the worker's result line, unchanged
             if command == "status":
                 # the reference nests getStatusInfo() as a JSON *string*; so does this

@@ -453,6 +453,12 @@ __device__ void boxes_one(const DbPostParams& P, const float* __restrict__ prob,
       };
       nh = geom::convex_hull_sorted_yx(pt, 2 * bh, hull, kHullCap);
       if (nh <= 0) ok = 0;
+      else {
+        geom::P2 st;  // the contour's start pixel: the slot itself (outer: first pixel; hole: the pixel left of the hole)
+        st.x = float(int((slot - ibase) % w));
+        st.y = float(int((slot - ibase) / w));
+        geom::hull_order_like_cv(hull, nh, outer, st);
+      }
     }
     if (ok) {
       const geom::RotRect rr = geom::min_area_rect_hull(hull, nh, sc_a, sc_b, sc_c);

@@ -13,6 +13,18 @@ void cuda_check(cudaError_t e, const char* what) {
   if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+void host_wait(cudaStream_t s, const char* what) {
+  static const bool spin = [] { const char* v = getenv("B200OCR_SPIN_SYNC"); return v && v[0] == '1'; }();
+  if (spin) { cuda_check(cudaStreamSynchronize(s), what); return; }
+  int dev = 0;
+  cuda_check(cudaGetDevice(&dev), "cudaGetDevice");
+  thread_local cudaEvent_t ev[64] = {};
+  if (dev < 0 || dev >= 64) { cuda_check(cudaStreamSynchronize(s), what); return; }
+  if (!ev[dev]) cuda_check(cudaEventCreateWithFlags(&ev[dev], cudaEventBlockingSync | cudaEventDisableTiming), "cudaEventCreate");
+  cuda_check(cudaEventRecord(ev[dev], s), what);
+  cuda_check(cudaEventSynchronize(ev[dev]), what);
+}
+
 struct Net::Inst {
   int n = 0, h = 0, w = 0;
   std::vector<Shape3> ts;            // per tensor

@@ -99,5 +99,10 @@ class Net {
 };
 
 void cuda_check(cudaError_t e, const char* what);
+// Host wait for everything queued on `s`.  A worker thread waits twice per batch (detected boxes, decoded ids);
+// cudaStreamSynchronize spins on a host core for the whole wait, which at 8 GPUs x 3 workers is more threads than the
+// box has cores.  This records a cudaEventBlockingSync event and sleeps on it instead (B200OCR_SPIN_SYNC=1 restores
+// the spinning wait).
+void host_wait(cudaStream_t s, const char* what);
 
 }  // namespace b200ocr

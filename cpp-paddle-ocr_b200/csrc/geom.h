@@ -77,6 +77,28 @@ GEOM_HD int convex_hull_sorted_yx(GetPt pt, int n, P2* out, int cap) {
   return k;
 }
 
+// The vertex ORDER cv::minAreaRect hands to its rotating calipers: cv::convexHull(points, clockwise = false) followed
+// by that function's final cyclic shift, which makes the hull's contour indices monotone.  For a border traced by
+// cv::findContours that comes out as (measured against cv2 4.13 on 8600 outer and hole borders, 0 mismatches):
+//   outer border: the reverse of the chain above, i.e. ending with the contour's start pixel (its first pixel in
+//                 raster order, which is chain[0]);
+//   hole border : the same reversed cycle, rotated to BEGIN with the contour's start pixel (the pixel left of the
+//                 hole's first pixel) when that pixel is a hull vertex.
+// The order decides which of two equal-area rectangles of a small lattice polygon wins (`area <= minarea`: the last
+// minimum in iteration order), so it is part of the result, not a detail.
+GEOM_HD void hull_order_like_cv(P2* h, int k, bool outer, P2 start) {
+  for (int i = 0, j = k - 1; i < j; ++i, --j) { const P2 t = h[i]; h[i] = h[j]; h[j] = t; }
+  if (outer) return;
+  int s = -1;
+  for (int i = 0; i < k; ++i)
+    if (h[i].x == start.x && h[i].y == start.y) { s = i; break; }
+  if (s <= 0) return;
+  // rotate left by s: three reversals
+  for (int i = 0, j = s - 1; i < j; ++i, --j) { const P2 t = h[i]; h[i] = h[j]; h[j] = t; }
+  for (int i = s, j = k - 1; i < j; ++i, --j) { const P2 t = h[i]; h[i] = h[j]; h[j] = t; }
+  for (int i = 0, j = k - 1; i < j; ++i, --j) { const P2 t = h[i]; h[i] = h[j]; h[j] = t; }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Rotating calipers, minimum-area enclosing rectangle of a convex polygon (float32 throughout).
 // out[0..1] = rectangle corner, out[2..3] = first edge vector, out[4..5] = second edge vector.

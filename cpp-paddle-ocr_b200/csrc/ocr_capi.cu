@@ -78,14 +78,47 @@ struct b200ocr_batch { int device = 0; ImageBatch b; };
 std::string profile_json(Net& net, cudaStream_t stream, int warmup, int reps, int thresh);
 
 // ------------------------------------------------------------------------------------------------ pool
+// Page-locked request buffers: the pool deep-copies every submitted image (like OCRRequest's clone, reference
+// include/paddle_ocr/ocr_worker.h:28-29); copying into PINNED memory lets the worker's upload run as one asynchronous
+// DMA at PCIe speed instead of the driver's staged pageable copy.  Buffers are recycled through a free list
+// (cudaHostAlloc costs milliseconds), sized in 256 KB steps.
+class PinnedPool {
+ public:
+  ~PinnedPool() { for (auto& kv : free_) for (void* p : kv.second) cudaFreeHost(p); }
+  uint8_t* take(size_t bytes, size_t* cap) {
+    const size_t c = std::max<size_t>(1, (bytes + (size_t(256) << 10) - 1) >> 18) << 18;
+    *cap = c;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      auto it = free_.find(c);
+      if (it != free_.end() && !it->second.empty()) { void* p = it->second.back(); it->second.pop_back(); return static_cast<uint8_t*>(p); }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, c, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); throw std::bad_alloc(); }
+    return static_cast<uint8_t*>(p);
+  }
+  void give(uint8_t* p, size_t cap) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(mu_);
+    free_[cap].push_back(p);
+  }
+ private:
+  std::mutex mu_;
+  std::map<size_t, std::vector<void*>> free_;
+};
+
 struct b200ocr_pool {
+  PinnedPool pinned;
   struct Request {
     long long ticket;
     int request_id;
-    std::vector<uint8_t> pixels;  // deep copy, like OCRRequest (reference include/paddle_ocr/ocr_worker.h:28-29)
-    bool encoded = false;         // pixels holds the encoded file (b200ocr_pool_submit_encoded)
+    PinnedPool* owner = nullptr;
+    uint8_t* data = nullptr;      // deep copy of the pixels (or of the encoded file), page-locked
+    size_t size = 0, cap = 0;
+    bool encoded = false;         // data holds the encoded file (b200ocr_pool_submit_encoded)
     int rows, cols;
     std::chrono::steady_clock::time_point t_submit;
+    ~Request() { if (owner) owner->give(data, cap); }
   };
   struct Device {
     int device;
@@ -135,7 +168,7 @@ struct b200ocr_pool {
           for (size_t k = 0; k < raw.size(); ++k) {
             const Request& r = *take[raw[k]];
             rid[k] = r.request_id;
-            imgs[k].data = r.pixels.empty() ? nullptr : r.pixels.data();
+            imgs[k].data = r.size ? r.data : nullptr;
             imgs[k].rows = r.rows; imgs[k].cols = r.cols; imgs[k].step = size_t(r.cols) * 3;
           }
           std::vector<std::string> o;
@@ -148,7 +181,7 @@ struct b200ocr_pool {
           std::vector<size_t> sizes(enc.size());
           for (size_t k = 0; k < enc.size(); ++k) {
             const Request& r = *take[enc[k]];
-            rid[k] = r.request_id; data[k] = r.pixels.data(); sizes[k] = r.pixels.size();
+            rid[k] = r.request_id; data[k] = r.data; sizes[k] = r.size;
           }
           std::vector<std::string> o;
           w->process_encoded(rid.data(), data.data(), sizes.data(), int(enc.size()), &o);
@@ -626,8 +659,11 @@ int b200ocr_pool_submit(b200ocr_pool_t pool, int request_id, const b200ocr_image
     r->rows = img->rows; r->cols = img->cols;
     if (img->data && img->rows > 0 && img->cols > 0) {
       const size_t row = size_t(img->cols) * 3, step = img->step ? img->step : row;
-      r->pixels.resize(row * img->rows);
-      for (int y = 0; y < img->rows; ++y) memcpy(r->pixels.data() + y * row, img->data + y * step, row);
+      r->owner = &pool->pinned;
+      r->size = row * img->rows;
+      r->data = pool->pinned.take(r->size, &r->cap);
+      if (step == row) memcpy(r->data, img->data, r->size);
+      else for (int y = 0; y < img->rows; ++y) memcpy(r->data + y * row, img->data + y * step, row);
     }
     pool_enqueue(pool, r);
     *ticket = r->ticket;
@@ -660,7 +696,12 @@ int b200ocr_pool_submit_encoded(b200ocr_pool_t pool, int request_id, const uint8
     pool->total_requests += 1;
     r->rows = r->cols = 0;
     r->encoded = true;
-    if (size) r->pixels.assign(data, data + size);
+    if (size) {
+      r->owner = &pool->pinned;
+      r->data = pool->pinned.take(size, &r->cap);
+      r->size = size;
+      memcpy(r->data, data, size);
+    }
     pool_enqueue(pool, r);
     *ticket = r->ticket;
   });

@@ -20,7 +20,13 @@
 namespace b200ocr {
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifdef B200OCR_PDL_EARLY
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+// measured (profiles/r02_notes.md): with three workers per GPU an early trigger costs 3 % -- the dependents that sit in
+// griddepcontrol.wait hold SM slots the other streams' runnable CTAs would have used.  Default: implicit trigger at exit.
+__device__ __forceinline__ void pdl_trigger() {}
+#endif
 
 inline bool pdl_enabled() {
   static const bool on = [] {

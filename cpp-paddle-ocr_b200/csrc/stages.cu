@@ -162,14 +162,14 @@ void DetStage::run_group(const std::vector<DevImg>& imgs, const std::vector<int>
   launch_dbpost(pp, net_.out_f32(), bitmap, info_.as<DbImageInfo>(), ws_.p, counts_.as<int>(), boxes_.as<DbBox>(), s);
   launches += 8 + pp.score_slow;
   cuda_check(cudaMemcpyAsync(h_counts_.p, counts_.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s), "det counts");
-  cuda_check(cudaStreamSynchronize(s), "det post-process");
+  host_wait(s, "det post-process");
   // second copy sized by what was found (boxes of image k live at [k * max_candidates, +count))
   int maxc = 0;
   for (int k = 0; k < n; ++k) maxc = std::max(maxc, h_counts_.as<int>()[k]);
   if (maxc > 0) {
     cuda_check(cudaMemcpy2DAsync(h_boxes_.p, sizeof(DbBox) * maxc, boxes_.p, sizeof(DbBox) * pp.max_candidates,
                                  sizeof(DbBox) * maxc, n, cudaMemcpyDeviceToHost, s), "det boxes");
-    cuda_check(cudaStreamSynchronize(s), "det boxes");
+    host_wait(s, "det boxes");
   }
   for (int k = 0; k < n; ++k) {
     std::vector<Box>& out = (*boxes)[idx[k]];
@@ -281,7 +281,7 @@ void ClsStage::run(const std::vector<DevImg>& imgs, const std::vector<Roi>& rois
     cuda_check(cudaMemcpyAsync(h_out_.p, labels_.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s), "cls labels");
     cuda_check(cudaMemcpyAsync(h_out_.as<uint8_t>() + size_t(n) * 4, probs_.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s),
                "cls scores");
-    cuda_check(cudaStreamSynchronize(s), "cls");
+    host_wait(s, "cls");
     if (labels) labels->assign(h_out_.as<int>(), h_out_.as<int>() + n);
     if (scores) scores->assign(reinterpret_cast<float*>(h_out_.as<uint8_t>() + size_t(n) * 4),
                                reinterpret_cast<float*>(h_out_.as<uint8_t>() + size_t(n) * 4) + n);
@@ -442,7 +442,7 @@ void RecStage::run(const std::vector<DevImg>& imgs, const std::vector<std::vecto
     cuda_check(cudaMemcpyAsync(h_cidx_.p, cidx_.p, sizeof(int) * total_ids, cudaMemcpyDeviceToHost, s), "rec ids");
     cuda_check(cudaMemcpyAsync(h_clen_.p, clen_.p, sizeof(int) * rows.size(), cudaMemcpyDeviceToHost, s), "rec len");
     cuda_check(cudaMemcpyAsync(h_cscore_.p, cscore_.p, sizeof(float) * rows.size(), cudaMemcpyDeviceToHost, s), "rec score");
-    cuda_check(cudaStreamSynchronize(s), "rec");
+    host_wait(s, "rec");
   }
   t[1] += ms_since(t0);
   t0 = Clock::now();

@@ -22,6 +22,7 @@ struct WarpArgs {
   long stride;
   double m[9];         // inverse map: destination pixel -> source coordinates
   int dw, dh;          // size of the warped image (before the optional transpose + flip)
+  int bw0;             // cv::WarpPerspectiveInvoker's block width for this output size
   int rot;             // 1: out = flip(transpose(warped), 0)
   uint8_t* out;        // rot ? [dw][dh][3] : [dh][dw][3]
 };
@@ -30,12 +31,17 @@ __global__ void __launch_bounds__(256) warp_perspective_kernel(WarpArgs a) {
   const long total = long(a.dw) * a.dh;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
     const int y = int(t / a.dw), x = int(t - long(y) * a.dw);
-    const double X0 = a.m[0] * x + a.m[1] * y + a.m[2];
-    const double Y0 = a.m[3] * x + a.m[4] * y + a.m[5];
-    double W = a.m[6] * x + a.m[7] * y + a.m[8];
-    W = W != 0. ? 32. / W : 0.;
-    const double fX = fmax(-2147483648., fmin(2147483647., X0 * W));
-    const double fY = fmax(-2147483648., fmin(2147483647., Y0 * W));
+    // cv::WarpPerspectiveInvoker (imgproc/src/imgwarp.cpp) evaluates the map per block of bw0 columns: the row terms at
+    // the block's first column, then one more product per pixel -- the same double operations in the same order here,
+    // with explicit round-to-nearest multiplies / adds (no FMA contraction: the CPU code has none)
+    const int xb = (x / a.bw0) * a.bw0, x1 = x - xb;
+    const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(a.m[0], double(xb)), __dmul_rn(a.m[1], double(y))), a.m[2]);
+    const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(a.m[3], double(xb)), __dmul_rn(a.m[4], double(y))), a.m[5]);
+    const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(a.m[6], double(xb)), __dmul_rn(a.m[7], double(y))), a.m[8]);
+    double W = __dadd_rn(W0, __dmul_rn(a.m[6], double(x1)));
+    W = W != 0. ? __ddiv_rn(32., W) : 0.;
+    const double fX = fmax(-2147483648., fmin(2147483647., __dmul_rn(__dadd_rn(X0, __dmul_rn(a.m[0], double(x1))), W)));
+    const double fY = fmax(-2147483648., fmin(2147483647., __dmul_rn(__dadd_rn(Y0, __dmul_rn(a.m[3], double(x1))), W)));
     const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
     int sx = X >> 5, sy = Y >> 5;
     sx = max(-32768, min(32767, sx));  // saturate_cast<short>
@@ -138,6 +144,10 @@ void launch_rotate_crop(const uint8_t* img, int rows, int cols, long stride, con
   a.src = img + long(top) * stride + long(left) * 3;
   a.sw = right - left; a.sh = bottom - top; a.stride = stride;
   a.dw = cw; a.dh = ch;
+  {  // BLOCK_SZ = 32: bh0 = min(16, height); bw0 = min(1024 / bh0, width)
+    const int bh0 = std::min(16, ch);
+    a.bw0 = std::max(1, std::min(1024 / bh0, cw));
+  }
   a.rot = float(ch) >= float(cw) * 1.5f;
   a.out = out;
   const long total = long(cw) * ch;

@@ -20,11 +20,13 @@ int geomtest_hull(const float* xy, int n, float* out_xy, int cap) {
   return k;
 }
 
-void geomtest_min_area_rect(const float* xy, int n, float out[5]) {
+// xy: the contour as cv::findContours returns it (xy[0..1] = its start point); outer: 1 = outer border, 0 = hole border
+void geomtest_min_area_rect(const float* xy, int n, int outer, float out[5]) {
   std::vector<float> hxy(2 * (n + 1));
   int k = geomtest_hull(xy, n, hxy.data(), n + 1);
   std::vector<P2> h(k);
   for (int i = 0; i < k; ++i) h[i] = P2{hxy[2 * i], hxy[2 * i + 1]};
+  hull_order_like_cv(h.data(), k, outer != 0, P2{xy[0], xy[1]});
   std::vector<float> vx(k + 1), vy(k + 1), il(k + 1);
   RotRect r = min_area_rect_hull(h.data(), k, vx.data(), vy.data(), il.data());
   out[0] = r.cx; out[1] = r.cy; out[2] = r.w; out[3] = r.h; out[4] = r.angle;
