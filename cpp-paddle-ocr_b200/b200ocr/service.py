@@ -72,11 +72,16 @@ class Protocol:
                     error = "Missing image_path or image_data"
                 if error:
                     return _err(error)
-                with self._lock:
-                    rid = self._next_id
-                    self._next_id += 1
-                # Device decode first: only the file's bytes cross PCIe (b200ocr_pool_submit_encoded; baseline JPEG).
-                if raw and hasattr(self.pool, "submit_encoded"):
+                rid = None
+
+                def take_id():  # the reference numbers a request once its image is known to be loadable
+                    with self._lock:
+                        self._next_id += 1
+                        return self._next_id - 1
+                # Device decode first: only the file's bytes cross PCIe (b200ocr_pool_submit_encoded; baseline JPEG,
+                # recognised by its SOI marker so that other formats do not cost a round trip).
+                if raw[:2] == b"\xff\xd8" and hasattr(self.pool, "submit_encoded"):
+                    rid = take_id()
                     line = self.pool.wait(self.pool.submit_encoded(rid, raw))
                     if '"Unsupported image encoding' not in line:
                         return line
@@ -85,6 +90,8 @@ class Protocol:
                 image = self._decode_bytes(raw) if raw else None
                 if image is None or image.size == 0:
                     return _err("Failed to load image from path: " + path if kind == "path" else "Failed to decode base64 image data")
+                if rid is None:
+                    rid = take_id()
                 return self.pool.wait(self.pool.submit(rid, image))   # the worker's result line, unchanged
             if command == "status":
                 # the reference nests getStatusInfo() as a JSON *string*; so does this

@@ -14,8 +14,8 @@ void cuda_check(cudaError_t e, const char* what) {
 }
 
 void host_wait(cudaStream_t s, const char* what) {
-  static const bool spin = [] { const char* v = getenv("B200OCR_SPIN_SYNC"); return v && v[0] == '1'; }();
-  if (spin) { cuda_check(cudaStreamSynchronize(s), what); return; }
+  static const bool block = [] { const char* v = getenv("B200OCR_BLOCKING_SYNC"); return v && v[0] == '1'; }();
+  if (!block) { cuda_check(cudaStreamSynchronize(s), what); return; }
   int dev = 0;
   cuda_check(cudaGetDevice(&dev), "cudaGetDevice");
   thread_local cudaEvent_t ev[64] = {};

@@ -99,10 +99,11 @@ class Net {
 };
 
 void cuda_check(cudaError_t e, const char* what);
-// Host wait for everything queued on `s`.  A worker thread waits twice per batch (detected boxes, decoded ids);
-// cudaStreamSynchronize spins on a host core for the whole wait, which at 8 GPUs x 3 workers is more threads than the
-// box has cores.  This records a cudaEventBlockingSync event and sleeps on it instead (B200OCR_SPIN_SYNC=1 restores
-// the spinning wait).
+// Host wait for everything queued on `s`.  A worker thread waits twice per batch (detected boxes, decoded ids).
+// Default: cudaStreamSynchronize (spins on a host core).  B200OCR_BLOCKING_SYNC=1: record a cudaEventBlockingSync event
+// and sleep on it -- frees the core, but measured on one B200 with 16 host cores (profiles/r02_notes.md) the wake-up
+// latency at the two sync points costs 34 % of the device-resident rate (5922 -> 3920 images/s) and 5.5 % end to end
+// (5703 -> 5386), so it is an opt-in for hosts with fewer cores than workers.
 void host_wait(cudaStream_t s, const char* what);
 
 }  // namespace b200ocr

@@ -105,6 +105,10 @@ def test_service_over_real_pool_matches_worker(models_dir, golden_dir):
         assert set(st["stage_ms_per_image"]) == {"det", "cls", "rec"}
         assert all(v >= 0 for v in st["stage_ms_per_image"].values())
         assert list(st) == sorted(st)  # jsoncpp key order
+        # a format the device decoder does not cover (PNG) goes through the host decoder, like the reference's imread
+        png = base64.b64encode(cv2.imencode(".png", cv2.imread(card))[1].tobytes()).decode()
+        got3 = service.request(path, {"command": "recognize", "image_data": png})
+        assert got3["success"] and got3["words"] == want["words"]
         assert service.request(path, {"command": "shutdown"})["success"] is True
         t.join(timeout=10)
     finally:
