@@ -487,7 +487,7 @@ def run_pool(args):
     t0 = time.perf_counter()
     imgs = make_inputs("c4", n_warm + n_timed, 9_000_000, pinned=False)
     gen_s = time.perf_counter() - t0
-    n_feed = max(1, min(cores - N * wpd // 2, 2 * N, 16))
+    n_feed = max(2, min(4 * N, cores - N * wpd, 16))
 
     def stream(submit, items, first_id):
         """n_feed threads: thread f submits items f, f + n_feed, ... keeping at most `window` of its requests in flight"""

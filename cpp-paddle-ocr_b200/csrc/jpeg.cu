@@ -21,18 +21,49 @@ __constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32,
 // ------------------------------------------------------------------------------------------------ entropy decoding
 // MSB-first bit reader over an entropy-coded segment: 0xFF00 is un-stuffed, any other marker feeds zero bits without
 // advancing (libjpeg's behaviour at the end of a segment; oracle/jpeg_decode.py::_Bits).
+constexpr int kRingBytes = 16384;   // shared-memory staging ring of the single-interval path: 4 chunks of 4 KB
+constexpr int kChunkBytes = 4096;
+constexpr int kRingChunks = kRingBytes / kChunkBytes;
+
+// RING = false: bytes come straight from global memory (many restart intervals per image, one thread each).
+// RING = true : the image is ONE interval, decoded by one thread; the CTA's second warp streams the bytes through a
+//               shared-memory ring ahead of it, so the decoder's dependent chain sees ~30-cycle shared-memory loads
+//               instead of L2 round trips.
+template <bool RING>
 struct BitReader {
-  const uint8_t* d;       // 4-byte aligned; readable up to 8 bytes past `end` (the batch buffer is padded)
+  const uint8_t* d;       // RING: the ring (shared memory); else the image's bytes (global, 4-byte aligned, padded)
   int p, end;
   uint64_t acc;
   int n;
   int pad;                // zero bits appended after the end of the data (they sit at the tail of acc)
+  // ring bookkeeping
+  volatile int* prod;     // chunks staged so far (written by the staging warp)
+  volatile int* cons;     // chunk the decoder is reading (written here)
+  int ready;              // bytes known to be staged
+  int chunk;
+  __device__ __forceinline__ void need(int upto) {  // make sure bytes [.., upto) are in the ring
+    if (RING) {
+      if (upto > ready) {
+        int c;
+        while ((c = *prod) * kChunkBytes < upto) {}
+        __threadfence_block();
+        ready = c * kChunkBytes;
+      }
+      const int ch = p / kChunkBytes;
+      if (ch != chunk) { chunk = ch; *cons = ch; }
+    }
+  }
+  __device__ __forceinline__ uint32_t word(int idx) const {
+    if (RING) return reinterpret_cast<const uint32_t*>(d)[idx & (kRingBytes / 4 - 1)];
+    return __ldg(reinterpret_cast<const uint32_t*>(d) + idx);
+  }
+  __device__ __forceinline__ uint32_t byte(int pos) const { return RING ? d[pos & (kRingBytes - 1)] : d[pos]; }
   __device__ __forceinline__ void fill() {
     if (n > 32) return;
+    need(p + 8);
     if (p + 4 <= end) {
       // four bytes at once when none of them is 0xFF (no stuffing, no marker): two aligned words, funnel-shifted
-      const uint32_t* w = reinterpret_cast<const uint32_t*>(d) + (p >> 2);
-      const uint32_t le = __funnelshift_r(__ldg(w), __ldg(w + 1), (p & 3) * 8);
+      const uint32_t le = __funnelshift_r(word(p >> 2), word((p >> 2) + 1), (p & 3) * 8);
       const uint32_t inv = ~le;
       if (((inv - 0x01010101u) & ~inv & 0x80808080u) == 0) {
         acc = (acc << 32) | __byte_perm(le, 0, 0x0123);
@@ -44,9 +75,10 @@ struct BitReader {
     while (n <= 56) {
       uint32_t b = 0;
       if (p < end) {
-        b = d[p];
+        need(p + 2);
+        b = byte(p);
         if (b == 0xFF) {
-          const uint32_t nx = p + 1 < end ? d[p + 1] : 0xD9u;
+          const uint32_t nx = p + 1 < end ? byte(p + 1) : 0xD9u;
           if (nx == 0) p += 2; else { b = 0; pad += 8; }
         } else {
           ++p;
@@ -68,7 +100,8 @@ struct BitReader {
   }
 };
 
-__device__ __forceinline__ int decode_symbol(BitReader& br, const JpegHuffLut& t) {
+template <bool RING>
+__device__ __forceinline__ int decode_symbol(BitReader<RING>& br, const JpegHuffLut& t) {
   const uint32_t look = br.peek(9);
   const uint32_t e = t.fast[look];
   if (e) {
@@ -89,10 +122,57 @@ __device__ __forceinline__ int decode_symbol(BitReader& br, const JpegHuffLut& t
 
 constexpr int kHuffThreads = 64;
 
+// Decodes one restart interval (JPEG F.2.2): DC difference + AC run/size pairs per block, blocks in MCU order.
+template <bool RING>
+__device__ __forceinline__ void decode_interval(BitReader<RING>& br, const JpegSeg sg, const JpegHuffLut* lut,
+                                                const long long* s_off, const int* s_bw, const int* s_hs, const int* s_vs,
+                                                int ncomp, int mcux, int16_t* __restrict__ coef) {
+  br.p = sg.begin; br.end = sg.end; br.acc = 0; br.n = 0; br.pad = 0;
+  int pred[3] = {0, 0, 0};
+  int my = sg.mcu0 / mcux, mx = sg.mcu0 - my * mcux;
+  for (int m = 0; m < sg.nmcu; ++m) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c >= ncomp) break;
+      const JpegHuffLut& tdc = lut[2 * c];
+      const JpegHuffLut& tac = lut[2 * c + 1];
+      const int hs = s_hs[c], vs = s_vs[c], bw = s_bw[c];
+      for (int by = 0; by < vs; ++by)
+        for (int bx = 0; bx < hs; ++bx) {
+          int16_t* blk = coef + (s_off[c] + (long long)(my * vs + by) * bw + (mx * hs + bx)) * 64;
+          br.fill();
+          const int t = decode_symbol(br, tdc) & 15;
+          br.fill();
+          pred[c] += br.receive_extend(t);
+          blk[0] = int16_t(pred[c]);
+          int k = 1;
+          while (k < 64) {
+            br.fill();
+            const int rs = decode_symbol(br, tac);
+            const int r = rs >> 4, s = rs & 15;
+            if (s == 0) {
+              if (r != 15) break;
+              k += 16;
+              continue;
+            }
+            k += r;
+            const int v = br.receive_extend(s);
+            if (k < 64) blk[c_zigzag[k]] = int16_t(v);
+            ++k;
+          }
+        }
+    }
+    if (++mx == mcux) { mx = 0; ++my; }
+    // Out of data (jdhuff.c `insufficient_data`): the MCU in which the decoder ran past the end of the segment is
+    // completed with zero bits, the MCUs after it are not decoded at all (their coefficients stay zero: mid grey).
+    if (br.pad > br.n) break;
+  }
+}
+
 // One CTA per image: its six look-up tables are staged in shared memory, then every thread decodes restart intervals
 // (thread t takes intervals t, t + 64, ...).  Files without restart markers have one interval: one thread decodes
-// the whole image while the CTA's other threads idle -- the kernel is latency-bound per image and meant to run
-// beside other work (a batch of images = that many busy threads on as many SMs).
+// the whole image from a shared-memory ring the CTA's second warp keeps filled -- latency-bound per image and meant
+// to run beside other work (a batch of images = that many decoding threads on as many SMs).
 __global__ void __launch_bounds__(kHuffThreads)
 jpeg_huffman_kernel(const JpegImage* __restrict__ imgs, const JpegSeg* __restrict__ segs, const uint8_t* __restrict__ bytes,
                     int16_t* __restrict__ coef) {
@@ -115,50 +195,38 @@ jpeg_huffman_kernel(const JpegImage* __restrict__ imgs, const JpegSeg* __restric
   __syncthreads();
   const int ncomp = im.ncomp, mcux = im.mcux, nseg = im.seg_count, seg0 = im.seg_begin;
   const uint8_t* data = bytes + im.data_off;
-  for (int si = threadIdx.x; si < nseg; si += kHuffThreads) {
-    const JpegSeg sg = segs[seg0 + si];
-    BitReader br;
-    br.d = data;
-    br.p = sg.begin; br.end = sg.end; br.acc = 0; br.n = 0; br.pad = 0;
-    int pred[3] = {0, 0, 0};
-    int my = sg.mcu0 / mcux, mx = sg.mcu0 - my * mcux;
-    for (int m = 0; m < sg.nmcu; ++m) {
+  if (nseg == 1) {
+    // one interval: thread 0 decodes from the ring, warp 1 stages the bytes, the rest of warp 0 has nothing to do
+    __shared__ __align__(16) uint8_t ring[kRingBytes];
+    __shared__ volatile int prod, cons;
+    if (threadIdx.x == 0) { prod = 0; cons = 0; }
+    __syncthreads();
+    const JpegSeg sg = segs[seg0];
+    const int nchunks = (sg.end + 8 + kChunkBytes - 1) / kChunkBytes;
+    if (threadIdx.x >= 32) {
+      const int lane = threadIdx.x - 32;
+      for (int c = 0; c < nchunks; ++c) {
+        while (c - cons >= kRingChunks) {}   // the slot's previous chunk (c - kRingChunks) must be behind the decoder
+        const uint4* src = reinterpret_cast<const uint4*>(data + size_t(c) * kChunkBytes);
+        uint4* dst = reinterpret_cast<uint4*>(ring + (c % kRingChunks) * kChunkBytes);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (c >= ncomp) break;
-        const JpegHuffLut& tdc = lut[2 * c];
-        const JpegHuffLut& tac = lut[2 * c + 1];
-        const int hs = s_hs[c], vs = s_vs[c], bw = s_bw[c];
-        for (int by = 0; by < vs; ++by)
-          for (int bx = 0; bx < hs; ++bx) {
-            int16_t* blk = coef + (s_off[c] + (long long)(my * vs + by) * bw + (mx * hs + bx)) * 64;
-            br.fill();
-            const int t = decode_symbol(br, tdc) & 15;
-            br.fill();
-            pred[c] += br.receive_extend(t);
-            blk[0] = int16_t(pred[c]);
-            int k = 1;
-            while (k < 64) {
-              br.fill();
-              const int rs = decode_symbol(br, tac);
-              const int r = rs >> 4, s = rs & 15;
-              if (s == 0) {
-                if (r != 15) break;
-                k += 16;
-                continue;
-              }
-              k += r;
-              const int v = br.receive_extend(s);
-              if (k < 64) blk[c_zigzag[k]] = int16_t(v);
-              ++k;
-            }
-          }
+        for (int i = 0; i < kChunkBytes / 16 / 32; ++i) dst[lane + 32 * i] = __ldg(src + lane + 32 * i);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) prod = c + 1;
       }
-      if (++mx == mcux) { mx = 0; ++my; }
-      // Out of data (jdhuff.c `insufficient_data`): the MCU in which the decoder ran past the end of the segment is
-      // completed with zero bits, the MCUs after it are not decoded at all (their coefficients stay zero: mid grey).
-      if (br.pad > br.n) break;
+    } else if (threadIdx.x == 0) {
+      BitReader<true> br;
+      br.d = ring; br.prod = &prod; br.cons = &cons; br.ready = 0; br.chunk = 0;
+      decode_interval<true>(br, sg, lut, s_off, s_bw, s_hs, s_vs, ncomp, mcux, coef);
+      cons = 1 << 28;  // release the staging warp if it is still waiting for ring space
     }
+    return;
+  }
+  for (int si = threadIdx.x; si < nseg; si += kHuffThreads) {
+    BitReader<false> br;
+    br.d = data; br.prod = nullptr; br.cons = nullptr; br.ready = 0; br.chunk = 0;
+    decode_interval<false>(br, segs[seg0 + si], lut, s_off, s_bw, s_hs, s_vs, ncomp, mcux, coef);
   }
 }
 
@@ -386,7 +454,7 @@ int JpegBatch::decode(const uint8_t* const* data, const size_t* sizes, int n, cu
   if (I.pending) { cuda_check(cudaEventSynchronize(I.copied), "jpeg staging reuse"); I.pending = false; }
   const size_t off_segs = a256(sizeof(JpegImage) * size_t(m));
   const size_t off_bytes = off_segs + a256(sizeof(JpegSeg) * segs.size());
-  const size_t total = off_bytes + bytes_total + 16;
+  const size_t total = off_bytes + bytes_total + 2 * kChunkBytes;  // the staging warp reads whole 4 KB chunks
   I.stage.ensure(total);
   I.meta.ensure(total);
   I.coef.ensure(coef_blocks * 128);
