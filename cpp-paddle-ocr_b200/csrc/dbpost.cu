@@ -496,9 +496,9 @@ __device__ void boxes_one(const DbPostParams& P, const float* __restrict__ prob,
     const int ymin = clampi(int(floorf(mny)), 0, h - 1), ymax = clampi(int(ceilf(mxy)), 0, h - 1);
     int qx[4], qy[4];
     for (int k = 0; k < 4; ++k) { qx[k] = int(mb[k].x) - xmin; qy[k] = int(mb[k].y) - ymin; }
-    geom::QuadMask qm;
-    qm.init(qx, qy);
     const int mw = xmax - xmin + 1, mh = ymax - ymin + 1;
+    geom::QuadMask qm;
+    qm.init(qx, qy, mw, mh);
     double sum = 0;
     int cnt = 0;
     for (int i = threadIdx.x; i < mw * mh; i += blockDim.x) {

@@ -244,31 +244,85 @@ GEOM_HD float mini_box(const RotRect& r, P2 box[4]) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// cv::fillPoly of one quad with integer vertices: mask(y, x) == inside(y, x).
-// OpenCV draws each edge with the 8-connected Bresenham line (left-to-right ordered) and fills
-// the scan lines y0 <= y < y1 of every non-horizontal edge between ceil(x_left) and floor(x_right)
-// in 16.16 fixed point (x advances by the truncated slope (dx << 16) / dy per line).  Bit-identical
-// to cv2.fillPoly (4.13) whenever the vertices lie inside the mask (tests/test_geom_host.py); for
-// vertices outside it OpenCV first clips every edge to the mask (cv::clipLine), which moves a few
-// outline pixels -- not restated here, see DESIGN.md "known residuals".
+// cv::fillPoly of one quad with integer vertices into a mask of mw x mh pixels: mask(y, x) == inside(y, x).
+// OpenCV (imgproc/src/drawing.cpp, CollectPolyEdges + FillEdgeCollection) draws each edge with the 8-connected
+// Bresenham line of cv::LineIterator -- CLIPPED to the mask first (cv::clipLine), then ordered left to right -- and
+// fills the scan lines y0 <= y < y1 of every non-horizontal edge between ceil(x_left) and floor(x_right) in 16.16 fixed
+// point (x advances by the truncated slope per line).  For an edge with an end point outside the mask the fill edge is
+// rebuilt from the clipped end points: x always, y only when the clipped segment is not horizontal (a segment clipped
+// to a single point becomes a vertical edge at the mask border over the original y range).  Bit-identical to
+// cv2.fillPoly (4.13) for vertices inside AND outside the mask (tests/test_oracle_cpu.py::test_geom_fill_poly_vs_cv2).
 struct QuadMask {
   int vx[4], vy[4];
   // per edge (i -> i+1)
   int64_t ex[4], edx[4];
   int ey0[4], ey1[4];
   bool eok[4];
+  // outline segments after clipping
+  int lax[4], lay[4], lbx[4], lby[4];
+  bool lok[4];
 
-  GEOM_HD void init(const int x[4], const int y[4]) {
+  // cv::clipLine(Size(w, h), pt1, pt2): the end points are modified in place, also when the result is "outside"
+  GEOM_HD static bool clip_line(int w, int h, int64_t& x1, int64_t& y1, int64_t& x2, int64_t& y2) {
+    const int64_t right = w - 1, bottom = h - 1;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+      int64_t a;
+      if (c1 & 12) {
+        a = c1 < 8 ? 0 : bottom;
+        x1 += int64_t(double(a - y1) * double(x2 - x1) / double(y2 - y1));
+        y1 = a;
+        c1 = (x1 < 0) + (x1 > right) * 2;
+      }
+      if (c2 & 12) {
+        a = c2 < 8 ? 0 : bottom;
+        x2 += int64_t(double(a - y2) * double(x2 - x1) / double(y2 - y1));
+        y2 = a;
+        c2 = (x2 < 0) + (x2 > right) * 2;
+      }
+      if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        if (c1) {
+          a = c1 == 1 ? 0 : right;
+          y1 += int64_t(double(a - x1) * double(y2 - y1) / double(x2 - x1));
+          x1 = a;
+          c1 = 0;
+        }
+        if (c2) {
+          a = c2 == 1 ? 0 : right;
+          y2 += int64_t(double(a - x2) * double(y2 - y1) / double(x2 - x1));
+          x2 = a;
+          c2 = 0;
+        }
+      }
+    }
+    return (c1 | c2) == 0;
+  }
+
+  GEOM_HD void init(const int x[4], const int y[4], int mw, int mh) {
     for (int i = 0; i < 4; ++i) { vx[i] = x[i]; vy[i] = y[i]; }
     for (int i = 0; i < 4; ++i) {
       const int j = (i + 3) & 3;  // edge from vertex j (previous) to vertex i, like CollectPolyEdges
-      const int64_t x0 = int64_t(vx[j]) << 16, x1 = int64_t(vx[i]) << 16;
+      // outline: Line(img, t0, t1) = LineIterator over the clipped segment
+      int64_t ax = vx[j], ay = vy[j], bx = vx[i], by = vy[i];
+      lok[i] = clip_line(mw, mh, ax, ay, bx, by);
+      lax[i] = int(ax); lay[i] = int(ay); lbx[i] = int(bx); lby[i] = int(by);
+      // fill edge
+      int64_t x0 = int64_t(vx[j]) << 16, x1 = int64_t(vx[i]) << 16;
+      int64_t y0c = vy[j], y1c = vy[i];
       const int y0 = vy[j], y1 = vy[i];
+      const bool outside = unsigned(vx[j]) >= unsigned(mw) || unsigned(vx[i]) >= unsigned(mw) ||
+                           unsigned(vy[j]) >= unsigned(mh) || unsigned(vy[i]) >= unsigned(mh);
+      if (outside) {  // "use clipped endpoints to create a more accurate PolyEdge" (ax.. already hold clipLine's result)
+        if (ay != by) { y0c = ay; y1c = by; }
+        x0 = ax << 16;
+        x1 = bx << 16;
+      }
       eok[i] = y0 != y1;
       if (!eok[i]) continue;
-      edx[i] = (x1 - x0) / (y1 - y0);
-      if (y0 < y1) { ey0[i] = y0; ey1[i] = y1; ex[i] = x0; }
-      else { ey0[i] = y1; ey1[i] = y0; ex[i] = x1; }
+      edx[i] = (x1 - x0) / (y1c - y0c);
+      if (y0 < y1) { ey0[i] = y0; ey1[i] = y1; ex[i] = x0 + (int64_t(y0) - y0c) * edx[i]; }
+      else { ey0[i] = y1; ey1[i] = y0; ex[i] = x1 + (int64_t(y1) - y1c) * edx[i]; }
     }
   }
 
@@ -315,10 +369,8 @@ struct QuadMask {
 
   GEOM_HD bool inside(int px, int py) const {
     // outline
-    for (int i = 0; i < 4; ++i) {
-      const int j = (i + 3) & 3;
-      if (on_line(vx[j], vy[j], vx[i], vy[i], px, py)) return true;
-    }
+    for (int i = 0; i < 4; ++i)
+      if (lok[i] && on_line(lax[i], lay[i], lbx[i], lby[i], px, py)) return true;
     // scan-line fill: edges active on row py sorted by x; pairs (0,1), (2,3)
     int64_t xs[4];
     int cnt = 0;

@@ -687,7 +687,15 @@ void Worker::process_encoded(const int* request_ids, const uint8_t* const* data,
   std::vector<std::string> errors(n);
   std::vector<std::vector<WordOut>> words(n);
   try {
+    static const bool trace = getenv("B200OCR_TRACE") != nullptr;
+    const auto t_dec = Clock::now();
     jpeg_->decode(data, sizes, n, stream_, &dec, &why);
+    if (trace) {  // (the synchronisation is part of the trace only)
+      const double enq = ms_since(t_dec);
+      cudaStreamSynchronize(stream_);
+      fprintf(stderr, "[b200ocr trace] worker %d: jpeg decode of %d files: enqueue %.2f ms, done after %.2f ms, %zu bytes uploaded\n",
+              worker_id_, n, enq, ms_since(t_dec), jpeg_->h2d_bytes());
+    }
   } catch (const std::exception& e) {
     recover_after_failure();
     dec.assign(n, DevImg());

@@ -42,7 +42,7 @@ float geomtest_mini_box(const float rr[5], float out[8]) {
 
 void geomtest_quad_mask(const int* x, const int* y, int w, int h, unsigned char* mask) {
   QuadMask q;
-  q.init(x, y);
+  q.init(x, y, w, h);
   for (int r = 0; r < h; ++r)
     for (int c = 0; c < w; ++c) mask[r * w + c] = q.inside(c, r) ? 1 : 0;
 }

@@ -221,22 +221,36 @@ def test_geom_min_area_rect_vs_cv2(geomlib):
 
 
 def test_geom_fill_poly_vs_cv2(geomlib):
+    """geom::QuadMask == cv2.fillPoly for quads inside the mask AND quads that stick out of it (BoxScoreFast's mask is
+    the box's bounding rectangle clamped to the probability map: a box at the map's border has vertices outside its
+    mask, which OpenCV handles by clipping every edge first, src/postprocess_op.cpp:216-253)."""
+    import math
     rng = np.random.default_rng(5)
-    n = 0
-    for t in range(3000):
-        W, H = int(rng.integers(4, 90)), int(rng.integers(4, 60))
-        rr = ((rng.uniform(0, W), rng.uniform(0, H)), (rng.uniform(1, W), rng.uniform(1, H / 2)), rng.uniform(-90, 0))
-        pts = cv2.boxPoints(rr).astype(np.int32)
-        if pts[:, 0].min() < 0 or pts[:, 1].min() < 0 or pts[:, 0].max() >= W or pts[:, 1].max() >= H:
-            continue
+    n_in = n_out = 0
+    for t in range(6000):
+        if t % 2:
+            W, H = int(rng.integers(4, 90)), int(rng.integers(4, 60))
+            rr = ((rng.uniform(-5, W + 5), rng.uniform(-5, H + 5)), (rng.uniform(1, W), rng.uniform(1, H / 2)), rng.uniform(-90, 0))
+            pts = cv2.boxPoints(rr).astype(np.int32)
+        else:  # exactly BoxScoreFast's construction for a text-like box near the border of a w x h map
+            w, h = int(rng.integers(40, 200)), int(rng.integers(30, 120))
+            cx = rng.choice([rng.uniform(-2, 12), rng.uniform(w - 12, w + 2), rng.uniform(0, w)])
+            cy = rng.choice([rng.uniform(-2, 8), rng.uniform(h - 8, h + 2), rng.uniform(0, h)])
+            box = cv2.boxPoints(((float(cx), float(cy)), (float(rng.uniform(4, 80)), float(rng.uniform(3, 25))), float(rng.uniform(-90, 0))))
+            xmin, xmax = int(np.clip(math.floor(box[:, 0].min()), 0, w - 1)), int(np.clip(math.ceil(box[:, 0].max()), 0, w - 1))
+            ymin, ymax = int(np.clip(math.floor(box[:, 1].min()), 0, h - 1)), int(np.clip(math.ceil(box[:, 1].max()), 0, h - 1))
+            W, H = xmax - xmin + 1, ymax - ymin + 1
+            pts = np.array([[int(p[0]) - xmin, int(p[1]) - ymin] for p in box], np.int32)
+        inside = pts[:, 0].min() >= 0 and pts[:, 1].min() >= 0 and pts[:, 0].max() < W and pts[:, 1].max() < H
         m = np.zeros((H, W), np.uint8)
         cv2.fillPoly(m, [pts], 1)
         mine = np.zeros((H, W), np.uint8)
         x, y = np.ascontiguousarray(pts[:, 0], np.int32), np.ascontiguousarray(pts[:, 1], np.int32)
         geomlib.geomtest_quad_mask(_fp(x), _fp(y), W, H, _fp(mine))
-        assert np.array_equal(m, mine), pts.tolist()
-        n += 1
-    assert n > 500
+        assert np.array_equal(m, mine), (W, H, pts.tolist())
+        n_in += inside
+        n_out += not inside
+    assert n_in > 500 and n_out > 2000, (n_in, n_out)
 
 
 def test_geom_mini_box_unclip_and_finish_vs_oracle(geomlib):
