@@ -4,6 +4,7 @@
 #include "jpeg.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -100,8 +101,8 @@ struct BitReader {
   }
 };
 
-template <bool RING>
-__device__ __forceinline__ int decode_symbol(BitReader<RING>& br, const JpegHuffLut& t) {
+template <class BR>
+__device__ __forceinline__ int decode_symbol(BR& br, const JpegHuffLut& t) {
   const uint32_t look = br.peek(9);
   const uint32_t e = t.fast[look];
   if (e) {
@@ -175,9 +176,17 @@ __device__ __forceinline__ void decode_interval(BitReader<RING>& br, const JpegS
 // to run beside other work (a batch of images = that many decoding threads on as many SMs).
 __global__ void __launch_bounds__(kHuffThreads)
 jpeg_huffman_kernel(const JpegImage* __restrict__ imgs, const JpegSeg* __restrict__ segs, const uint8_t* __restrict__ bytes,
-                    int16_t* __restrict__ coef) {
+                    const int* __restrict__ flags, int16_t* __restrict__ coef) {
   __shared__ JpegHuffLut lut[6];
   const JpegImage& im = imgs[blockIdx.x];
+  if (im.seg_count == 1) {
+    // decoded by jpeg_parallel_huffman_kernel unless that kernel asked for the sequential decoder (truncated / corrupt
+    // stream: libjpeg's out-of-data behaviour is only restated here); its partial output is cleared first
+    if (!flags[im.index]) return;
+    uint4* z = reinterpret_cast<uint4*>(coef + im.block_begin * 64);
+    for (long long i = threadIdx.x; i < im.nblocks * 8; i += kHuffThreads) z[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+  }
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(im.lut);
     uint32_t* dst = reinterpret_cast<uint32_t*>(lut);
@@ -227,6 +236,292 @@ jpeg_huffman_kernel(const JpegImage* __restrict__ imgs, const JpegSeg* __restric
     BitReader<false> br;
     br.d = data; br.prod = nullptr; br.cons = nullptr; br.ready = 0; br.chunk = 0;
     decode_interval<false>(br, segs[seg0 + si], lut, s_off, s_bw, s_hs, s_vs, ncomp, mcux, coef);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ parallel entropy decode
+// Files without restart markers are one long Huffman stream.  JPEG's codes self-synchronise: a decoder that starts at an
+// arbitrary bit with the wrong state falls into step with the true symbol sequence after a few hundred bits.  Following
+// Weissenberger & Schmidt (ICPP 2018) the stream is cut into subsequences of 1024 bits:
+//   phase 0  the CTA removes the 0xFF00 byte stuffing (block-wide stream compaction), so that bit positions are plain;
+//   phase 1  every subsequence is decoded from its first bit with the state "start of an MCU";
+//   phase 2  repeat: subsequence i is decoded again from the end position / state its LEFT neighbour reached in the
+//            previous round, until no end state changes (subsequence 0 starts from the true state, so the fixed point
+//            is the true decode; a subsequence whose input did not change is not decoded again);
+//   phase 3  a prefix sum over the blocks completed per subsequence gives every subsequence its first block number; one
+//            more pass writes the coefficients.  DC values are written as DIFFERENCES; jpeg_dc_scan_kernel turns them
+//            into predictions with a per-component prefix sum.
+// One CTA (256 threads) per image.  If the blocks found do not add up to the frame (truncated / corrupt file) the image
+// is handed to the sequential decoder, which restates libjpeg's out-of-data behaviour.
+constexpr int kParThreads = 256;
+constexpr int kSubBits = kJpegSubBytes * 8;
+
+struct ParReader {   // MSB-first reader over the un-stuffed copy (zero padded); position = bits consumed so far
+  const uint32_t* w;
+  int p4;
+  uint64_t acc;
+  int n;
+  __device__ __forceinline__ void init(const uint8_t* clean, int pos) {
+    w = reinterpret_cast<const uint32_t*>(clean);
+    p4 = pos >> 5;
+    acc = __byte_perm(w[p4], 0, 0x0123);
+    ++p4;
+    n = 32 - (pos & 31);
+  }
+  __device__ __forceinline__ void fill() {
+    if (n <= 32) { acc = (acc << 32) | __byte_perm(w[p4], 0, 0x0123); ++p4; n += 32; }
+  }
+  __device__ __forceinline__ int pos() const { return p4 * 32 - n; }
+  __device__ __forceinline__ uint32_t peek(int k) const { return uint32_t(acc >> (n - k)) & ((1u << k) - 1u); }
+  __device__ __forceinline__ void skip(int k) { n -= k; }
+  __device__ __forceinline__ int receive_extend(int s) {
+    if (s == 0) return 0;
+    const int v = int(peek(s));
+    skip(s);
+    return v >= (1 << (s - 1)) ? v : v - (1 << s) + 1;
+  }
+};
+
+struct ParGeom {   // per image, in shared memory
+  long long off[3];
+  int bw[3], hs[3], vs[3];
+  int comp[12], by[12], bx[12];
+  int bpm, mcux;
+  long long total_blocks;
+};
+
+// Decodes from the reader's position up to bit `end` (symbols that START before `end`).  State: block-in-MCU `blk`,
+// next coefficient index `k` (0 = a DC symbol is due).  WRITE: coefficients go to the block with sequence number q.
+template <bool WRITE>
+__device__ __forceinline__ void run_sub(ParReader& br, int end, int& blk, int& k, int& nblk, long long q, const JpegHuffLut* lut,
+                                        const ParGeom& g, int16_t* __restrict__ coef) {
+  int16_t* bp = nullptr;
+  auto locate = [&](long long qq) {
+    const long long mcu = qq / g.bpm;
+    const int b = int(qq - mcu * g.bpm), c = g.comp[b];
+    const int my = int(mcu / g.mcux), mx = int(mcu - (long long)my * g.mcux);
+    return coef + (g.off[c] + (long long)(my * g.vs[c] + g.by[b]) * g.bw[c] + (mx * g.hs[c] + g.bx[b])) * 64;
+  };
+  if (WRITE) { if (q >= g.total_blocks) return; bp = locate(q); }
+  while (br.pos() < end) {
+    const int c = g.comp[blk];
+    br.fill();
+    if (k == 0) {
+      const int t = decode_symbol(br, lut[2 * c]) & 15;
+      br.fill();
+      const int v = br.receive_extend(t);
+      if (WRITE) bp[0] = int16_t(v);   // the DC DIFFERENCE
+      k = 1;
+    } else {
+      const int rs = decode_symbol(br, lut[2 * c + 1]);
+      const int r = rs >> 4, s = rs & 15;
+      if (s == 0) {
+        k = r == 15 ? k + 16 : 64;
+      } else {
+        k += r;
+        const int v = br.receive_extend(s);
+        if (WRITE && k < 64) bp[c_zigzag[k]] = int16_t(v);
+        ++k;
+      }
+    }
+    if (k >= 64) {
+      k = 0;
+      ++nblk;
+      blk = blk + 1 == g.bpm ? 0 : blk + 1;
+      if (WRITE) {
+        if (++q >= g.total_blocks) return;
+        bp = locate(q);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < kParThreads / 32; ++i) {
+    const int s = warp_sums[i];
+    if (i < warp) base += s;
+    tot += s;
+  }
+  *total = tot;
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kParThreads)
+jpeg_parallel_huffman_kernel(const JpegImage* __restrict__ imgs, const uint8_t* __restrict__ bytes, uint8_t* __restrict__ clean_all,
+                             uint4* __restrict__ sub_all, long long n_sub_total, int* __restrict__ flags,
+                             int16_t* __restrict__ coef) {
+  const JpegImage& im = imgs[blockIdx.x];
+  if (im.seg_count != 1) {
+    if (threadIdx.x == 0) flags[im.index] = 0;
+    return;
+  }
+  __shared__ JpegHuffLut lut[6];
+  __shared__ ParGeom g;
+  __shared__ int warp_sums[kParThreads / 32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(im.lut);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(lut);
+    const int words = int(sizeof(JpegHuffLut) * 2 * im.ncomp / 4);
+    for (int i = tid; i < words; i += kParThreads) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    int b = 0;
+    for (int c = 0; c < im.ncomp; ++c) {
+      g.off[c] = im.comp[c].coef_off; g.bw[c] = im.comp[c].bw; g.hs[c] = im.comp[c].hs; g.vs[c] = im.comp[c].vs;
+      for (int y = 0; y < im.comp[c].vs; ++y)
+        for (int x = 0; x < im.comp[c].hs; ++x, ++b) { g.comp[b] = c; g.by[b] = y; g.bx[b] = x; }
+    }
+    g.bpm = b;
+    g.mcux = im.mcux;
+    g.total_blocks = (long long)im.mcux * im.mcuy * b;
+    s_carry = 0;
+  }
+  __syncthreads();
+  // ---- phase 0: remove byte stuffing (0x00 after 0xFF) and 0xFF fill bytes
+  const uint8_t* raw = bytes + im.data_off;
+  uint8_t* clean = clean_all + im.data_off;
+  const int len = im.data_len;
+  for (int base = 0; base < len; base += kParThreads * 16) {
+    const int i0 = base + tid * 16;
+    uint8_t b[16];
+    int cnt = 0;
+    unsigned keep = 0;
+    if (i0 < len) {
+      const uint4 v = *reinterpret_cast<const uint4*>(raw + i0);   // (the batch buffer is padded: reading past len is safe)
+      memcpy(b, &v, 16);
+      uint8_t prev = i0 > 0 ? raw[i0 - 1] : 0;
+      const int m = min(16, len - i0);
+      for (int j = 0; j < m; ++j) {
+        const bool drop = (prev == 0xFF && b[j] == 0x00) || (b[j] == 0xFF && i0 + j + 1 < len && raw[i0 + j + 1] == 0xFF);
+        if (!drop) { keep |= 1u << j; ++cnt; }
+        prev = b[j];
+      }
+    }
+    int total;
+    const int excl = block_exclusive_scan(cnt, warp_sums, &total);
+    uint8_t* o = clean + s_carry + excl;
+    for (int j = 0; j < 16; ++j)
+      if (keep >> j & 1) *o++ = b[j];
+    __syncthreads();
+    if (tid == 0) s_carry += total;
+    __syncthreads();
+  }
+  const int clen = s_carry;
+  for (int i = tid; i < 64; i += kParThreads) clean[clen + i] = 0;   // zero bits after the end, like the sequential reader
+  const int total_bits = clen * 8;
+  const int nsub = min((total_bits + kSubBits - 1) / kSubBits, im.sub_max);
+  uint4* info_a = sub_all + im.sub_begin;
+  uint4* info_b = sub_all + n_sub_total + im.sub_begin;
+  int* first_blk = reinterpret_cast<int*>(sub_all + 2 * n_sub_total) + im.sub_begin;
+  __syncthreads();
+  // ---- phase 1
+  for (int i = tid; i < nsub; i += kParThreads) {
+    ParReader br;
+    br.init(clean, i * kSubBits);
+    int blk = 0, k = 0, nb = 0;
+    run_sub<false>(br, min((i + 1) * kSubBits, total_bits), blk, k, nb, 0, lut, g, coef);
+    info_a[i] = make_uint4(unsigned(br.pos()), unsigned(blk | (k << 8)), unsigned(nb), 1u);
+  }
+  __syncthreads();
+  // ---- phase 2
+  uint4* cur = info_a;
+  uint4* nxt = info_b;
+  for (int iter = 0; iter <= nsub; ++iter) {
+    int changed = 0;
+    for (int i = tid; i < nsub; i += kParThreads) {
+      const uint4 mine = cur[i];
+      if (i == 0) { nxt[0] = make_uint4(mine.x, mine.y, mine.z, 0u); continue; }
+      const uint4 prev = cur[i - 1];
+      if (prev.w == 0u) { nxt[i] = make_uint4(mine.x, mine.y, mine.z, 0u); continue; }  // same input as last round
+      ParReader br;
+      br.init(clean, int(prev.x));
+      int blk = int(prev.y & 255u), k = int(prev.y >> 8), nb = 0;
+      run_sub<false>(br, min((i + 1) * kSubBits, total_bits), blk, k, nb, 0, lut, g, coef);
+      const uint4 now = make_uint4(unsigned(br.pos()), unsigned(blk | (k << 8)), unsigned(nb), 0u);
+      const unsigned ch = (now.x != mine.x || now.y != mine.y || now.z != mine.z) ? 1u : 0u;
+      nxt[i] = make_uint4(now.x, now.y, now.z, ch);
+      changed |= int(ch);
+    }
+    uint4* t = cur; cur = nxt; nxt = t;
+    if (!__syncthreads_or(changed)) break;
+  }
+  // ---- phase 3: first block number of every subsequence, then the writing pass
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nsub; base += kParThreads) {
+    const int i = base + tid;
+    const int v = i < nsub ? int(cur[i].z) : 0;
+    int total;
+    const int excl = block_exclusive_scan(v, warp_sums, &total);
+    if (i < nsub) first_blk[i] = s_carry + excl;
+    __syncthreads();
+    if (tid == 0) s_carry += total;
+    __syncthreads();
+  }
+  const bool complete = (long long)s_carry >= g.total_blocks;
+  if (tid == 0) flags[im.index] = complete ? 0 : 1;
+  if (!complete) return;
+  for (int i = tid; i < nsub; i += kParThreads) {
+    ParReader br;
+    int blk = 0, k = 0, nb = 0, start = 0;
+    if (i > 0) { const uint4 prev = cur[i - 1]; start = int(prev.x); blk = int(prev.y & 255u); k = int(prev.y >> 8); }
+    br.init(clean, start);
+    run_sub<true>(br, min((i + 1) * kSubBits, total_bits), blk, k, nb, (long long)first_blk[i], lut, g, coef);
+  }
+}
+
+// DC prediction of the images the parallel kernel decoded: per component, an inclusive prefix sum over the DC
+// differences in scan order (F.2.2.1: DIFF = DC - PRED).  One CTA per (component, image).
+__global__ void __launch_bounds__(kParThreads)
+jpeg_dc_scan_kernel(const JpegImage* __restrict__ imgs, const int* __restrict__ flags, int16_t* __restrict__ coef) {
+  const JpegImage& im = imgs[blockIdx.y];
+  const int c = blockIdx.x;
+  if (im.seg_count != 1 || flags[im.index] || c >= im.ncomp) return;
+  __shared__ int warp_sums[kParThreads / 32];
+  __shared__ int s_carry;
+  const JpegComp& cp = im.comp[c];
+  const int per = cp.hs * cp.vs, mcux = im.mcux;
+  const long long n = (long long)im.mcux * im.mcuy * per;
+  auto at = [&](long long j) {
+    const long long mcu = j / per;
+    const int b = int(j - mcu * per), by = b / cp.hs, bx = b - by * cp.hs;
+    const int my = int(mcu / mcux), mx = int(mcu - (long long)my * mcux);
+    return coef + (cp.coef_off + (long long)(my * cp.vs + by) * cp.bw + (mx * cp.hs + bx)) * 64;
+  };
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  constexpr int kPer = 8;
+  for (long long base = 0; base < n; base += kParThreads * kPer) {
+    const long long j0 = base + (long long)threadIdx.x * kPer;
+    int v[kPer], sum = 0;
+#pragma unroll
+    for (int e = 0; e < kPer; ++e) {
+      v[e] = j0 + e < n ? int(at(j0 + e)[0]) : 0;
+      sum += v[e];
+      v[e] = sum;
+    }
+    int total;
+    const int excl = block_exclusive_scan(sum, warp_sums, &total) + s_carry;
+#pragma unroll
+    for (int e = 0; e < kPer; ++e)
+      if (j0 + e < n) at(j0 + e)[0] = int16_t(excl + v[e]);
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += total;
+    __syncthreads();
   }
 }
 
@@ -374,13 +669,24 @@ jpeg_color_kernel(const JpegImage* __restrict__ imgs, const uint8_t* __restrict_
 }  // namespace
 
 void launch_jpeg_decode(const JpegImage* imgs_dev, const JpegImage* imgs_host, int n_images, const JpegSeg* segs_dev,
-                        int n_segs, const uint8_t* bytes_dev, int16_t* coef_dev, size_t coef_bytes, uint8_t* planes_dev,
-                        uint8_t* out_dev, cudaStream_t s) {
+                        int n_segs, const uint8_t* bytes_dev, uint8_t* clean_dev, void* sub_dev, long long n_sub,
+                        int16_t* coef_dev, size_t coef_bytes, uint8_t* planes_dev, uint8_t* out_dev, cudaStream_t s) {
   (void)n_segs;
   if (n_images < 1) return;
-  // only the non-zero coefficients are written by the entropy decoder
+  // only the non-zero coefficients are written by the entropy decoders
   if (cudaMemsetAsync(coef_dev, 0, coef_bytes, s) != cudaSuccess) throw std::runtime_error("jpeg: cudaMemsetAsync failed");
-  jpeg_huffman_kernel<<<n_images, kHuffThreads, 0, s>>>(imgs_dev, segs_dev, bytes_dev, coef_dev);
+  uint4* sub = static_cast<uint4*>(sub_dev);
+  int* flags = reinterpret_cast<int*>(sub + 3 * n_sub);
+  static const bool sequential_only = getenv("B200OCR_JPEG_SEQUENTIAL") != nullptr;  // A/B: one thread per interval only
+  bool any_single = false;
+  for (int i = 0; i < n_images; ++i) any_single |= imgs_host[i].seg_count == 1;
+  if (any_single && !sequential_only) {
+    jpeg_parallel_huffman_kernel<<<n_images, kParThreads, 0, s>>>(imgs_dev, bytes_dev, clean_dev, sub, n_sub, flags, coef_dev);
+  } else if (cudaMemsetAsync(flags, 0xff, sizeof(int) * size_t(n_images), s) != cudaSuccess) {   // "use the sequential decoder"
+    throw std::runtime_error("jpeg: cudaMemsetAsync failed");
+  }
+  jpeg_huffman_kernel<<<n_images, kHuffThreads, 0, s>>>(imgs_dev, segs_dev, bytes_dev, flags, coef_dev);
+  if (any_single && !sequential_only) jpeg_dc_scan_kernel<<<dim3(3, n_images), kParThreads, 0, s>>>(imgs_dev, flags, coef_dev);
   const JpegImage& last = imgs_host[n_images - 1];
   const long long total_blocks = last.block_begin + last.nblocks;
   const int per = kIdctThreads / 8;
@@ -396,7 +702,7 @@ void launch_jpeg_decode(const JpegImage* imgs_dev, const JpegImage* imgs_host, i
 
 // ------------------------------------------------------------------------------------------------ batch front end
 struct JpegBatch::Impl {
-  DevBuf meta, coef, planes, out;
+  DevBuf meta, coef, planes, out, clean, sub;
   DevBuf stage{true};
   cudaEvent_t copied = nullptr;
   bool pending = false;
@@ -419,7 +725,7 @@ int JpegBatch::decode(const uint8_t* const* data, const size_t* sizes, int n, cu
   std::vector<std::pair<size_t, size_t>> ecs;
   imgs.reserve(size_t(n));
   auto a256 = [](size_t x) { return (x + 255) & ~size_t(255); };
-  size_t bytes_total = 0, coef_blocks = 0, plane_bytes = 0, out_bytes = 0;
+  size_t bytes_total = 0, coef_blocks = 0, plane_bytes = 0, out_bytes = 0, n_sub = 0;
   for (int i = 0; i < n; ++i) {
     JpegImage im;
     std::vector<JpegSeg> sg;
@@ -428,7 +734,9 @@ int JpegBatch::decode(const uint8_t* const* data, const size_t* sizes, int n, cu
     if (!jpeg_parse(data[i], sizes[i], &im, &b, &e, &sg, &(*why)[i])) continue;
     im.data_off = (long long)bytes_total;
     im.data_len = int(e - b);
-    bytes_total += (size_t(im.data_len) + 16 + 15) & ~size_t(15);  // 4-byte aligned start, readable past the end
+    // 16-byte aligned start; 96 bytes of slack: the readers look up to 16 bytes past the end and the parallel decoder
+    // zero-pads 64 bytes behind its un-stuffed copy, which lives at the same offsets in a second buffer
+    bytes_total += (size_t(im.data_len) + 96 + 15) & ~size_t(15);
     im.seg_begin = int(segs.size());
     im.seg_count = int(sg.size());
     for (auto& x : sg) { x.image = int(imgs.size()); segs.push_back(x); }
@@ -440,6 +748,10 @@ int JpegBatch::decode(const uint8_t* const* data, const size_t* sizes, int n, cu
       plane_bytes += a256(size_t(im.comp[c].bw) * 8 * im.comp[c].bh * 8);
     }
     im.nblocks = (long long)coef_blocks - im.block_begin;
+    im.index = int(imgs.size());
+    im.sub_begin = (long long)n_sub;
+    im.sub_max = sg.size() == 1 ? (im.data_len + kJpegSubBytes - 1) / kJpegSubBytes + 1 : 0;
+    n_sub += size_t(im.sub_max);
     im.out_off = (long long)out_bytes;
     im.out_stride = (long long)im.width * 3;
     out_bytes += a256(size_t(im.width) * im.height * 3);
@@ -460,6 +772,8 @@ int JpegBatch::decode(const uint8_t* const* data, const size_t* sizes, int n, cu
   I.coef.ensure(coef_blocks * 128);
   I.planes.ensure(plane_bytes);
   I.out.ensure(out_bytes);
+  I.clean.ensure(bytes_total + 2 * kChunkBytes);
+  I.sub.ensure(n_sub * 48 + size_t(m) * 16 + 256);
   uint8_t* h = I.stage.as<uint8_t>();
   memcpy(h, imgs.data(), sizeof(JpegImage) * size_t(m));
   memcpy(h + off_segs, segs.data(), sizeof(JpegSeg) * segs.size());
@@ -474,9 +788,9 @@ int JpegBatch::decode(const uint8_t* const* data, const size_t* sizes, int n, cu
   h2d_bytes_ = total;
   const uint8_t* d = I.meta.as<uint8_t>();
   launch_jpeg_decode(reinterpret_cast<const JpegImage*>(d), imgs.data(), m, reinterpret_cast<const JpegSeg*>(d + off_segs),
-                     int(segs.size()), d + off_bytes, I.coef.as<int16_t>(), coef_blocks * 128, I.planes.as<uint8_t>(),
-                     I.out.as<uint8_t>(), s);
-  launches += 3;
+                     int(segs.size()), d + off_bytes, I.clean.as<uint8_t>(), I.sub.p, (long long)n_sub, I.coef.as<int16_t>(),
+                     coef_blocks * 128, I.planes.as<uint8_t>(), I.out.as<uint8_t>(), s);
+  launches += 5;
   for (int k = 0; k < m; ++k) {
     DevImg& o = (*out)[size_t(index[k])];
     o.p = I.out.as<uint8_t>() + imgs[k].out_off;

@@ -8,8 +8,10 @@
 // Split of the work:
 //   host  : marker parsing only (tables, frame, scan header, restart-marker positions) -- a few hundred bytes per file;
 //           the entropy-coded bytes are uploaded as they are (about 10x fewer PCIe bytes than the BGR pixels).
-//   device: jpeg_huffman_kernel (one thread per restart interval; one per image when the file has none) ->
-//           int16 coefficients; jpeg_idct_kernel (8 threads per 8x8 block) -> component planes;
+//   device: entropy decoding -> int16 coefficients: files with restart markers by jpeg_huffman_kernel (one thread per
+//           restart interval); files without by jpeg_parallel_huffman_kernel (self-synchronising decode: 256 threads
+//           per image work on 1024-bit subsequences, see jpeg.cu) + jpeg_dc_scan_kernel (DC prediction as a prefix sum);
+//           jpeg_idct_kernel (8 threads per 8x8 block) -> component planes;
 //           jpeg_color_kernel (upsampling + colour conversion) -> BGR u8 in the layout the det / cls / rec
 //           pre-processing kernels read.
 // Scope: what the restated algorithm covers -- baseline / extended sequential, Huffman, 8-bit, one interleaved scan,
@@ -52,7 +54,12 @@ struct JpegImage {          // POD shared by host and device
   long long nblocks;
   long long out_off;        // byte offset of the BGR image in the output buffer
   long long out_stride;
+  long long sub_begin;      // single-interval images: first entry of the image's subsequence table (parallel decode)
+  int sub_max;              // its capacity: ceil(data_len / kJpegSubBytes)
+  int index;                // position of the image in the batch (flags)
 };
+
+constexpr int kJpegSubBytes = 128;  // the parallel entropy decoder cuts an interval into subsequences of 1024 bits
 
 struct JpegSeg { int image; int begin, end; int mcu0, nmcu; };  // [begin, end) relative to the image's data_off
 
@@ -63,9 +70,11 @@ bool jpeg_parse(const uint8_t* data, size_t size, JpegImage* img, size_t* ecs_be
                 std::vector<JpegSeg>* segs, std::string* why);
 
 // Device side.  All pointers are device memory; `imgs` / `segs` were uploaded by the caller.
+// `clean_dev`: as large as the byte buffer (un-stuffed copies); `sub_dev`: 3 x 16 bytes per subsequence + 4 per image
+// (see jpeg.cu); `n_sub`: total subsequences of the batch.
 void launch_jpeg_decode(const JpegImage* imgs_dev, const JpegImage* imgs_host, int n_images, const JpegSeg* segs_dev,
-                        int n_segs, const uint8_t* bytes_dev, int16_t* coef_dev, size_t coef_bytes, uint8_t* planes_dev,
-                        uint8_t* out_dev, cudaStream_t s);
+                        int n_segs, const uint8_t* bytes_dev, uint8_t* clean_dev, void* sub_dev, long long n_sub,
+                        int16_t* coef_dev, size_t coef_bytes, uint8_t* planes_dev, uint8_t* out_dev, cudaStream_t s);
 
 struct DevBuf;
 struct DevImg;

@@ -138,3 +138,43 @@ def test_unsupported_files_are_refused_with_a_reason():
     cut = b200ocr.jpeg_decode(raw[: sos + (len(raw) - sos) * 2 // 3])
     assert cut.shape == whole.shape and np.array_equal(cut[:8], whole[:8])
     assert len(np.unique(cut[-8:].reshape(-1, 3), axis=0)) == 1
+
+
+def test_sequential_and_parallel_entropy_decoders_agree(tmp_path):
+    """Files without restart markers go through the self-synchronising parallel decoder; B200OCR_JPEG_SEQUENTIAL=1 (read
+    once per process, hence the subprocess) sends them through the one-thread-per-interval decoder instead.  Same bytes
+    out, and both equal cv2.imdecode."""
+    import subprocess
+    import sys
+    import cv2
+    import synth_data
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rng = np.random.default_rng(11)
+    imgs = [synth_data.card(900), synth_data.page(9)[:1500, :1111], synth_data.card(901)[:97, :203],
+            cv2.GaussianBlur(rng.integers(0, 256, (333, 517, 3), dtype=np.uint8), (3, 3), 0.8)]
+    files = []
+    for k, im in enumerate(imgs):
+        for q, sf in ((50, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420), (92, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444),
+                      (100, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422)):
+            path = os.path.join(str(tmp_path), f"f{k}_{q}.jpg")
+            assert cv2.imwrite(path, im, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf])
+            files.append(path)
+    script = (
+        "import sys, numpy as np\n"
+        "root = sys.argv[1]\n"
+        "sys.path[:0] = [root, root + '/cpp-paddle-ocr_b200']\n"
+        "import b200ocr\n"
+        "np.savez(sys.argv[2], *[b200ocr.jpeg_decode(open(f, 'rb').read()) for f in sys.argv[3:]])\n")
+    outs = {}
+    for name, env in (("parallel", {}), ("sequential", {"B200OCR_JPEG_SEQUENTIAL": "1"})):
+        out = os.path.join(str(tmp_path), name + ".npz")
+        e = dict(os.environ)
+        e.update(env)
+        r = subprocess.run([sys.executable, "-c", script, root, out] + files, capture_output=True, text=True, env=e, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[name] = np.load(out)
+    for k, f in enumerate(files):
+        ref = cv2.imdecode(np.fromfile(f, np.uint8), cv2.IMREAD_COLOR)
+        a, b = outs["parallel"][f"arr_{k}"], outs["sequential"][f"arr_{k}"]
+        assert np.array_equal(a, ref), (f, int((a != ref).sum()))
+        assert np.array_equal(b, ref), (f, int((b != ref).sum()))
