@@ -5,7 +5,7 @@ sharded across ranks, no collective on the data path.
     python bench.py --impl reference ...                                     # the reference's CPU path, restated (oracle/)
 
 --config (BASELINE.json `configs`; default c4 = the configuration the metric is quoted on):
-  c4  full det->cls->rec on synthetic 1024x640 card images, worker defaults          (64 images / GPU / step)
+  c4  full det->cls->rec on synthetic 1024x640 card images, worker defaults          (192 images / GPU / step)
   c2  recognition-only: 48x320 text-line crops through CRNN/SVTR + CTC greedy decode  (4096 crops / GPU / step)
   c3  detection-only: cards at limit_side_len 960 -> [*,3,608,960] DB forward + DBPostProcess (64 images / GPU / step)
   c5  dense 2048x2048 pages (200+ lines) through det(960)->cls->rec                   (8 pages / GPU / step)
@@ -37,8 +37,11 @@ METRIC = "OCR images/sec (det+cls+rec)"
 UNIT = "images/s"
 WEIGHTS = "cls: shipped; det, rec: synthetic-trained on this repo's generators (reference det/rec weights absent)"
 CONFIGS = {
+    # 192 images per GPU and step = 64 per worker: measured on one B200 (profiles/r02_notes.md section 8) 64 / 128 / 192 /
+    # 256 images per step give 5.94-5.99 / 6.07 / 6.20-6.35 / 6.29 k images/s resident (per-kernel efficiency of the
+    # launch-bound det / cls layers and of the recognizer's neck grows with the rows per launch)
     "c4": dict(workload="C4: full det->cls->rec on synthetic 1024x640 card images (cv2.putText, 8-12 lines each), worker defaults",
-               batch=64, unit_name="images", cpu_sample=24, ref_per_step=16),
+               batch=192, unit_name="images", cpu_sample=24, ref_per_step=16),
     "c2": dict(workload="C2: recognition-only, synthetic 48x320 text-line crops through CRNN/SVTR forward + CTC greedy decode "
                         "(CRNNRecognizer::Run, rec_batch_num 6)",
                batch=4096, unit_name="crops", cpu_sample=192, ref_per_step=128),
