@@ -17,7 +17,8 @@ def scaled(r, name, want):
     if i is None or r[i] in ("", "n/a"):
         return 0.0
     v, u = float(r[i].replace(",", "")), units[i]
-    f = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1}.get(u, 1)
+    f = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1,
+         "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1}.get(u, 1)
     g = {"byte": 1, "MB": 1e6, "us": 1e-6}[want]
     return v * f / g
 pat = re.compile(sys.argv[2]) if len(sys.argv) > 2 else None

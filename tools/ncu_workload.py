@@ -1,5 +1,5 @@
 """Workloads for the ncu captures committed under profiles/ (run on the GPU box under ncu --profile-from-start off):
-    rec       one forward pass of the recognizer at the shape bench.py's roofline is timed on (default [205,28,704])
+    rec | det | cls  [n,h,w]   one forward pass of that network at the shape bench.py's roofline is timed on
     pipeline  one Worker.process_batch over 32 S-cards (det pre-process, DB head, DB post-process, crop pre-process,
               CTC head ...), after an untimed warm-up call
 """
@@ -14,13 +14,14 @@ import b200ocr, make_synth_weights, synth_data
 models = make_synth_weights.ensure_models()
 rt = torch.cuda.cudart()
 what = sys.argv[1]
-if what == "rec":
+if what in ("rec", "det", "cls"):
     n, h, w = json.loads(sys.argv[2]) if len(sys.argv) > 2 else (205, 28, 704)
-    net = b200ocr.Net(f"{models}/rec", 0, b200ocr.NET_NO_GRAPH)
+    net = b200ocr.Net(f"{models}/{what}", 0, b200ocr.NET_NO_GRAPH)
     x = np.random.default_rng(0).standard_normal((n, 3, h, w)).astype(np.float32)
-    net.forward(x)
+    kw = {"thresh_u8": 51} if what == "det" else {}
+    net.forward(x, **kw)
     rt.cudaProfilerStart()
-    net.forward(x)
+    net.forward(x, **kw)
     rt.cudaProfilerStop()
 else:
     os.environ.setdefault("B200OCR_PDL", "0")
