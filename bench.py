@@ -369,6 +369,9 @@ def run_ours(args):
         # staging buffers have reached their working size (growing one means cudaFree + cudaMalloc, which stalls the
         # whole device) and the shapes that do repeat (det) have their CUDA graph
         run_steps(fn, nw, prime + prime)
+        t_prime = time.perf_counter()
+        while time.perf_counter() - t_prime < args.prime_seconds:   # clocks / power state settled before anything is timed
+            run_steps(fn, nw, prime)
         if args.recycle:
             run_steps(fn, nw, sets + sets)
             warm, meas = [sets[s % n_sets] for s in range(W)], [sets[(W + s) % n_sets] for s in range(K)]
@@ -602,6 +605,8 @@ def main():
     ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="units per GPU per step; 0 = the configuration's default")
     ap.add_argument("--recycle", action="store_true", help="rotate 4 pre-seen batches instead of distinct inputs per step")
+    ap.add_argument("--prime-seconds", type=float, default=1.5,
+                    help="untimed load on the priming batches before the W warm-up steps of each measurement")
     ap.add_argument("--workers", type=int, default=0,
                     help="handles (streams) per GPU sharing a step's batch; 0 = min(3, host cores // GPUs)")
     ap.add_argument("--e2e-workers", type=int, default=0,

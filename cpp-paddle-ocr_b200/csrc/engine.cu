@@ -180,6 +180,13 @@ Net::Inst* Net::instantiate(int n, int h, int w) {
       case LKind::CtcHead: I->bbytes[ob] = align_up(size_t(in.n) * in.w * 4, 256) * 2; break;
       default: break;
     }
+    // the pooled partial sums of an SE block stay live until its Scale layer: the fused pool + gate + scale kernel
+    // writes the scaled map while other samples' blocks still read / write their partial sums
+    if (L.kind == LKind::Gap && li + 2 < nl && plan_.layers[li + 1].kind == LKind::SeFc && plan_.layers[li + 2].kind == LKind::Scale) {
+      last[ob] = std::max(last[ob], li + 2);
+      const int sb = plan_.tensors[plan_.layers[li + 2].out].buf;   // ... and the scaled map is written from here on
+      first[sb] = std::min(first[sb], li);
+    }
     auto touch_r = [&](int t) { if (t >= 0) { int b = plan_.tensors[t].buf; last[b] = std::max(last[b], li); } };
     touch_r(L.in); touch_r(L.in2); touch_r(L.residual);
     for (int k = 0; k < 4; ++k) touch_r(L.ins[k]);
@@ -305,6 +312,8 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
   auto vecp = [&](int t) { return reinterpret_cast<float*>(arena_ + I.boff[plan_.tensors[t].buf]); };
   int launches = 0;
   static const bool no_se_fuse = getenv("B200OCR_NO_SE_FUSE") != nullptr;
+  static const bool no_se_apply = getenv("B200OCR_NO_SE_APPLY_FUSE") != nullptr;
+  int scale_fused_at = -1;
   for (size_t li = 0; li < plan_.layers.size(); ++li) {
     if (only >= 0 && int(li) != only) continue;
     const Layer& L = plan_.layers[li];
@@ -351,6 +360,16 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
           f.c = F.cin; f.cmid = F.cmid; f.slope = F.act_a; f.offset = F.act_b;
           f.inv_hw = 1.f / float(I.hw[L.out]);
           f.vw_in = vwp(L.in); f.h = I.ts[L.in].h;
+          // ... and the gate is applied there too when the Scale layer follows (x -> pool -> gate -> x * gate) and the
+          // batch has enough samples to keep the GPU busy with one block per sample
+          if (!no_se_apply && only < 0 && li + 2 < plan_.layers.size() && I.ts[L.in].n >= 16) {
+            const Layer& S = plan_.layers[li + 2];
+            if (S.kind == LKind::Scale && S.in == L.in && S.in2 == F.out) {
+              TV so = tv(S.out);
+              f.sc_out = so.p; f.sc_out_pitch = so.pitch; f.sc_add_x = S.scale_residual ? 1 : 0;
+              scale_fused_at = int(li + 2);
+            }
+          }
           launch_gap_partial(tv(L.in), vecp(L.out), I.splits[L.out], plan_.kind == "rec", s, &f);
         } else {
           launch_gap_partial(tv(L.in), vecp(L.out), I.splits[L.out], plan_.kind == "rec", s);
@@ -365,7 +384,10 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
         launch_se_fc(vecp(L.in), I.splits[L.in], I.hw[L.in], I.ts[L.in].n, L.cin, L.cmid, d_wf_ + L.wf_off,
                      L.act_a, L.act_b, vecp(L.out), s, vwp(I.gap_src[L.in]), I.ts[I.gap_src[L.in]].h);
         break;
-      case LKind::Scale: launch_scale(tv(L.in), vecp(L.in2), L.scale_residual, tv(L.out), s); break;
+      case LKind::Scale:
+        if (scale_fused_at == int(li)) { --launches; break; }  // done by the pool + gate kernel two layers up
+        launch_scale(tv(L.in), vecp(L.in2), L.scale_residual, tv(L.out), s);
+        break;
       case LKind::UpAdd: launch_upadd(tv(L.in), tv(L.in2), tv(L.out), s); break;
       case LKind::UpCat: {
         TV ins[4];

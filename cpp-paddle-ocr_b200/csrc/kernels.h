@@ -67,6 +67,10 @@ struct SeFuse {
   int c = 0, cmid = 0, h = 0;
   float slope = 0.f, offset = 0.f, inv_hw = 0.f;
   const int* vw_in = nullptr;
+  // also apply the gate (the SE block's elementwise_mul [+ add]): the block that computes a sample's gate multiplies the
+  // sample's map with it right away -- nullptr = the Scale layer runs as its own kernel
+  __half* sc_out = nullptr;
+  int sc_out_pitch = 0, sc_add_x = 0;
 };
 void launch_gap_partial(const TV& in, float* partial, int splits, bool ragged_safe, cudaStream_t s,
                         const SeFuse* fuse = nullptr);

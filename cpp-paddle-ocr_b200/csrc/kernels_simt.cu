@@ -846,6 +846,31 @@ gap_se_kernel(TV in, float* __restrict__ partial, int splits, int cbs, int cbw, 
   __syncthreads();
   if (!s_last) return;
   se_fc_body<1>(sm, partial, splits, fc.inv_hw, n, in.n, fc.c, fc.cmid, fc.blk, fc.slope, fc.offset, fc.gate, fc.vw_in, fc.h);
+  if (!fc.sc_out) return;
+  // Gate applied by the same block (x * gate [+ x], the arithmetic of scale_kernel): one launch less per SE block, and
+  // the map is still in L2 from the pooling pass.  Blocks of different samples work in parallel; nothing waits on
+  // another block, so any number of these kernels can share the GPU.
+  __syncthreads();  // the gate was written by this block's threads
+  const int cgs = (in.c + 7) >> 3;
+  const int cp = cgs * 8;
+  for (int i = threadIdx.x; i < cp; i += blockDim.x) sm[i] = fc.gate[long(n) * cp + i];
+  __syncthreads();
+  const long hw = long(in.h) * in.w;
+  const long total = hw * cgs;
+  const __half* src = in.p + long(n) * hw * in.pitch;
+  __half* dst = fc.sc_out + long(n) * hw * fc.sc_out_pitch;
+  for (long t = threadIdx.x; t < total; t += blockDim.x) {
+    const int cg = int(t % cgs);
+    const long pix = t / cgs;
+    float x[8];
+    ld8(src + pix * in.pitch + cg * 8).to_float(x);
+    const float* g = sm + cg * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = fc.sc_add_x ? fmaf(x[i], g[i], x[i]) : x[i] * g[i];
+    H8 o;
+    o.from_float(x);
+    st8(dst + pix * fc.sc_out_pitch + cg * 8, o);
+  }
 }
 
 __global__ void __launch_bounds__(kThreads)

@@ -34,6 +34,13 @@ out["det_prob"] = prob
 net.close()
 net = b200ocr.Net(f"{models}/cls", 0, 0)
 out["cls"] = net.forward(rng.standard_normal((9, 3, 48, 192)).astype(np.float32))
+out["cls20"] = net.forward(rng.standard_normal((20, 3, 48, 192)).astype(np.float32))   # >= 16 samples: SE scale fused
+net.close()
+net = b200ocr.Net(f"{models}/det", 0, 0)
+out["det16"] = net.forward(rng.standard_normal((16, 3, 64, 96)).astype(np.float32), thresh_u8=51)[0]
+net.close()
+net = b200ocr.Net(f"{models}/rec", 0, 0)
+out["rec24"] = net.forward(rng.standard_normal((24, 3, 28, 200)).astype(np.float32), widths=np.array([200] * 8 + [96] * 8 + [168] * 8, np.int32))[0]
 net.close()
 np.savez(sys.argv[3], **out)
 """
@@ -65,6 +72,8 @@ VARIANTS = [
     ({"B200OCR_TMA_STORE": "1"}, True),           # same accumulators, stored through shared memory + TMA
     ({"B200OCR_CONV_PERSIST_MIN": "1000000"}, True),  # never the persistent convolution kernel
     ({"B200OCR_NO_PWCONV": "1"}, False),          # narrow 1x1 convolutions on tcgen05 instead of the mma.sync stream
+    ({"B200OCR_NO_SE_APPLY_FUSE": "1"}, True),    # SE gate applied by scale_kernel instead of the pool + gate kernel
+    ({"B200OCR_PDL": "0"}, True),                 # no programmatic dependent launch
 ]
 
 
