@@ -78,13 +78,21 @@ struct b200ocr_batch { int device = 0; ImageBatch b; };
 std::string profile_json(Net& net, cudaStream_t stream, int warmup, int reps, int thresh);
 
 // ------------------------------------------------------------------------------------------------ pool
-// Page-locked request buffers: the pool deep-copies every submitted image (like OCRRequest's clone, reference
-// include/paddle_ocr/ocr_worker.h:28-29); copying into PINNED memory lets the worker's upload run as one asynchronous
-// DMA at PCIe speed instead of the driver's staged pageable copy.  Buffers are recycled through a free list
-// (cudaHostAlloc costs milliseconds), sized in 256 KB steps.
-class PinnedPool {
+// The pool deep-copies every submitted image (like OCRRequest's clone, reference include/paddle_ocr/ocr_worker.h:28-29).
+// Pixels are cloned STRAIGHT INTO THE MEMORY OF THE DEVICE the request is dispatched to (b200ocr_pool_submit): a host-side
+// clone costs a 2 MB memcpy per card, and the host's copy bandwidth (measured ~20 GB/s over all cores of the box,
+// profiles/r02_notes.md section 8) capped a two-GPU pool at 6.8 k images/s; a page-locked caller buffer now moves as one
+// DMA and no CPU core touches the pixels.  Encoded files (tens of KB, parsed on the host) are cloned into page-locked
+// host memory.  Both kinds of buffer are recycled through free lists (cudaHostAlloc / cudaMalloc cost milliseconds
+// and serialise the whole process), sized in 256 KB steps.
+class BufferPool {
  public:
-  ~PinnedPool() { for (auto& kv : free_) for (void* p : kv.second) cudaFreeHost(p); }
+  BufferPool(bool on_device, int device) : on_device_(on_device), device_(device) {}
+  ~BufferPool() {
+    if (on_device_) cudaSetDevice(device_);
+    for (auto& kv : free_) for (void* p : kv.second) { if (on_device_) cudaFree(p); else cudaFreeHost(p); }
+  }
+  // device pools: the caller has made `device` current
   uint8_t* take(size_t bytes, size_t* cap) {
     const size_t c = std::max<size_t>(1, (bytes + (size_t(256) << 10) - 1) >> 18) << 18;
     *cap = c;
@@ -94,7 +102,8 @@ class PinnedPool {
       if (it != free_.end() && !it->second.empty()) { void* p = it->second.back(); it->second.pop_back(); return static_cast<uint8_t*>(p); }
     }
     void* p = nullptr;
-    if (cudaHostAlloc(&p, c, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); throw std::bad_alloc(); }
+    const cudaError_t e = on_device_ ? cudaMalloc(&p, c) : cudaHostAlloc(&p, c, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); throw std::bad_alloc(); }
     return static_cast<uint8_t*>(p);
   }
   void give(uint8_t* p, size_t cap) {
@@ -103,25 +112,47 @@ class PinnedPool {
     free_[cap].push_back(p);
   }
  private:
+  const bool on_device_;
+  const int device_;
   std::mutex mu_;
   std::map<size_t, std::vector<void*>> free_;
 };
 
 struct b200ocr_pool {
-  PinnedPool pinned;
+  BufferPool pinned{false, 0};
   struct Request {
     long long ticket;
     int request_id;
-    PinnedPool* owner = nullptr;
-    uint8_t* data = nullptr;      // deep copy of the pixels (or of the encoded file), page-locked
+    BufferPool* owner = nullptr;
+    uint8_t* data = nullptr;      // deep copy: the pixels in DEVICE memory, or the encoded file in page-locked host memory
     size_t size = 0, cap = 0;
     bool encoded = false;         // data holds the encoded file (b200ocr_pool_submit_encoded)
     int rows, cols;
     std::chrono::steady_clock::time_point t_submit;
     ~Request() { if (owner) owner->give(data, cap); }
   };
+  // One uploader thread per device owns the H2D clones: submitting threads hand it a job and sleep until the pixels
+  // have landed.  (Issuing the copy from the submitting threads themselves -- 8 to 16 extra threads calling into the
+  // CUDA runtime next to the workers -- serialised on the driver at ~115 us per image and slowed the workers' own
+  // launches three-fold: profiles/r02_notes.md section 8.)  The uploader takes every job that is waiting, queues their
+  // copies back to back on its stream and synchronises once.
+  struct CopyJob {
+    std::shared_ptr<Request> r;
+    const uint8_t* src = nullptr;
+    size_t step = 0, row = 0;
+    bool done = false;
+    std::string error;
+  };
   struct Device {
+    explicit Device(int dev) : device(dev), pixels(true, dev) {}
+    ~Device() { queue.clear(); }   // requests give their buffers back before `pixels` goes
     int device;
+    BufferPool pixels;              // declared before the queues: destroyed after the requests that point into it
+    std::mutex copy_mu;
+    std::condition_variable copy_cv, copy_done_cv;
+    std::deque<CopyJob*> copy_q;
+    std::atomic<int> copying{0};    // jobs handed to the uploader and not yet in `queue` (counted as load by the dispatch)
+    std::thread uploader;
     std::mutex mu;
     std::condition_variable cv;
     std::deque<std::shared_ptr<Request>> queue;
@@ -145,6 +176,53 @@ struct b200ocr_pool {
   std::atomic<long long> total_time_us{0};   // sum over requests of (completion - submission)
   std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
 
+  void upload_loop(Device* d) {
+    cudaStream_t stream = nullptr;
+    if (cudaSetDevice(d->device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      stream = nullptr;   // every job fails with a message below
+    }
+    std::vector<CopyJob*> jobs;
+    while (true) {
+      jobs.clear();
+      {
+        std::unique_lock<std::mutex> lk(d->copy_mu);
+        d->copy_cv.wait(lk, [&] { return !d->copy_q.empty() || !running; });
+        if (d->copy_q.empty()) break;   // shutting down and drained
+        while (!d->copy_q.empty() && jobs.size() < 64) { jobs.push_back(d->copy_q.front()); d->copy_q.pop_front(); }
+      }
+      for (CopyJob* j : jobs) {
+        try {
+          if (!stream) throw std::runtime_error("the pool's copy stream could not be created");
+          Request& r = *j->r;
+          r.owner = &d->pixels;
+          r.data = d->pixels.take(r.size, &r.cap);
+          if (j->step == j->row) cuda_check(cudaMemcpyAsync(r.data, j->src, r.size, cudaMemcpyHostToDevice, stream), "image clone");
+          else cuda_check(cudaMemcpy2DAsync(r.data, j->row, j->src, j->step, j->row, r.rows, cudaMemcpyHostToDevice, stream), "image clone");
+        } catch (const std::exception& e) {
+          j->error = e.what()[0] ? e.what() : "image clone failed";
+        }
+      }
+      if (stream && cudaStreamSynchronize(stream) != cudaSuccess) {
+        const char* msg = cudaGetErrorString(cudaGetLastError());
+        for (CopyJob* j : jobs) if (j->error.empty()) j->error = std::string("image clone: ") + msg;
+      }
+      {  // the clones are on the device: hand the requests to the workers, then release the submitting threads
+        std::lock_guard<std::mutex> lk(d->mu);
+        for (CopyJob* j : jobs) if (j->error.empty()) d->queue.push_back(j->r);
+        d->copying -= int(jobs.size());
+      }
+      d->cv.notify_all();
+      {
+        std::lock_guard<std::mutex> lk(d->copy_mu);
+        for (CopyJob* j : jobs) j->done = true;
+      }
+      d->copy_done_cv.notify_all();
+    }
+    if (stream) cudaStreamDestroy(stream);
+  }
+
   void loop(Device* d, Worker* w) {
     while (true) {
       std::vector<std::shared_ptr<Request>> take;
@@ -159,21 +237,33 @@ struct b200ocr_pool {
       for (size_t i = 0; i < take.size(); ++i) ids[i] = take[i]->request_id;
       std::vector<std::string> out(take.size());
       try {
-        // raw and encoded requests of one batch go through the worker as two groups
-        std::vector<size_t> raw, enc;
-        for (size_t i = 0; i < take.size(); ++i) (take[i]->encoded ? enc : raw).push_back(i);
+        // raw (already on this device), empty and encoded requests of one batch go through the worker as three groups
+        std::vector<size_t> raw, enc, empty;
+        for (size_t i = 0; i < take.size(); ++i) (take[i]->encoded ? enc : take[i]->size ? raw : empty).push_back(i);
         if (!raw.empty()) {
           std::vector<int> rid(raw.size());
-          std::vector<HostImage> imgs(raw.size());
+          std::vector<DevImg> imgs(raw.size());
           for (size_t k = 0; k < raw.size(); ++k) {
             const Request& r = *take[raw[k]];
             rid[k] = r.request_id;
-            imgs[k].data = r.size ? r.data : nullptr;
-            imgs[k].rows = r.rows; imgs[k].cols = r.cols; imgs[k].step = size_t(r.cols) * 3;
+            imgs[k].p = r.data;
+            imgs[k].rows = r.rows; imgs[k].cols = r.cols; imgs[k].stride = long(r.cols) * 3;
           }
           std::vector<std::string> o;
-          w->process_batch(rid.data(), imgs.data(), int(raw.size()), &o);
+          w->process_resident(rid.data(), imgs, &o);
           for (size_t k = 0; k < raw.size(); ++k) out[raw[k]] = std::move(o[k]);
+        }
+        if (!empty.empty()) {   // "Empty image data provided" (src/ocr_worker.cpp:223-226), no GPU work
+          std::vector<int> rid(empty.size());
+          std::vector<HostImage> imgs(empty.size());
+          for (size_t k = 0; k < empty.size(); ++k) {
+            const Request& r = *take[empty[k]];
+            rid[k] = r.request_id;
+            imgs[k].data = nullptr; imgs[k].rows = r.rows; imgs[k].cols = r.cols; imgs[k].step = 0;
+          }
+          std::vector<std::string> o;
+          w->process_batch(rid.data(), imgs.data(), int(empty.size()), &o);
+          for (size_t k = 0; k < empty.size(); ++k) out[empty[k]] = std::move(o[k]);
         }
         if (!enc.empty()) {
           std::vector<int> rid(enc.size());
@@ -217,6 +307,9 @@ struct b200ocr_pool {
       res_cv.wait(lk, [&] { return waiters == 0; });
     }
     for (auto& d : devs) {
+      { std::lock_guard<std::mutex> lk(d->copy_mu); }
+      d->copy_cv.notify_all();
+      if (d->uploader.joinable()) d->uploader.join();
       { std::lock_guard<std::mutex> lk(d->mu); }
       d->cv.notify_all();
       for (auto& t : d->threads) if (t.joinable()) t.join();
@@ -632,22 +725,40 @@ int b200ocr_pool_create(const char* model_dir, int n_devices, const int* devices
     for (int i = 0; i < n_devices; ++i) {
       const int dev = devices ? devices[i] : i;
       need_device(dev);
-      auto d = std::make_unique<b200ocr_pool::Device>();
-      d->device = dev;
+      auto d = std::make_unique<b200ocr_pool::Device>(dev);
       WorkerOptions o;
       o.enable_cls = enable_cls != 0;
       o.max_batch = p->max_batch;
       for (int k = 0; k < workers_per_device; ++k) d->workers.push_back(std::make_unique<Worker>(wid++, model_dir, dev, o));
       p->devs.push_back(std::move(d));
     }
-    for (auto& d : p->devs)
+    for (auto& d : p->devs) {
+      d->uploader = std::thread(&b200ocr_pool::upload_loop, p.get(), d.get());
       for (auto& w : d->workers) d->threads.emplace_back(&b200ocr_pool::loop, p.get(), d.get(), w.get());
+    }
     *out = p.release();
   });
 }
 void b200ocr_pool_destroy(b200ocr_pool_t pool) { delete pool; }
 
-static void pool_enqueue(b200ocr_pool_t pool, const std::shared_ptr<b200ocr_pool::Request>& r);
+// shortest queue first; ties broken round-robin (reference src/gpu_worker_pool.cpp:46-59: idle worker, else round-robin)
+static b200ocr_pool::Device& pool_pick_device(b200ocr_pool_t pool) {
+  const size_t nd = pool->devs.size(), start = pool->rr++ % nd;
+  size_t best = start, best_load = ~size_t(0);
+  for (size_t k = 0; k < nd; ++k) {
+    auto& d = *pool->devs[(start + k) % nd];
+    std::lock_guard<std::mutex> lk(d.mu);
+    const size_t load = d.queue.size() + size_t(d.copying.load()) + size_t(d.busy.load()) * size_t(pool->max_batch);
+    if (load < best_load) { best_load = load; best = (start + k) % nd; }
+  }
+  return *pool->devs[best];
+}
+static void pool_enqueue(b200ocr_pool_t pool, b200ocr_pool::Device& d, const std::shared_ptr<b200ocr_pool::Request>& r) {
+  { std::lock_guard<std::mutex> lk(pool->res_mu); pool->outstanding.insert(r->ticket); }
+  { std::lock_guard<std::mutex> lk(d.mu); d.queue.push_back(r); }
+  d.cv.notify_one();
+}
+
 int b200ocr_pool_submit(b200ocr_pool_t pool, int request_id, const b200ocr_image* img, long long* ticket) {
   return capi_guard([&] {
     if (!pool || !img || !ticket) throw std::invalid_argument("null argument");
@@ -657,33 +768,47 @@ int b200ocr_pool_submit(b200ocr_pool_t pool, int request_id, const b200ocr_image
     r->t_submit = std::chrono::steady_clock::now();
     pool->total_requests += 1;
     r->rows = img->rows; r->cols = img->cols;
+    auto& d = pool_pick_device(pool);
     if (img->data && img->rows > 0 && img->cols > 0) {
+      // the clone: host pixels -> the memory of the device the request goes to; the call returns when the copy has
+      // landed, so the caller's buffer is free again (OCRRequest's img.clone())
       const size_t row = size_t(img->cols) * 3, step = img->step ? img->step : row;
-      r->owner = &pool->pinned;
       r->size = row * img->rows;
-      r->data = pool->pinned.take(r->size, &r->cap);
-      if (step == row) memcpy(r->data, img->data, r->size);
-      else for (int y = 0; y < img->rows; ++y) memcpy(r->data + y * row, img->data + y * step, row);
+      b200ocr_pool::CopyJob job;
+      job.r = r;
+      job.src = img->data; job.step = step; job.row = row;
+      // Pageable caller memory: the driver would stage it through its own bounce buffer inside the (single) uploader
+      // thread; cloning it into page-locked memory HERE keeps that CPU copy on the submitting threads, in parallel.
+      cudaPointerAttributes at;
+      const bool locked = cudaPointerGetAttributes(&at, img->data) == cudaSuccess && at.type == cudaMemoryTypeHost;
+      if (!locked) cudaGetLastError();
+      uint8_t* bounce = nullptr;
+      size_t bounce_cap = 0;
+      if (!locked) {
+        bounce = pool->pinned.take(r->size, &bounce_cap);
+        if (step == row) memcpy(bounce, img->data, r->size);
+        else for (int y = 0; y < img->rows; ++y) memcpy(bounce + y * row, img->data + y * step, row);
+        job.src = bounce; job.step = row;
+      }
+      { std::lock_guard<std::mutex> lk(pool->res_mu); pool->outstanding.insert(r->ticket); }
+      {
+        std::unique_lock<std::mutex> lk(d.copy_mu);
+        d.copying += 1;
+        d.copy_q.push_back(&job);
+        d.copy_cv.notify_one();
+        d.copy_done_cv.wait(lk, [&] { return job.done; });
+      }
+      if (bounce) pool->pinned.give(bounce, bounce_cap);
+      if (!job.error.empty()) {
+        { std::lock_guard<std::mutex> lk(pool->res_mu); pool->outstanding.erase(r->ticket); }
+        throw std::runtime_error(job.error);
+      }
+      *ticket = r->ticket;
+      return;
     }
-    pool_enqueue(pool, r);
+    pool_enqueue(pool, d, r);
     *ticket = r->ticket;
   });
-}
-
-static void pool_enqueue(b200ocr_pool_t pool, const std::shared_ptr<b200ocr_pool::Request>& r) {
-  // shortest queue first; ties broken round-robin (reference src/gpu_worker_pool.cpp:46-59: idle worker, else round-robin)
-  const size_t nd = pool->devs.size(), start = pool->rr++ % nd;
-  size_t best = start, best_load = ~size_t(0);
-  for (size_t k = 0; k < nd; ++k) {
-    auto& d = *pool->devs[(start + k) % nd];
-    std::lock_guard<std::mutex> lk(d.mu);
-    const size_t load = d.queue.size() + size_t(d.busy.load()) * size_t(pool->max_batch);
-    if (load < best_load) { best_load = load; best = (start + k) % nd; }
-  }
-  auto& d = *pool->devs[best];
-  { std::lock_guard<std::mutex> lk(pool->res_mu); pool->outstanding.insert(r->ticket); }
-  { std::lock_guard<std::mutex> lk(d.mu); d.queue.push_back(r); }
-  d.cv.notify_one();
 }
 
 int b200ocr_pool_submit_encoded(b200ocr_pool_t pool, int request_id, const uint8_t* data, size_t size, long long* ticket) {
@@ -702,7 +827,7 @@ int b200ocr_pool_submit_encoded(b200ocr_pool_t pool, int request_id, const uint8
       r->size = size;
       memcpy(r->data, data, size);
     }
-    pool_enqueue(pool, r);
+    pool_enqueue(pool, pool_pick_device(pool), r);
     *ticket = r->ticket;
   });
 }

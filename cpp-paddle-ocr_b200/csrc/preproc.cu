@@ -14,6 +14,7 @@
 // threads share rows through L1), every output pixel is one 16-byte store.
 #include "kernels.h"
 #include "pdl.h"
+#include "resize.cuh"
 
 namespace b200ocr {
 
@@ -21,77 +22,7 @@ namespace {
 
 constexpr int kThreads = 256;
 
-struct Coef {
-  int s;       // source index of the first tap
-  int c0, c1;  // 11-bit weights
-};
-
-// x axis: indices outside the image collapse onto the edge pixel with weight 1 (cv::resize xofs/alpha set-up)
-__device__ __forceinline__ Coef coef_x(int d, double scale, int sn) {
-  float f = float((double(d) + 0.5) * scale - 0.5);
-  int s = int(floorf(f));
-  f -= float(s);
-  if (s < 0) { f = 0.f; s = 0; }
-  if (s >= sn - 1) { f = 0.f; s = sn - 1; }
-  Coef c;
-  c.s = s;
-  c.c0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
-  c.c1 = __float2int_rn(__fmul_rn(f, 2048.f));
-  return c;
-}
-// y axis: weights are kept, row indices are clamped when read
-__device__ __forceinline__ Coef coef_y(int d, double scale) {
-  float f = float((double(d) + 0.5) * scale - 0.5);
-  int s = int(floorf(f));
-  f -= float(s);
-  Coef c;
-  c.s = s;
-  c.c0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
-  c.c1 = __float2int_rn(__fmul_rn(f, 2048.f));
-  return c;
-}
-
-struct Src {
-  const uint8_t* p;  // top-left pixel of the (cropped) source
-  int w, h;
-  long stride;  // bytes per row
-};
-
-// One output pixel (3 channels) of cv::resize(src -> dw x dh, INTER_LINEAR) on CV_8UC3.
-__device__ __forceinline__ void resize_px(const Src& s, int dw, int dh, int dx, int dy, int out[3]) {
-  if (s.w == dw && s.h == dh) {
-    const uint8_t* q = s.p + dy * s.stride + dx * 3;
-    out[0] = q[0]; out[1] = q[1]; out[2] = q[2];
-    return;
-  }
-  if (s.w == 2 * dw && s.h == 2 * dh) {  // INTER_LINEAR with an exact 2x2 shrink runs as INTER_AREA
-    const uint8_t* q0 = s.p + (2 * dy) * s.stride + (2 * dx) * 3;
-    const uint8_t* q1 = q0 + s.stride;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) out[c] = (int(q0[c]) + int(q0[c + 3]) + int(q1[c]) + int(q1[c + 3]) + 2) >> 2;
-    return;
-  }
-  const double scale_x = 1.0 / (double(dw) / double(s.w));
-  const double scale_y = 1.0 / (double(dh) / double(s.h));
-  const Coef cx = coef_x(dx, scale_x, s.w);
-  const Coef cy = coef_y(dy, scale_y);
-  const int x1 = min(cx.s + 1, s.w - 1);
-  const int y0 = min(max(cy.s, 0), s.h - 1), y1 = min(max(cy.s + 1, 0), s.h - 1);
-  const uint8_t* r0 = s.p + y0 * s.stride;
-  const uint8_t* r1 = s.p + y1 * s.stride;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const int S0 = int(r0[cx.s * 3 + c]) * cx.c0 + int(r0[x1 * 3 + c]) * cx.c1;
-    const int S1 = int(r1[cx.s * 3 + c]) * cx.c0 + int(r1[x1 * 3 + c]) * cx.c1;
-    int v = (((cy.c0 * (S0 >> 4)) >> 16) + ((cy.c1 * (S1 >> 4)) >> 16) + 2) >> 2;
-    out[c] = min(max(v, 0), 255);
-  }
-}
-
-// Normalize::Run: f = u8 * (1/255.f); f * scale + shift, two fp32 roundings, no contraction.
-__device__ __forceinline__ float norm1(int v, float scale, float shift) {
-  return __fadd_rn(__fmul_rn(__fmul_rn(float(v), 0.0039215688593685627f /* (float)(1/255.) */), scale), shift);
-}
+using namespace resize;
 
 __device__ __forceinline__ void store_px(__half* out, long pix, float a, float b, float c) {
   uint4 o;

@@ -200,9 +200,13 @@ int b200ocr_rec_profile(b200ocr_rec_t rec, int warmup, int reps, char** json);
 /* ------------------------------------------------------------------ per-device worker pool
  * Replaces PaddleOCR::GPUWorkerPool (include/paddle_ocr/gpu_worker_pool.h:14-31, src/gpu_worker_pool.cpp:8-59), which
  * pins every worker to GPU 0: here workers are spread over `n_devices` GPUs (devices[i], or 0..n-1 when NULL),
- * `workers_per_device` each; submit() is thread-safe, copies the image (like OCRRequest's clone) and returns a
+ * `workers_per_device` each; submit() is thread-safe, clones the image (like OCRRequest's clone) and returns a
  * ticket; a worker drains up to `max_batch` queued requests at a time.  Dispatch: the device with the shortest queue
- * (the reference's idle-first / round-robin, generalised). */
+ * (the reference's idle-first / round-robin, generalised).
+ * The clone goes straight into the memory of the device the request is dispatched to, through that device's uploader
+ * thread: when `img->data` is page-locked (b200ocr_host_alloc / cudaHostAlloc / cudaHostRegister) it is one DMA and
+ * no CPU core touches the pixels; ordinary pageable memory is first copied into a page-locked bounce buffer by the
+ * calling thread.  submit() returns when the pixels have landed: the caller's buffer is free again. */
 typedef struct b200ocr_pool* b200ocr_pool_t;
 int b200ocr_pool_create(const char* model_dir, int n_devices, const int* devices, int workers_per_device,
                         int enable_cls, int max_batch, b200ocr_pool_t* out);
