@@ -374,7 +374,7 @@ list_kernel(const int* __restrict__ flag, int h, int w, int max_cand, int* __res
 }
 
 // ---------------------------------------------------------------- 4. one CTA per candidate
-constexpr int kBoxThreads = 128;
+constexpr int kBoxThreads = 512;   // the border scan and the masked mean are latency-bound: more pixels in flight per candidate
 constexpr int kHullCap = 1024;
 
 __device__ __forceinline__ double block_sum(double v, double* sh) {
@@ -417,21 +417,40 @@ __device__ void boxes_one(const DbPostParams& P, const float* __restrict__ prob,
   const int C = outer ? slot : L[slot];
   const int Bkey = outer ? outer_bg(L, touch, C, w) : slot + 1;
   int nb = 0;
-  for (int i = threadIdx.x; i < bw * bh; i += blockDim.x) {
-    const int yy = i / bw, xx = i - yy * bw;
-    const int x = x0 + xx, y = y0 + yy;
-    const long t = ibase + long(y) * w + x;
-    if (bm[t] == 0 || L[t] != C) continue;
-    bool on = false;
-    if (x == 0 || y == 0 || x == w - 1 || y == h - 1) on = Bkey == kFrame;
-    if (!on && x > 0 && bm[t - 1] == 0) on = canon_bg(L, touch, t - 1) == Bkey;
-    if (!on && x + 1 < w && bm[t + 1] == 0) on = canon_bg(L, touch, t + 1) == Bkey;
-    if (!on && y > 0 && bm[t - w] == 0) on = canon_bg(L, touch, t - w) == Bkey;
-    if (!on && y + 1 < h && bm[t + w] == 0) on = canon_bg(L, touch, t + w) == Bkey;
-    if (!on) continue;
-    ++nb;
-    atomicMin(&rowmin[yy], x);
-    atomicMax(&rowmax[yy], x);
+  // The scan is latency-bound (a chain of dependent loads per pixel): four pixels per thread are in flight at a time,
+  // and a pixel's four neighbour bytes are requested together before any of them is looked at.
+  const int total_px = bw * bh;
+  for (int base = threadIdx.x; base < total_px; base += 4 * blockDim.x) {
+    long tt[4];
+    int xs[4], ys[4];
+    bool comp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * blockDim.x;
+      const bool ok = i < total_px;
+      const int yy = ok ? i / bw : 0, xx = ok ? i - yy * bw : 0;
+      xs[u] = x0 + xx; ys[u] = y0 + yy;
+      tt[u] = ibase + long(ys[u]) * w + xs[u];
+      comp[u] = ok && bm[tt[u]] != 0 && L[tt[u]] == C;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!comp[u]) continue;
+      const int x = xs[u], y = ys[u];
+      const long t = tt[u];
+      const uint8_t nl = x > 0 ? bm[t - 1] : uint8_t(1), nr = x + 1 < w ? bm[t + 1] : uint8_t(1);
+      const uint8_t nu = y > 0 ? bm[t - w] : uint8_t(1), nd = y + 1 < h ? bm[t + w] : uint8_t(1);
+      bool on = false;
+      if (x == 0 || y == 0 || x == w - 1 || y == h - 1) on = Bkey == kFrame;
+      if (!on && nl == 0) on = canon_bg(L, touch, t - 1) == Bkey;
+      if (!on && nr == 0) on = canon_bg(L, touch, t + 1) == Bkey;
+      if (!on && nu == 0) on = canon_bg(L, touch, t - w) == Bkey;
+      if (!on && nd == 0) on = canon_bg(L, touch, t + w) == Bkey;
+      if (!on) continue;
+      ++nb;
+      atomicMin(&rowmin[y - y0], x);
+      atomicMax(&rowmax[y - y0], x);
+    }
   }
   atomicAdd(&sh_i[0], nb);
   __syncthreads();

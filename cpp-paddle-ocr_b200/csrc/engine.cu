@@ -35,6 +35,7 @@ struct Net::Inst {
   size_t need = 0;
   cudaGraphExec_t graph = nullptr;
   int graph_thresh = -2;
+  StemSource graph_src;              // the 8-bit source baked into the captured stem launch
   int runs = 0;
   int launches = 0;
   ~Inst() {
@@ -333,7 +334,11 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
         TV in = tv(L.in), out = tv(L.out);
         const __half* w = d_wh_ + L.wh_off;
         const float* bias = d_wf_ + L.bias_off;
-        if (!opt_.force_simt && launch_pwconv_mma(in, out, w, bias, g, e, s, vwp(L.out))) {
+        if (li == 0 && stem_.kind != 0) {
+          // pre-processing fused into the first convolution: the input tensor is never written (kernels_simt.cu)
+          if (!fused_stem_eligible(in, out, g, e)) throw std::runtime_error("fused stem: the first layer is not a 3x3 stride-2 stem");
+          launch_fused_stem(stem_, in, out, w, bias, g, e, s, vwp(L.out));
+        } else if (!opt_.force_simt && launch_pwconv_mma(in, out, w, bias, g, e, s, vwp(L.out))) {
           // narrow 1x1 convolution: streamed on mma.sync
         } else if (!opt_.force_simt && conv_tc_eligible(in, out, g)) {
           if (!I.tc[li].impl) I.tc[li] = make_conv_tc_plan(in, out, w, g);
@@ -516,10 +521,31 @@ std::vector<Net::LayerProfile> Net::profile(cudaStream_t stream, int warmup, int
   return out;
 }
 
-void Net::run(cudaStream_t stream, int thresh_u8) {
+bool Net::stem_fusable() const {
+  if (plan_.layers.empty() || plan_.layers[0].kind != LKind::Conv || plan_.layers[0].in != plan_.input) return false;
+  const Layer& L = plan_.layers[0];
+  TV in, out;
+  in.c = L.cin; in.h = 64; in.w = 64;
+  out.c = L.cout; out.h = 32; out.w = 32;
+  ConvGeom g;
+  g.kh = L.kh; g.kw = L.kw; g.sh = L.sh; g.sw = L.sw; g.ph = L.ph; g.pw = L.pw;
+  Epi e;
+  e.act = int(L.act);
+  if (L.residual >= 0) return false;
+  // the input tensor must have no other reader
+  for (size_t li = 1; li < plan_.layers.size(); ++li) {
+    const Layer& M = plan_.layers[li];
+    if (M.in == plan_.input || M.in2 == plan_.input || M.residual == plan_.input) return false;
+    for (int k = 0; k < 4; ++k) if (M.ins[k] == plan_.input) return false;
+  }
+  return fused_stem_eligible(in, out, g, e);
+}
+
+void Net::run(cudaStream_t stream, int thresh_u8, const StemSource* src) {
   if (!cur_) throw std::runtime_error("Net::run before prepare");
   Inst& I = *cur_;
   ++I.runs;
+  stem_ = src ? *src : StemSource();
   if (ragged_)
     cuda_check(cudaMemcpyAsync(vw_dev_, vw_pin_, plan_.tensors.size() * size_t(I.n) * sizeof(int), cudaMemcpyHostToDevice,
                                stream), "width table upload");
@@ -529,7 +555,8 @@ void Net::run(cudaStream_t stream, int thresh_u8) {
     cuda_check(cudaGetLastError(), "forward launch");
     return;
   }
-  if (!I.graph || I.graph_thresh != thresh_u8) {
+  if (!I.graph || I.graph_thresh != thresh_u8 || I.graph_src.kind != stem_.kind || I.graph_src.items != stem_.items ||
+      I.graph_src.pad_value != stem_.pad_value || memcmp(&I.graph_src.np, &stem_.np, sizeof(NormParams)) != 0) {
     if (I.graph) { cudaGraphExecDestroy(I.graph); I.graph = nullptr; }
     cudaGraph_t g = nullptr;
     cuda_check(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal), "begin capture");
@@ -544,6 +571,7 @@ void Net::run(cudaStream_t stream, int thresh_u8) {
     cuda_check(cudaGraphInstantiate(&I.graph, g, 0), "graph instantiate");
     cudaGraphDestroy(g);
     I.graph_thresh = thresh_u8;
+    I.graph_src = stem_;
   }
   cuda_check(cudaGraphLaunch(I.graph, stream), "graph launch");
 }

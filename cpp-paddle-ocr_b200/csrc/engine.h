@@ -51,7 +51,10 @@ class Net {
   __half* prepare(int n, int h, int w, const int* widths = nullptr, cudaStream_t stream = nullptr);
   // Execute the forward pass for the last prepared shape on `stream`.
   //   det: `thresh_u8` >= 0 also writes the thresholded bitmap.
-  void run(cudaStream_t stream, int thresh_u8 = -1);
+  // `src` (optional, only when stem_fusable()): the first convolution pre-processes these 8-bit sources on the fly
+  // instead of reading the network input; the caller then skips its pre-processing kernel and the input stays unwritten.
+  void run(cudaStream_t stream, int thresh_u8 = -1, const StemSource* src = nullptr);
+  bool stem_fusable() const;
 
   // Outputs of the last prepared shape (device pointers, valid until the next prepare()).
   Shape3 out_shape() const;              // det: (n, H, W); cls: (n,1,1); rec: (n, 1, T)
@@ -89,6 +92,7 @@ class Net {
   size_t arena_bytes_ = 0;
   std::map<std::tuple<int, int, int>, std::unique_ptr<Inst>> cache_;
   Inst* cur_ = nullptr;
+  StemSource stem_;         // source of the last run(): profile() times the same first layer
   // ragged batches: per tensor, per row valid widths (int[nt][n]); host copy is pageable (see prepare)
   bool ragged_ = false;
   int* vw_pin_ = nullptr;

@@ -122,6 +122,17 @@ void launch_det_preprocess(const DetPreItem* items_dev, int n, int dh, int dw, c
 // [n] ROIs -> [n, dh, dw]; columns >= resize_w hold pad_value (rec: -1 = normalised u8 zero; cls: 0)
 void launch_crop_preprocess(const CropItem* items_dev, int n, int dh, int dw, const NormParams& np, float pad_value,
                             __half* out, cudaStream_t s);
+// The 8-bit sources a network's stem convolution (3 -> 8/16, 3x3, stride 2) can pre-process on the fly instead of
+// reading the network input tensor (kernels_simt.cu: fused_stem_kernel); `items` is device memory.
+struct StemSource {
+  int kind = 0;               // 0: none; 1: DetPreItem[n], every image resized to the input's h x w; 2: CropItem[n]
+  const void* items = nullptr;
+  NormParams np;
+  float pad_value = 0.f;      // CropItem columns [resize_w, pad_w)
+};
+bool fused_stem_eligible(const TV& in, const TV& out, const ConvGeom& g, const Epi& e);
+void launch_fused_stem(const StemSource& src, const TV& in, const TV& out, const __half* w, const float* bias,
+                       const ConvGeom& g, const Epi& e, cudaStream_t s, const int* vw);
 void launch_rotate180_if(uint8_t* img, long stride, int x0, int y0, int w, int h, const int* label_dev, cudaStream_t s);
 void launch_resize_u8(const uint8_t* src, int sw, int sh, long stride, int dw, int dh, uint8_t* out, cudaStream_t s);
 

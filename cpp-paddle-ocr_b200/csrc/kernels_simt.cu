@@ -4,6 +4,7 @@
 // is fp32.  HBM/L2-bound kernels: one thread per (pixel, 8-channel group), coalesced along C.
 #include "kernels.h"
 #include "pdl.h"
+#include "resize.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -494,6 +495,154 @@ stem_conv_s2x4_kernel(TV in, TV out, const __half* __restrict__ w, const float* 
       case 2: stem_store<COUT, 2, PX>(acc, sb, e, out, pix0, ox0, vwn); break;
       default: stem_store<COUT, 0, PX>(acc, sb, e, out, pix0, ox0, vwn); break;
     }
+  }
+}
+
+// First layer fused with the stage's pre-processing: the CTA builds the resized + normalised fp16 input tile of its
+// 32 x TH output pixels in shared memory straight from the 8-bit source (cv::resize INTER_LINEAR + Normalize, the
+// arithmetic of preproc.cu: resize.cuh) and convolves from there, so the [n, h, w, 8] fp16 network input -- written
+// once and read once at 16 B per pixel for 6 B of data -- never exists in HBM (reference: ResizeImgType0 / CrnnResizeImg /
+// ClsResizeImg + Normalize + Permute feeding predictor->Run, src/preprocess_op.cpp:19-137, src/ocr_det.cpp:93-120).
+// Values and summation order are those of det/crop_preprocess followed by stem_conv_s2x4_kernel<COUT, 2>: the output is
+// bit-identical (tests/test_env_paths_gpu.py::test_fused_stem_equals_unfused).
+// The axis coefficients of the tile's 65 columns and 2*TH+1 rows are computed once per CTA (they cost two double
+// divisions each), not once per pixel.
+constexpr int kFsTW = 32;                    // output columns per tile
+constexpr int kFsCols = 2 * kFsTW + 1;       // input columns per tile
+constexpr int kFsPlane = kFsCols / 4 + 1;    // tile columns are stored de-interleaved by (column mod 4): conflict-free reads
+template <int COUT, int KIND>                // KIND 1: DetPreItem (whole images), 2: CropItem (ROIs, right-padded)
+__global__ void __launch_bounds__(128, 4)
+fused_stem_kernel(const void* __restrict__ items_, NormParams np, float pad_value, int dh, int dw, TV out,
+                  const __half* __restrict__ w, const float* __restrict__ bias, ConvGeom g, Epi e,
+                  const int* __restrict__ vw, int th, int tiles_x, int tiles_y) {
+  pdl_trigger();
+  __shared__ __align__(16) float sw[9 * 3 * COUT];
+  __shared__ float sb[COUT];
+  __shared__ uint2 tile[17][4 * kFsPlane];
+  __shared__ resize::Coef cxs[kFsCols], cys[17];
+  // the filter is a constant: fetched while the previous kernel drains
+  for (int i = threadIdx.x; i < 9 * 3 * COUT; i += blockDim.x) {
+    const int co = i % COUT, ci = (i / COUT) % 3, tap = i / (3 * COUT);
+    sw[i] = __half2float(w[(long(co) * 9 + tap) * g.cin_pad + ci]);
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
+  pdl_wait();
+  const int tx = blockIdx.x % tiles_x;
+  const int ty = (blockIdx.x / tiles_x) % tiles_y;
+  const int n = blockIdx.x / (tiles_x * tiles_y);
+  const int ox_t = tx * kFsTW, oy_t = ty * th;
+  const int vwn = vw ? vw[n] : out.w;
+  const int r = threadIdx.x >> 4, strip = threadIdx.x & 15;
+  const int oy = oy_t + r, ox0 = ox_t + strip * 2;
+  const bool active = r < th && oy < out.h && ox0 < out.w;
+  if (ox_t >= vwn) {  // a tile beyond this row's width (ragged batch): zeros, like stem_store's mask
+    if (active) {
+      for (int p = 0; p < 2 && ox0 + p < out.w; ++p)
+        for (int c0 = 0; c0 < COUT; c0 += 8) {
+          H8 o;
+          o.u = make_uint4(0, 0, 0, 0);
+          st8(out.p + ((long(n) * out.h + oy) * out.w + ox0 + p) * out.pitch + c0, o);
+        }
+    }
+    return;
+  }
+  resize::Src src;
+  int rw, pad_w;   // resized width of this item; columns [rw, pad_w) hold the pad value, [pad_w, dw) zero
+  if (KIND == 1) {
+    const DetPreItem it = static_cast<const DetPreItem*>(items_)[n];
+    src = resize::Src{it.src, it.w, it.h, it.stride};
+    rw = dw; pad_w = dw;
+  } else {
+    const CropItem it = static_cast<const CropItem*>(items_)[n];
+    src = resize::Src{it.img + long(it.y) * it.stride + long(it.x) * 3, it.w, it.h, it.stride};
+    rw = it.resize_w; pad_w = it.pad_w;
+  }
+  const int mode = (src.w == rw && src.h == dh) ? 0 : (src.w == 2 * rw && src.h == 2 * dh) ? 1 : 2;  // copy / 2x2 area / bilinear
+  const int rows = 2 * th + 1;
+  const int ix_t = ox_t * 2 - g.pw, iy_t = oy_t * 2 - g.ph;
+  if (mode == 2) {
+    if (threadIdx.x < kFsCols) {
+      const int ix = ix_t + threadIdx.x;
+      if (ix >= 0 && ix < rw) cxs[threadIdx.x] = resize::coef_x(ix, 1.0 / (double(rw) / double(src.w)), src.w);
+    } else if (threadIdx.x < kFsCols + rows) {
+      const int k = threadIdx.x - kFsCols;
+      const int iy = iy_t + k;
+      if (iy >= 0 && iy < dh) cys[k] = resize::coef_y(iy, 1.0 / (double(dh) / double(src.h)));
+    }
+    __syncthreads();
+  }
+  const __half2 pad2 = __floats2half2_rn(pad_value, pad_value);
+  const __half2 pad1 = __floats2half2_rn(pad_value, 0.f);
+  for (int i = threadIdx.x; i < rows * kFsCols; i += blockDim.x) {
+    const int k = i / kFsCols, j = i - k * kFsCols;
+    const int iy = iy_t + k, ix = ix_t + j;
+    uint2 v = make_uint2(0u, 0u);   // the convolution's zero padding, and the ragged filler beyond pad_w
+    if (iy >= 0 && iy < dh && ix >= 0 && ix < dw) {
+      if (ix >= rw) {
+        if (ix < pad_w) { v.x = *reinterpret_cast<const uint32_t*>(&pad2); v.y = *reinterpret_cast<const uint32_t*>(&pad1); }
+      } else {
+        int px[3];
+        if (mode == 0) {
+          const uint8_t* q = src.p + iy * src.stride + ix * 3;
+          px[0] = q[0]; px[1] = q[1]; px[2] = q[2];
+        } else if (mode == 1) {
+          const uint8_t* q0 = src.p + (2 * iy) * src.stride + (2 * ix) * 3;
+          const uint8_t* q1 = q0 + src.stride;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) px[c] = (int(q0[c]) + int(q0[c + 3]) + int(q1[c]) + int(q1[c + 3]) + 2) >> 2;
+        } else {
+          resize::resize_px_coef(src, cxs[j], cys[k], px);
+        }
+        const __half2 ab = __floats2half2_rn(resize::norm1(px[0], np.scale[0], np.shift[0]),
+                                             resize::norm1(px[1], np.scale[1], np.shift[1]));
+        const __half2 c0 = __floats2half2_rn(resize::norm1(px[2], np.scale[2], np.shift[2]), 0.f);
+        v.x = *reinterpret_cast<const uint32_t*>(&ab);
+        v.y = *reinterpret_cast<const uint32_t*>(&c0);
+      }
+    }
+    tile[k][(j & 3) * kFsPlane + (j >> 2)] = v;
+  }
+  __syncthreads();
+  if (!active) return;
+  float acc[2][COUT];
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int i = 0; i < COUT; ++i) acc[p][i] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    float x[5][3];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const uint2 raw = tile[2 * r + ky][(j & 3) * kFsPlane + strip + (j >> 2)];
+      const float2 ab = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+      x[j][0] = ab.x; x[j][1] = ab.y;
+      x[j][2] = __half2float(*reinterpret_cast<const __half*>(&raw.y));
+    }
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float4* wp = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * 3 + ci) * COUT);
+#pragma unroll
+        for (int q = 0; q < COUT / 4; ++q) {
+          const float4 wv = wp[q];
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const float xv = x[2 * p + kx][ci];
+            acc[p][4 * q] = fmaf(xv, wv.x, acc[p][4 * q]);
+            acc[p][4 * q + 1] = fmaf(xv, wv.y, acc[p][4 * q + 1]);
+            acc[p][4 * q + 2] = fmaf(xv, wv.z, acc[p][4 * q + 2]);
+            acc[p][4 * q + 3] = fmaf(xv, wv.w, acc[p][4 * q + 3]);
+          }
+        }
+      }
+  }
+  const long pix0 = (long(n) * out.h + oy) * out.w + ox0;
+  switch (e.act) {
+    case 1: stem_store<COUT, 1, 2>(acc, sb, e, out, pix0, ox0, vwn); break;
+    case 2: stem_store<COUT, 2, 2>(acc, sb, e, out, pix0, ox0, vwn); break;
+    default: stem_store<COUT, 0, 2>(acc, sb, e, out, pix0, ox0, vwn); break;
   }
 }
 
@@ -1365,6 +1514,25 @@ inline int grid_for(long total, int threads = kThreads) {
 }
 
 }  // namespace
+
+bool fused_stem_eligible(const TV& in, const TV& out, const ConvGeom& g, const Epi& e) {
+  static const bool off = getenv("B200OCR_FUSED_STEM") && atoi(getenv("B200OCR_FUSED_STEM")) == 0;
+  return !off && in.c == 3 && g.kh == 3 && g.kw == 3 && g.sh == 2 && g.sw == 2 && g.ph == 1 && g.pw == 1 && e.res == nullptr &&
+         (out.c == 8 || out.c == 16) && e.act >= 0 && e.act <= 2 && out.h == (in.h + 1) / 2 && out.w == (in.w + 1) / 2;
+}
+
+void launch_fused_stem(const StemSource& src, const TV& in, const TV& out, const __half* w, const float* bias,
+                       const ConvGeom& g, const Epi& e, cudaStream_t s, const int* vw) {
+  // rows per tile: 8, or 7 when that divides the output height (the recognizer at rec_img_h 28: 14 rows)
+  const int th = (out.h % 8 != 0 && out.h % 7 == 0) ? 7 : 8;
+  const int tiles_x = (out.w + kFsTW - 1) / kFsTW, tiles_y = (out.h + th - 1) / th;
+  const dim3 grid(unsigned(long(out.n) * tiles_x * tiles_y));
+  auto go = [&](auto kern) {
+    launch_k(kern, grid, dim3(128), 0, s, src.items, src.np, src.pad_value, in.h, in.w, out, w, bias, g, e, vw, th, tiles_x, tiles_y);
+  };
+  if (src.kind == 1) { if (out.c == 16) go(fused_stem_kernel<16, 1>); else go(fused_stem_kernel<8, 1>); }
+  else { if (out.c == 16) go(fused_stem_kernel<16, 2>); else go(fused_stem_kernel<8, 2>); }
+}
 
 void launch_conv_simt(const TV& in, const TV& out, const __half* w, const float* bias,
                       const ConvGeom& g, const Epi& e, cudaStream_t s, const int* vw) {

@@ -134,11 +134,15 @@ void DetStage::run_group(const std::vector<DevImg>& imgs, const std::vector<int>
   cuda_check(cudaMemcpyAsync(info_.p, h_info_.p, sizeof(DbImageInfo) * n, cudaMemcpyHostToDevice, s), "det info");
   static const float mean[3] = {0.485f, 0.456f, 0.406f};                     // reference ocr_det.h:121
   static const float scale[3] = {1 / 0.229f, 1 / 0.224f, 1 / 0.225f};        // reference ocr_det.h:122
-  launch_det_preprocess(items_.as<DetPreItem>(), n, rh, rw, make_norm(mean, scale), in, s);
+  // resize + normalise run inside the first convolution when the graph's stem allows it (kernels_simt.cu: fused_stem_kernel)
+  const bool fuse = net_.stem_fusable();
+  StemSource src;
+  src.kind = 1; src.items = items_.p; src.np = make_norm(mean, scale);
+  if (!fuse) launch_det_preprocess(items_.as<DetPreItem>(), n, rh, rw, src.np, in, s);
   t_ms[0] += ms_since(t0);
   t0 = Clock::now();
-  net_.run(s, thresh_u8_);
-  launches += net_.launches_per_run() + 1;
+  net_.run(s, thresh_u8_, fuse ? &src : nullptr);
+  launches += net_.launches_per_run() + (fuse ? 0 : 1);
   t_ms[1] += ms_since(t0);
   t0 = Clock::now();
   DbPostParams pp;
@@ -263,10 +267,13 @@ void ClsStage::run(const std::vector<DevImg>& imgs, const std::vector<Roi>& rois
     if (b0 == 0) { prof_n = nb; prof_h = 48; prof_w = 192; }
     __half* in = net_.prepare(nb, 48, 192, nullptr, s);
     // pad value 0.0: the classifier pads AFTER normalisation (src/ocr_cls.cpp:52-56)
-    launch_crop_preprocess(items_.as<CropItem>() + b0, nb, 48, 192, make_norm(kMean05, kScale2), 0.f, in, s);
+    const bool fuse = net_.stem_fusable();
+    StemSource src;
+    src.kind = 2; src.items = items_.as<CropItem>() + b0; src.np = make_norm(kMean05, kScale2); src.pad_value = 0.f;
+    if (!fuse) launch_crop_preprocess(items_.as<CropItem>() + b0, nb, 48, 192, src.np, 0.f, in, s);
     t[0] += ms_since(t0);
     t0 = Clock::now();
-    net_.run(s);
+    net_.run(s, -1, fuse ? &src : nullptr);
     t[1] += ms_since(t0);
     t0 = Clock::now();
     const int ncls = net_.plan().layers.back().cout;
@@ -430,8 +437,11 @@ void RecStage::run(const std::vector<DevImg>& imgs, const std::vector<std::vecto
     for (int k = 0; k < ch.nb; ++k) widths[k] = rows[ch.b0 + k].width;
     __half* in = net_.prepare(ch.nb, img_h_, ch.wmax, widths.data(), s);
     // pad value -1.0: CrnnResizeImg pads with u8 zeros BEFORE normalisation (src/preprocess_op.cpp:115-117)
-    launch_crop_preprocess(items_.as<CropItem>() + ch.b0, ch.nb, img_h_, ch.wmax, make_norm(kMean05, kScale2), -1.f, in, s);
-    net_.run(s);
+    const bool fuse = net_.stem_fusable();
+    StemSource src;
+    src.kind = 2; src.items = items_.as<CropItem>() + ch.b0; src.np = make_norm(kMean05, kScale2); src.pad_value = -1.f;
+    if (!fuse) launch_crop_preprocess(items_.as<CropItem>() + ch.b0, ch.nb, img_h_, ch.wmax, src.np, -1.f, in, s);
+    net_.run(s, -1, fuse ? &src : nullptr);
     ch.T = net_.out_shape().w;
     if (size_t(ch.nb) * ch.T > size_t(ch.nb) * (ch.wmax / 8 + 2)) throw std::runtime_error("rec: unexpected sequence length");
     launch_ctc_collapse(net_.out_idx(), net_.out_f32(), ch.nb, ch.T, cidx_.as<int>() + ch.off, clen_.as<int>() + ch.b0,

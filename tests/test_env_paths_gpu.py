@@ -89,3 +89,65 @@ def test_switch_agrees_with_default(models_dir, tmp_path, default, env, exact):
             assert diff.mean() < 0.05, (k, diff.mean())
         else:
             assert np.allclose(got[k], ref, rtol=0, atol=3e-2), (k, np.abs(got[k] - ref).max())
+
+
+# The stem convolution that pre-processes on the fly (kernels_simt.cu: fused_stem_kernel) only exists at the stage level
+# (8-bit sources), so it is compared through the stages: detector boxes, classifier scores, recognizer strings / scores and
+# the worker's result lines -- minus the elapsed-time field -- must be IDENTICAL with B200OCR_FUSED_STEM=0 (the stand-alone
+# det/crop_preprocess kernels + stem_conv_s2x4): same fp16 input values, same summation order.
+STAGE_SCRIPT = r"""
+import json, os, sys, numpy as np
+root = sys.argv[1]
+for p in (root, os.path.join(root, "cpp-paddle-ocr_b200"), os.path.join(root, "tools")):
+    sys.path.insert(0, p)
+import cv2
+import b200ocr, synth_data
+models = sys.argv[2]
+imgs = [cv2.imread(os.path.join(root, "tests", "golden", "card-jd.jpg")), synth_data.reference_test_image(),
+        synth_data.card(3), synth_data.card(4, 800, 500), synth_data.card(5, 1023, 637)]
+out = {}
+det = b200ocr.Detector(f"{models}/det")
+boxes = [det.run(im) for im in imgs]
+out["det"] = [np.asarray(b).tolist() for b in boxes]
+crops = []
+for im, bs in zip(imgs, boxes):
+    for b in np.asarray(bs).reshape(-1, 4, 2)[:12]:
+        x0, y0 = b.min(0); x1, y1 = b.max(0)
+        c = im[max(y0, 0):y1 + 1, max(x0, 0):x1 + 1]
+        if c.size: crops.append(np.ascontiguousarray(c))
+cls = b200ocr.Classifier(f"{models}/cls")
+labels, scores = cls.run(crops)
+out["cls"] = [list(map(int, labels)), [float(s).hex() for s in scores]]
+for h in (28, 48):
+    rec = b200ocr.Recognizer(f"{models}/rec", f"{models}/rec/ppocr_keys_v1.txt", rec_img_h=h)
+    texts, sc = rec.run(crops)
+    out[f"rec{h}"] = [list(texts), [float(s).hex() for s in sc]]
+w = b200ocr.Worker(0, models, enable_cls=True)
+lines = w.process_batch(list(range(len(imgs))), imgs)
+res = []
+for l in lines:
+    d = json.loads(l)
+    d.pop("processing_time_ms", None)
+    res.append(d)
+out["worker"] = res
+json.dump(out, open(sys.argv[3], "w"))
+"""
+
+
+def _run_stages(models_dir, tmp_path, name, env):
+    import json
+    path = os.path.join(str(tmp_path), name + ".json")
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", STAGE_SCRIPT, ROOT, models_dir, path], capture_output=True, text=True, env=e,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return json.load(open(path))
+
+
+def test_fused_stem_equals_unfused(models_dir, tmp_path):
+    fused = _run_stages(models_dir, tmp_path, "fused", {})
+    plain = _run_stages(models_dir, tmp_path, "plain", {"B200OCR_FUSED_STEM": "0"})
+    assert sum(len(b) for b in fused["det"]) > 20 and len(fused["worker"]) == 5
+    for k in fused:
+        assert fused[k] == plain[k], k
