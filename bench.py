@@ -531,8 +531,9 @@ def run_pool(args):
         raise SystemExit(f"--pool --gpus {N}: only {b200ocr.device_count()} devices visible")
     B, K, W = (args.batch or 192), args.steps, args.warmup
     cores = len(os.sched_getaffinity(0))
-    # threads: per device `wpd` workers (spinning on their streams) + one uploader; the feeders mostly sleep
-    wpd = args.workers if args.workers > 0 else min(3, max(1, (cores - 2 * N) // N))
+    # threads: per device `wpd` workers (spinning on their streams) + one uploader (sleeps while its DMAs run); the
+    # submitting threads mostly sleep too: same rule as the one-process-per-GPU arm
+    wpd = args.workers if args.workers > 0 else min(3, max(1, cores // N))
     max_batch = max(8, B // wpd)
     n_feed = min(32, max(4, 2 * N))
     n_warm, n_timed = W * N * B, K * N * B

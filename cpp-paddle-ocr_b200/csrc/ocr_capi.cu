@@ -178,9 +178,12 @@ struct b200ocr_pool {
 
   void upload_loop(Device* d) {
     cudaStream_t stream = nullptr;
+    cudaEvent_t landed = nullptr;   // blocking wait: the uploader sleeps while its DMAs run (the host cores belong to the workers)
     if (cudaSetDevice(d->device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&landed, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
       cudaGetLastError();
+      if (stream) cudaStreamDestroy(stream);
       stream = nullptr;   // every job fails with a message below
     }
     std::vector<CopyJob*> jobs;
@@ -204,7 +207,7 @@ struct b200ocr_pool {
           j->error = e.what()[0] ? e.what() : "image clone failed";
         }
       }
-      if (stream && cudaStreamSynchronize(stream) != cudaSuccess) {
+      if (stream && (cudaEventRecord(landed, stream) != cudaSuccess || cudaEventSynchronize(landed) != cudaSuccess)) {
         const char* msg = cudaGetErrorString(cudaGetLastError());
         for (CopyJob* j : jobs) if (j->error.empty()) j->error = std::string("image clone: ") + msg;
       }
@@ -220,6 +223,7 @@ struct b200ocr_pool {
       }
       d->copy_done_cv.notify_all();
     }
+    if (landed) cudaEventDestroy(landed);
     if (stream) cudaStreamDestroy(stream);
   }
 
