@@ -118,6 +118,28 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// ---- 2-CTA cluster helpers (filter multicast, conv_tc_kernel<ACT, 1>)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one L2 read, delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -251,7 +273,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& a, const float* 
   }
 }
 
-template <int ACT>
+// MC = 1: launched as clusters of two CTAs that work on two neighbouring pixel tiles of the SAME N tile.  Each CTA fetches
+// half of every filter tile and multicasts it into both CTAs' shared memory, so a filter byte crosses the L2 -> SM fabric
+// once per 256 pixels instead of once per 128.  For the layers whose filter block does not fit next to the A ring (the
+// recognizer's 480 -> 480 convolutions re-stream 230 KB of filter per pixel tile and N tile and are bound by exactly that
+// traffic, profiles/r02_notes.md section 10) this removes a third of the bytes a CTA pulls per K step (46 -> 31 KB).
+// A stage is free again when BOTH CTAs' MMAs have read it (the peer writes into it): the empty barriers count two
+// arrivals and every tcgen05.commit is multicast to the pair.
+template <int ACT, int MC>
 __global__ void __launch_bounds__(kThreadsTc)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcArgs a) {
@@ -270,8 +299,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   // tile coordinates.  The N tiles of one pixel tile are neighbours in launch order (blockIdx.x = tile * n_tiles +
   // nblk): they run at the same time and the second one finds the activation tile in L2.
-  int t = blockIdx.x / a.n_tiles;
-  const int nblk = blockIdx.x - t * a.n_tiles;  // N tile index
+  int t, nblk;
+  uint32_t rank = 0;
+  if (MC) {  // pair p = blockIdx.x / 2 -> (pixel tile pair, N tile); the pair's CTAs take pixel tiles 2j and 2j + 1
+    rank = cluster_ctarank();
+    const int p = int(blockIdx.x >> 1);
+    t = (p / a.n_tiles) * 2 + int(rank);
+    nblk = p % a.n_tiles;
+  } else {
+    t = blockIdx.x / a.n_tiles;
+    nblk = blockIdx.x - t * a.n_tiles;  // N tile index
+  }
   const int tx = t % a.tiles_x; t /= a.tiles_x;
   const int ty = t % a.tiles_y; t /= a.tiles_y;
   const int x0 = tx * a.tw, y0 = ty * a.th, n0 = t * a.tn;
@@ -283,7 +321,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC ? 2 : 1);
     }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -297,12 +335,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (MC) cluster_sync_all();  // the peer's barriers are initialised before anything of ours can reach them
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();  // everything above (barriers, TMEM, tensor maps) overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t tx_bytes = uint32_t(a.tw * a.th * a.tn * 128 + a.bn * 128);
+      const int half_rows = a.bn >> 1;
       int it = 0;
       for (int ky = 0; ky < a.kh; ++ky)
         for (int kx = 0; kx < a.kw; ++kx)
@@ -314,7 +354,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint8_t* sb = sa + kATileBytes;
             mbar_expect_tx(&full_bar[s], tx_bytes);
             tma_load_4d(&tmA, &full_bar[s], sa, kc * 64, x0 + kx - a.pw, y0 + ky - a.ph, n0);
-            tma_load_2d(&tmB, &full_bar[s], sb, (ky * a.kw + kx) * a.cin_pad + kc * 64, nblk * a.bn);
+            if (MC)   // tmB's box is half an N tile here: this CTA's half goes to both CTAs
+              tma_load_2d_mc(&tmB, &full_bar[s], sb + size_t(rank) * half_rows * 128, (ky * a.kw + kx) * a.cin_pad + kc * 64,
+                             nblk * a.bn + int(rank) * half_rows, uint16_t(3));
+            else
+              tma_load_2d(&tmB, &full_bar[s], sb, (ky * a.kw + kx) * a.cin_pad + kc * 64, nblk * a.bn);
           }
     }
   } else if (warp == 1) {
@@ -333,7 +377,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int k16 = rem >= 64 ? 4 : (rem + 15) >> 4;
           const uint32_t alo = umma_desc_lo(sa), blo = umma_desc_lo(sb);
           for (int k = 0; k < k16; ++k) umma_f16_lo(tmem_base, alo + 2 * k, blo + 2 * k, idesc, (it | k) != 0);
-          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+          if (MC) umma_commit_mc(&empty_bar[s], uint16_t(3));  // ... in both CTAs: the peer's producer writes this stage too
+          else umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
         }
       umma_commit(tmem_full);
     }
@@ -344,6 +389,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer's last commits arrive on OUR barriers: stay resident until it is done too
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(uint32_t(a.tmem_cols))
@@ -567,6 +613,7 @@ struct ConvTcPlanImpl {
   dim3 grid;
   size_t smem;
   bool persistent = false;
+  bool multicast = false;  // non-persistent kernel launched as 2-CTA clusters sharing the filter stream
   int n_mtiles = 0, kt = 0;
 };
 
@@ -715,6 +762,18 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
       }
     }
   }
+  // ---- filter multicast for the layers that stay on the non-persistent kernel (see conv_tc_kernel<ACT, 1>)
+  {
+    static const int mc_min = getenv("B200OCR_CONV_MULTICAST_MIN") ? atoi(getenv("B200OCR_CONV_MULTICAST_MIN")) : 296;
+    static const bool mc_off = getenv("B200OCR_CONV_MULTICAST") && atoi(getenv("B200OCR_CONV_MULTICAST")) == 0;
+    const int m_tiles = a.tiles_x * a.tiles_y * tiles_n;
+    if (!impl->persistent && !mc_off && pointwise && m_tiles >= mc_min && (a.bn & 15) == 0 && a.stages >= 2) {
+      impl->multicast = true;
+      cuuint32_t bH[2] = {64, cuuint32_t(a.bn / 2)};
+      encode(&impl->tmB, const_cast<__half*>(w), 2, dB, sB, bH);
+      impl->grid = dim3(unsigned(2 * ((m_tiles + 1) / 2) * n_tiles), 1u);
+    }
+  }
   impl->args = a;
   // function attributes live in the device context: set once per device
   {
@@ -724,12 +783,18 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(mu);
     if (dev >= 64 || !done[dev]) {
-    cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv_tc_persist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(conv_tc_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(conv_tc_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -767,13 +832,24 @@ void launch_conv_tc(const ConvTcPlan& p, const float* bias, const Epi& e, cudaSt
     }
     return;
   }
+  if (p.impl->multicast) {
+    switch (e.act) {
+      case 1: launch_k_cluster(conv_tc_kernel<1, 1>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, 2, p.impl->tmA, p.impl->tmB, a); break;
+      case 2: launch_k_cluster(conv_tc_kernel<2, 1>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, 2, p.impl->tmA, p.impl->tmB, a); break;
+      case 3: launch_k_cluster(conv_tc_kernel<3, 1>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, 2, p.impl->tmA, p.impl->tmB, a); break;
+      case 4: launch_k_cluster(conv_tc_kernel<4, 1>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, 2, p.impl->tmA, p.impl->tmB, a); break;
+      case 5: launch_k_cluster(conv_tc_kernel<5, 1>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, 2, p.impl->tmA, p.impl->tmB, a); break;
+      default: launch_k_cluster(conv_tc_kernel<0, 1>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, 2, p.impl->tmA, p.impl->tmB, a); break;
+    }
+    return;
+  }
   switch (e.act) {
-    case 1: launch_k(conv_tc_kernel<1>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
-    case 2: launch_k(conv_tc_kernel<2>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
-    case 3: launch_k(conv_tc_kernel<3>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
-    case 4: launch_k(conv_tc_kernel<4>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
-    case 5: launch_k(conv_tc_kernel<5>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
-    default: launch_k(conv_tc_kernel<0>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
+    case 1: launch_k(conv_tc_kernel<1, 0>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
+    case 2: launch_k(conv_tc_kernel<2, 0>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
+    case 3: launch_k(conv_tc_kernel<3, 0>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
+    case 4: launch_k(conv_tc_kernel<4, 0>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
+    case 5: launch_k(conv_tc_kernel<5, 0>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
+    default: launch_k(conv_tc_kernel<0, 0>, dim3(p.impl->grid), dim3(kThreadsTc), p.impl->smem, s, p.impl->tmA, p.impl->tmB, a); break;
   }
 }
 
