@@ -765,7 +765,7 @@ ConvTcPlan make_conv_tc_plan(const TV& in_, const TV& out_, const __half* w, con
   // ---- filter multicast for the layers that stay on the non-persistent kernel (see conv_tc_kernel<ACT, 1>)
   {
     static const int mc_min = getenv("B200OCR_CONV_MULTICAST_MIN") ? atoi(getenv("B200OCR_CONV_MULTICAST_MIN")) : 296;
-    static const bool mc_off = getenv("B200OCR_CONV_MULTICAST") && atoi(getenv("B200OCR_CONV_MULTICAST")) == 0;
+    static const bool mc_off = !(getenv("B200OCR_CONV_MULTICAST") && atoi(getenv("B200OCR_CONV_MULTICAST")) != 0);  // opt-in until measured
     const int m_tiles = a.tiles_x * a.tiles_y * tiles_n;
     if (!impl->persistent && !mc_off && pointwise && m_tiles >= mc_min && (a.bn & 15) == 0 && a.stages >= 2) {
       impl->multicast = true;

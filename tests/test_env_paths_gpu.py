@@ -74,8 +74,8 @@ VARIANTS = [
     ({"B200OCR_NO_PWCONV": "1"}, False),          # narrow 1x1 convolutions on tcgen05 instead of the mma.sync stream
     ({"B200OCR_NO_SE_APPLY_FUSE": "1"}, True),    # SE gate applied by scale_kernel instead of the pool + gate kernel
     ({"B200OCR_PDL": "0"}, True),                 # no programmatic dependent launch
-    ({"B200OCR_CONV_MULTICAST_MIN": "1"}, True),  # every non-persistent 1x1 convolution as 2-CTA clusters with filter multicast
-    ({"B200OCR_CONV_MULTICAST": "0"}, True),      # never
+    # every non-persistent 1x1 convolution as 2-CTA clusters with filter multicast
+    ({"B200OCR_CONV_MULTICAST": "1", "B200OCR_CONV_MULTICAST_MIN": "1"}, True),
 ]
 
 
