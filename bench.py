@@ -535,7 +535,7 @@ def run_pool(args):
     # submitting threads mostly sleep too: same rule as the one-process-per-GPU arm
     wpd = args.workers if args.workers > 0 else min(3, max(1, cores // N))
     max_batch = max(8, B // wpd)
-    n_feed = min(32, max(4, 2 * N))
+    n_feed = min(64, max(8, 8 * N))   # submit() returns when the clone has landed (~0.3-0.6 ms): many threads, mostly asleep
     n_warm, n_timed = W * N * B, K * N * B
     distinct = min(n_warm + n_timed, 2048)
     t0 = time.perf_counter()

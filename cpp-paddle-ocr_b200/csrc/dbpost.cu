@@ -40,10 +40,24 @@ __device__ __forceinline__ int uf_find(const int* L, int i) {
   while (p != i) { i = p; p = L[i]; }
   return i;
 }
+// The same with path halving (the intermediate pointer jumping of ECL-CC, Jaiganesh & Burtscher, HPDC 2018): every
+// element the walk passes is re-pointed at its grandparent.  Parents only ever move towards the root of the same set, so
+// the plain stores race benignly with each other and with uf_union's atomicMin (which only ever LINKS at a root; a
+// non-root never becomes a root again).  Without it the frame-connected background -- one run per row, each linked to
+// the row above -- is a chain as long as the map is high, walked in full by every union and every pixel of the flatten
+// pass.  The labels that come out are the same: the smallest pixel index of the component.
+__device__ __forceinline__ int uf_find_halving(int* L, int i) {
+  int cur = L[i];
+  if (cur != i) {
+    int prev = i, next;
+    while (cur > (next = L[cur])) { L[prev] = next; prev = cur; cur = next; }
+  }
+  return cur;
+}
 __device__ __forceinline__ void uf_union(int* L, int a, int b) {
   while (true) {
-    a = uf_find(L, a);
-    b = uf_find(L, b);
+    a = uf_find_halving(L, a);
+    b = uf_find_halving(L, b);
     if (a == b) return;
     if (a > b) { const int t = a; a = b; b = t; }
     const int old = atomicMin(&L[b], a);
@@ -135,6 +149,7 @@ ccl_flatten_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int* __r
   pdl_wait();
   const long per = long(h) * w, total = per * n;
   for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < total; t += long(gridDim.x) * blockDim.x) {
+    // read-only walk: a halving store of another thread could land after this pixel's final label and leave it non-flat
     const int root = uf_find(L, int(t));
     L[t] = root;
     if (bm[t] == 0) {
@@ -374,7 +389,10 @@ list_kernel(const int* __restrict__ flag, int h, int w, int max_cand, int* __res
 }
 
 // ---------------------------------------------------------------- 4. one CTA per candidate
-constexpr int kBoxThreads = 512;   // the border scan and the masked mean are latency-bound: more pixels in flight per candidate
+// 128 threads: the candidates of a batch (~10 per card) then all run at the same time, five CTAs per SM.  Measured with 512
+// threads (one CTA per SM at 112 registers): 134 us instead of 81 us for 32 cards -- the kernel's duration is the latency
+// of its slowest candidate (thread 0's hull / calipers / Clipper offset in double precision), not the pixel scans.
+constexpr int kBoxThreads = 128;
 constexpr int kHullCap = 1024;
 
 __device__ __forceinline__ double block_sum(double v, double* sh) {

@@ -120,7 +120,17 @@ class BufferPool {
 
 struct b200ocr_pool {
   BufferPool pinned{false, 0};
+  // What b200ocr_pool_wait sleeps on: one per request, so a finished batch wakes exactly the threads that wait for ITS
+  // requests (a single condition variable for the pool woke every waiter on every batch: with 64 client threads and
+  // 10^4 batches/s the clients did nothing but wake up and go back to sleep, profiles/r02_notes.md section 8).
+  struct Pending {
+    std::mutex mu;
+    std::condition_variable cv;
+    bool done = false;
+    std::string json;
+  };
   struct Request {
+    std::shared_ptr<Pending> pending;
     long long ticket;
     int request_id;
     BufferPool* owner = nullptr;
@@ -142,6 +152,7 @@ struct b200ocr_pool {
     size_t step = 0, row = 0;
     bool done = false;
     std::string error;
+    std::condition_variable cv;   // waited on with the device's copy_mu: only this job's submitter wakes
   };
   struct Device {
     explicit Device(int dev) : device(dev), pixels(true, dev) {}
@@ -149,7 +160,7 @@ struct b200ocr_pool {
     int device;
     BufferPool pixels;              // declared before the queues: destroyed after the requests that point into it
     std::mutex copy_mu;
-    std::condition_variable copy_cv, copy_done_cv;
+    std::condition_variable copy_cv;
     std::deque<CopyJob*> copy_q;
     std::atomic<int> copying{0};    // jobs handed to the uploader and not yet in `queue` (counted as load by the dispatch)
     std::thread uploader;
@@ -165,9 +176,8 @@ struct b200ocr_pool {
   std::atomic<long long> next_ticket{1};
   std::atomic<size_t> rr{0};
   std::mutex res_mu;
-  std::condition_variable res_cv;
-  std::map<long long, std::string> results;
-  std::set<long long> outstanding;   // issued and not yet consumed by b200ocr_pool_wait (guarded by res_mu)
+  std::condition_variable res_cv;    // destructor <- last waiter
+  std::map<long long, std::shared_ptr<Pending>> outstanding;   // issued and not yet consumed by b200ocr_pool_wait (guarded by res_mu)
   int waiters = 0;                   // threads inside b200ocr_pool_wait (guarded by res_mu)
   int max_batch = 64;
   // status counters (reference OCRIPCService::getStatusInfo, src/ocr_ipc_service.cpp:438-448 -- whose success / time
@@ -176,55 +186,71 @@ struct b200ocr_pool {
   std::atomic<long long> total_time_us{0};   // sum over requests of (completion - submission)
   std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
 
+  // Two slots (stream + event + job list) alternate: while slot k's DMAs run, the uploader collects and queues slot
+  // k+1's copies, then sleeps on slot k's event, hands its requests to the workers and wakes their submitters.
   void upload_loop(Device* d) {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t landed = nullptr;   // blocking wait: the uploader sleeps while its DMAs run (the host cores belong to the workers)
-    if (cudaSetDevice(d->device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&landed, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
-      cudaGetLastError();
-      if (stream) cudaStreamDestroy(stream);
-      stream = nullptr;   // every job fails with a message below
-    }
-    std::vector<CopyJob*> jobs;
-    while (true) {
-      jobs.clear();
+    struct Slot {
+      cudaStream_t stream = nullptr;
+      cudaEvent_t landed = nullptr;   // blocking wait: the uploader sleeps while its DMAs run (the host cores belong to the workers)
+      std::vector<CopyJob*> jobs;
+    } slot[2];
+    bool ok = cudaSetDevice(d->device) == cudaSuccess;
+    for (auto& sl : slot)
+      ok = ok && cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&sl.landed, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) cudaGetLastError();   // every job fails with a message below
+    auto finish = [&](Slot& sl) {
+      if (sl.jobs.empty()) return;
+      if (ok && cudaEventSynchronize(sl.landed) != cudaSuccess) {
+        const char* msg = cudaGetErrorString(cudaGetLastError());
+        for (CopyJob* j : sl.jobs) if (j->error.empty()) j->error = std::string("image clone: ") + msg;
+      }
+      {  // the clones are on the device: hand the requests to the workers ...
+        std::lock_guard<std::mutex> lk(d->mu);
+        for (CopyJob* j : sl.jobs) if (j->error.empty()) d->queue.push_back(j->r);
+        d->copying -= int(sl.jobs.size());
+      }
+      d->cv.notify_all();
+      {  // ... then release the submitting threads (a job lives on its submitter's stack: notify under the lock)
+        std::lock_guard<std::mutex> lk(d->copy_mu);
+        for (CopyJob* j : sl.jobs) { j->done = true; j->cv.notify_one(); }
+      }
+      sl.jobs.clear();
+    };
+    for (int cur = 0;; cur ^= 1) {
+      Slot& sl = slot[cur];
+      Slot& other = slot[cur ^ 1];
+      bool stop = false;
       {
         std::unique_lock<std::mutex> lk(d->copy_mu);
-        d->copy_cv.wait(lk, [&] { return !d->copy_q.empty() || !running; });
-        if (d->copy_q.empty()) break;   // shutting down and drained
-        while (!d->copy_q.empty() && jobs.size() < 64) { jobs.push_back(d->copy_q.front()); d->copy_q.pop_front(); }
+        // with copies in flight in the other slot, do not sleep here: take what is waiting (possibly nothing)
+        if (other.jobs.empty()) d->copy_cv.wait(lk, [&] { return !d->copy_q.empty() || !running; });
+        stop = d->copy_q.empty() && !running;
+        while (!d->copy_q.empty() && sl.jobs.size() < 32) { sl.jobs.push_back(d->copy_q.front()); d->copy_q.pop_front(); }
       }
-      for (CopyJob* j : jobs) {
+      for (CopyJob* j : sl.jobs) {
         try {
-          if (!stream) throw std::runtime_error("the pool's copy stream could not be created");
+          if (!ok) throw std::runtime_error("the pool's copy stream could not be created");
           Request& r = *j->r;
           r.owner = &d->pixels;
           r.data = d->pixels.take(r.size, &r.cap);
-          if (j->step == j->row) cuda_check(cudaMemcpyAsync(r.data, j->src, r.size, cudaMemcpyHostToDevice, stream), "image clone");
-          else cuda_check(cudaMemcpy2DAsync(r.data, j->row, j->src, j->step, j->row, r.rows, cudaMemcpyHostToDevice, stream), "image clone");
+          if (j->step == j->row) cuda_check(cudaMemcpyAsync(r.data, j->src, r.size, cudaMemcpyHostToDevice, sl.stream), "image clone");
+          else cuda_check(cudaMemcpy2DAsync(r.data, j->row, j->src, j->step, j->row, r.rows, cudaMemcpyHostToDevice, sl.stream), "image clone");
         } catch (const std::exception& e) {
           j->error = e.what()[0] ? e.what() : "image clone failed";
         }
       }
-      if (stream && (cudaEventRecord(landed, stream) != cudaSuccess || cudaEventSynchronize(landed) != cudaSuccess)) {
+      if (ok && !sl.jobs.empty() && cudaEventRecord(sl.landed, sl.stream) != cudaSuccess) {
         const char* msg = cudaGetErrorString(cudaGetLastError());
-        for (CopyJob* j : jobs) if (j->error.empty()) j->error = std::string("image clone: ") + msg;
+        for (CopyJob* j : sl.jobs) if (j->error.empty()) j->error = std::string("image clone: ") + msg;
       }
-      {  // the clones are on the device: hand the requests to the workers, then release the submitting threads
-        std::lock_guard<std::mutex> lk(d->mu);
-        for (CopyJob* j : jobs) if (j->error.empty()) d->queue.push_back(j->r);
-        d->copying -= int(jobs.size());
-      }
-      d->cv.notify_all();
-      {
-        std::lock_guard<std::mutex> lk(d->copy_mu);
-        for (CopyJob* j : jobs) j->done = true;
-      }
-      d->copy_done_cv.notify_all();
+      finish(other);
+      if (stop && sl.jobs.empty()) break;   // shutting down and drained
     }
-    if (landed) cudaEventDestroy(landed);
-    if (stream) cudaStreamDestroy(stream);
+    for (auto& sl : slot) {
+      if (sl.landed) cudaEventDestroy(sl.landed);
+      if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
   }
 
   void loop(Device* d, Worker* w) {
@@ -295,10 +321,12 @@ struct b200ocr_pool {
           total_time_us += std::chrono::duration_cast<std::chrono::microseconds>(now - take[i]->t_submit).count();
         }
         batches += 1;
-        std::lock_guard<std::mutex> lk(res_mu);
-        for (size_t i = 0; i < take.size(); ++i) results[take[i]->ticket] = std::move(out[i]);
+        for (size_t i = 0; i < take.size(); ++i) {
+          Pending& p = *take[i]->pending;
+          { std::lock_guard<std::mutex> lk(p.mu); p.json = std::move(out[i]); p.done = true; }
+          p.cv.notify_all();
+        }
       }
-      res_cv.notify_all();
       d->busy -= 1;
     }
   }
@@ -307,7 +335,10 @@ struct b200ocr_pool {
     running = false;
     {  // waiters return B200OCR_ERR_RUNTIME instead of touching a destroyed condition variable
       std::unique_lock<std::mutex> lk(res_mu);
-      res_cv.notify_all();
+      for (auto& kv : outstanding) {
+        { std::lock_guard<std::mutex> pl(kv.second->mu); }
+        kv.second->cv.notify_all();
+      }
       res_cv.wait(lk, [&] { return waiters == 0; });
     }
     for (auto& d : devs) {
@@ -758,7 +789,8 @@ static b200ocr_pool::Device& pool_pick_device(b200ocr_pool_t pool) {
   return *pool->devs[best];
 }
 static void pool_enqueue(b200ocr_pool_t pool, b200ocr_pool::Device& d, const std::shared_ptr<b200ocr_pool::Request>& r) {
-  { std::lock_guard<std::mutex> lk(pool->res_mu); pool->outstanding.insert(r->ticket); }
+  r->pending = std::make_shared<b200ocr_pool::Pending>();
+  { std::lock_guard<std::mutex> lk(pool->res_mu); pool->outstanding.emplace(r->ticket, r->pending); }
   { std::lock_guard<std::mutex> lk(d.mu); d.queue.push_back(r); }
   d.cv.notify_one();
 }
@@ -794,13 +826,14 @@ int b200ocr_pool_submit(b200ocr_pool_t pool, int request_id, const b200ocr_image
         else for (int y = 0; y < img->rows; ++y) memcpy(bounce + y * row, img->data + y * step, row);
         job.src = bounce; job.step = row;
       }
-      { std::lock_guard<std::mutex> lk(pool->res_mu); pool->outstanding.insert(r->ticket); }
+      r->pending = std::make_shared<b200ocr_pool::Pending>();
+      { std::lock_guard<std::mutex> lk(pool->res_mu); pool->outstanding.emplace(r->ticket, r->pending); }
       {
         std::unique_lock<std::mutex> lk(d.copy_mu);
         d.copying += 1;
         d.copy_q.push_back(&job);
         d.copy_cv.notify_one();
-        d.copy_done_cv.wait(lk, [&] { return job.done; });
+        job.cv.wait(lk, [&] { return job.done; });
       }
       if (bounce) pool->pinned.give(bounce, bounce_cap);
       if (!job.error.empty()) {
@@ -840,21 +873,36 @@ int b200ocr_pool_wait_for(b200ocr_pool_t pool, long long ticket, int timeout_ms,
   return capi_guard([&] {
     if (!pool || !json) throw std::invalid_argument("null argument");
     *json = nullptr;
-    std::unique_lock<std::mutex> lk(pool->res_mu);
-    if (!pool->outstanding.count(ticket)) throw std::invalid_argument("unknown or already consumed ticket");
+    std::shared_ptr<b200ocr_pool::Pending> p;
+    {
+      std::lock_guard<std::mutex> lk(pool->res_mu);
+      auto it = pool->outstanding.find(ticket);
+      if (it == pool->outstanding.end()) throw std::invalid_argument("unknown or already consumed ticket");
+      p = it->second;
+      ++pool->waiters;
+    }
     struct Count {
-      b200ocr_pool* p;
-      explicit Count(b200ocr_pool* q) : p(q) { ++p->waiters; }
-      ~Count() { --p->waiters; p->res_cv.notify_all(); }
-    } count(pool);
-    auto ready = [&] { return pool->results.count(ticket) != 0 || !pool->running; };
-    if (timeout_ms < 0) pool->res_cv.wait(lk, ready);
-    else if (!pool->res_cv.wait_for(lk, std::chrono::milliseconds(timeout_ms), ready)) return;  // *json stays NULL
-    auto it = pool->results.find(ticket);
-    if (it == pool->results.end()) throw std::runtime_error("the pool is shutting down");
-    *json = dup_string(it->second);
-    pool->results.erase(it);
-    pool->outstanding.erase(ticket);
+      b200ocr_pool* q;
+      ~Count() {
+        std::lock_guard<std::mutex> lk(q->res_mu);
+        if (--q->waiters == 0) q->res_cv.notify_all();
+      }
+    } count{pool};
+    std::string line;
+    {
+      std::unique_lock<std::mutex> lk(p->mu);
+      auto ready = [&] { return p->done || !pool->running; };
+      if (timeout_ms < 0) p->cv.wait(lk, ready);
+      else if (!p->cv.wait_for(lk, std::chrono::milliseconds(timeout_ms), ready)) return;  // *json stays NULL
+      if (!p->done) throw std::runtime_error("the pool is shutting down");
+      line = std::move(p->json);
+      p->json.clear();
+    }
+    {
+      std::lock_guard<std::mutex> lk(pool->res_mu);
+      if (pool->outstanding.erase(ticket) == 0) throw std::invalid_argument("unknown or already consumed ticket");  // a second waiter took it
+    }
+    *json = dup_string(line);
   });
 }
 int b200ocr_pool_wait(b200ocr_pool_t pool, long long ticket, char** json) {

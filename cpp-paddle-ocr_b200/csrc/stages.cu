@@ -47,19 +47,31 @@ void ImageBatch::upload(const HostImage* imgs, int n, cudaStream_t s) {
   dev_.ensure(total);
   imgs_.resize(n);
   bytes_ = 0;
+  // images that follow each other in host memory the way they do in the device buffer (a caller's frame array) travel
+  // as ONE copy: the run [run0, i) is flushed when image i does not continue it
+  int run0 = 0;
+  size_t run_bytes = 0;
+  auto flush = [&](int upto) {
+    if (run_bytes) cuda_check(cudaMemcpyAsync(imgs_[run0].p, imgs[run0].data, run_bytes, cudaMemcpyHostToDevice, s), "image upload");
+    run0 = upto; run_bytes = 0;
+  };
   for (int i = 0; i < n; ++i) {
     DevImg d;
     d.p = dev_.as<uint8_t>() + off[i];
     d.rows = imgs[i].rows; d.cols = imgs[i].cols; d.stride = long(imgs[i].cols) * 3;
-    const size_t row = size_t(d.cols) * 3;
-    if (imgs[i].step == row)
-      cuda_check(cudaMemcpyAsync(d.p, imgs[i].data, row * d.rows, cudaMemcpyHostToDevice, s), "image upload");
-    else
-      cuda_check(cudaMemcpy2DAsync(d.p, row, imgs[i].data, imgs[i].step, row, d.rows, cudaMemcpyHostToDevice, s),
-                 "image upload");
-    bytes_ += row * d.rows;
+    const size_t row = size_t(d.cols) * 3, size = row * d.rows;
     imgs_[i] = d;
+    bytes_ += size;
+    if (imgs[i].step != row) {
+      flush(i + 1);
+      cuda_check(cudaMemcpy2DAsync(d.p, row, imgs[i].data, imgs[i].step, row, d.rows, cudaMemcpyHostToDevice, s), "image upload");
+      continue;
+    }
+    if (run_bytes && (imgs[i].data != imgs[run0].data + run_bytes || off[i] != off[run0] + run_bytes)) flush(i);
+    run_bytes += size;
+    if ((size & 255) != 0) flush(i + 1);   // the device slot is padded to 256 bytes: the next image cannot continue this run
   }
+  flush(n);
 }
 
 // ------------------------------------------------------------------------------------------------ det
