@@ -186,71 +186,79 @@ struct b200ocr_pool {
   std::atomic<long long> total_time_us{0};   // sum over requests of (completion - submission)
   std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
 
-  // Two slots (stream + event + job list) alternate: while slot k's DMAs run, the uploader collects and queues slot
-  // k+1's copies, then sleeps on slot k's event, hands its requests to the workers and wakes their submitters.
+  // Copies are queued on one stream as their jobs arrive, each followed by its own event; the uploader sleeps on the
+  // OLDEST copy in flight, hands that request to the workers and wakes its submitter, while the DMA engine already works
+  // on the copies behind it.  (Completing whole groups of copies at once made a submit wait for ~16 copies: 1.4 ms per
+  // request on 8 GPUs, which capped 64 submitting threads at 42 k images/s; profiles/r02_notes.md section 8.)
   void upload_loop(Device* d) {
-    struct Slot {
-      cudaStream_t stream = nullptr;
-      cudaEvent_t landed = nullptr;   // blocking wait: the uploader sleeps while its DMAs run (the host cores belong to the workers)
-      std::vector<CopyJob*> jobs;
-    } slot[2];
-    bool ok = cudaSetDevice(d->device) == cudaSuccess;
-    for (auto& sl : slot)
-      ok = ok && cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) == cudaSuccess &&
-           cudaEventCreateWithFlags(&sl.landed, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess;
+    cudaStream_t stream = nullptr;
+    bool ok = cudaSetDevice(d->device) == cudaSuccess && cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) cudaGetLastError();   // every job fails with a message below
-    auto finish = [&](Slot& sl) {
-      if (sl.jobs.empty()) return;
-      if (ok && cudaEventSynchronize(sl.landed) != cudaSuccess) {
-        const char* msg = cudaGetErrorString(cudaGetLastError());
-        for (CopyJob* j : sl.jobs) if (j->error.empty()) j->error = std::string("image clone: ") + msg;
+    std::vector<cudaEvent_t> spare;   // blocking-sync events, recycled: the uploader sleeps while its DMAs run
+    struct InFlight { CopyJob* job; cudaEvent_t landed; };
+    std::deque<InFlight> inflight;
+    std::vector<CopyJob*> fresh;
+    auto complete = [&](CopyJob* j) {
+      if (j->error.empty()) {  // the clone is on the device: hand the request to the workers ...
+        { std::lock_guard<std::mutex> lk(d->mu); d->queue.push_back(j->r); }
+        d->cv.notify_one();
       }
-      {  // the clones are on the device: hand the requests to the workers ...
-        std::lock_guard<std::mutex> lk(d->mu);
-        for (CopyJob* j : sl.jobs) if (j->error.empty()) d->queue.push_back(j->r);
-        d->copying -= int(sl.jobs.size());
-      }
-      d->cv.notify_all();
-      {  // ... then release the submitting threads (a job lives on its submitter's stack: notify under the lock)
-        std::lock_guard<std::mutex> lk(d->copy_mu);
-        for (CopyJob* j : sl.jobs) { j->done = true; j->cv.notify_one(); }
-      }
-      sl.jobs.clear();
+      d->copying -= 1;
+      // ... then release the submitting thread (the job lives on its stack: notify under the lock)
+      std::lock_guard<std::mutex> lk(d->copy_mu);
+      j->done = true;
+      j->cv.notify_one();
     };
-    for (int cur = 0;; cur ^= 1) {
-      Slot& sl = slot[cur];
-      Slot& other = slot[cur ^ 1];
-      bool stop = false;
+    while (true) {
+      fresh.clear();
       {
         std::unique_lock<std::mutex> lk(d->copy_mu);
-        // with copies in flight in the other slot, do not sleep here: take what is waiting (possibly nothing)
-        if (other.jobs.empty()) d->copy_cv.wait(lk, [&] { return !d->copy_q.empty() || !running; });
-        stop = d->copy_q.empty() && !running;
-        while (!d->copy_q.empty() && sl.jobs.size() < 32) { sl.jobs.push_back(d->copy_q.front()); d->copy_q.pop_front(); }
+        // with copies in flight do not sleep here: take what is waiting (possibly nothing) and go on completing
+        if (inflight.empty()) d->copy_cv.wait(lk, [&] { return !d->copy_q.empty() || !running; });
+        if (d->copy_q.empty() && inflight.empty()) break;   // shutting down and drained
+        while (!d->copy_q.empty() && fresh.size() < 32) { fresh.push_back(d->copy_q.front()); d->copy_q.pop_front(); }
       }
-      for (CopyJob* j : sl.jobs) {
+      for (CopyJob* j : fresh) {
+        cudaEvent_t ev = nullptr;
         try {
           if (!ok) throw std::runtime_error("the pool's copy stream could not be created");
           Request& r = *j->r;
           r.owner = &d->pixels;
           r.data = d->pixels.take(r.size, &r.cap);
-          if (j->step == j->row) cuda_check(cudaMemcpyAsync(r.data, j->src, r.size, cudaMemcpyHostToDevice, sl.stream), "image clone");
-          else cuda_check(cudaMemcpy2DAsync(r.data, j->row, j->src, j->step, j->row, r.rows, cudaMemcpyHostToDevice, sl.stream), "image clone");
+          if (j->step == j->row) cuda_check(cudaMemcpyAsync(r.data, j->src, r.size, cudaMemcpyHostToDevice, stream), "image clone");
+          else cuda_check(cudaMemcpy2DAsync(r.data, j->row, j->src, j->step, j->row, r.rows, cudaMemcpyHostToDevice, stream), "image clone");
+          if (spare.empty()) cuda_check(cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming), "cudaEventCreate");
+          else { ev = spare.back(); spare.pop_back(); }
+          cuda_check(cudaEventRecord(ev, stream), "image clone");
+          inflight.push_back(InFlight{j, ev});
         } catch (const std::exception& e) {
+          if (ev) spare.push_back(ev);
           j->error = e.what()[0] ? e.what() : "image clone failed";
+          cudaStreamSynchronize(stream);   // nothing of this job may still be reading the caller's buffer
+          cudaGetLastError();
+          complete(j);
         }
       }
-      if (ok && !sl.jobs.empty() && cudaEventRecord(sl.landed, sl.stream) != cudaSuccess) {
-        const char* msg = cudaGetErrorString(cudaGetLastError());
-        for (CopyJob* j : sl.jobs) if (j->error.empty()) j->error = std::string("image clone: ") + msg;
+      // complete the oldest copy (sleeping until it has landed), then everything that has landed since; go back for
+      // new jobs as soon as some are waiting, so that the DMA queue never runs dry
+      bool first = true;
+      while (!inflight.empty()) {
+        InFlight f = inflight.front();
+        if (first) {
+          if (cudaEventSynchronize(f.landed) != cudaSuccess) f.job->error = std::string("image clone: ") + cudaGetErrorString(cudaGetLastError());
+        } else {
+          const cudaError_t q = cudaEventQuery(f.landed);
+          if (q == cudaErrorNotReady) break;
+          if (q != cudaSuccess) f.job->error = std::string("image clone: ") + cudaGetErrorString(cudaGetLastError());
+        }
+        first = false;
+        inflight.pop_front();
+        spare.push_back(f.landed);
+        complete(f.job);
       }
-      finish(other);
-      if (stop && sl.jobs.empty()) break;   // shutting down and drained
     }
-    for (auto& sl : slot) {
-      if (sl.landed) cudaEventDestroy(sl.landed);
-      if (sl.stream) cudaStreamDestroy(sl.stream);
-    }
+    for (cudaEvent_t ev : spare) cudaEventDestroy(ev);
+    if (stream) cudaStreamDestroy(stream);
   }
 
   void loop(Device* d, Worker* w) {
