@@ -294,7 +294,7 @@ __half* Net::prepare(int n, int h, int w, const int* widths, cudaStream_t stream
     cache_.clear();
     cudaFree(arena_);
     arena_ = nullptr;
-    arena_bytes_ = align_up(need + need / 2, size_t(1) << 20);
+    arena_bytes_ = align_up(2 * need, size_t(1) << 20);  // generous: growing again means cudaFree + cudaMalloc, which stalls the whole device
     cuda_check(cudaMalloc(&arena_, arena_bytes_), "cudaMalloc activation arena");
     I = instantiate(n, h, w);
   }
