@@ -313,7 +313,9 @@ void Net::record(Inst& I, cudaStream_t s, int thresh_u8, const std::function<voi
   auto vecp = [&](int t) { return reinterpret_cast<float*>(arena_ + I.boff[plan_.tensors[t].buf]); };
   int launches = 0;
   static const bool no_se_fuse = getenv("B200OCR_NO_SE_FUSE") != nullptr;
-  static const bool no_se_apply = getenv("B200OCR_NO_SE_APPLY_FUSE") != nullptr;
+  // Applying the gate inside the pool + gate kernel (one launch less per SE block, one block per sample) measured 2.8 %
+  // SLOWER than the separate scale kernel on C4 at 192 cards per step (profiles/r02_notes.md section 13): opt-in.
+  static const bool no_se_apply = !(getenv("B200OCR_SE_APPLY_FUSE") && atoi(getenv("B200OCR_SE_APPLY_FUSE")) != 0);
   int scale_fused_at = -1;
   for (size_t li = 0; li < plan_.layers.size(); ++li) {
     if (only >= 0 && int(li) != only) continue;

@@ -133,7 +133,7 @@ class RecStage {
   int max_rows = 1024;       // rows per forward pass
   long max_cols = 400000;    // rows x padded width per forward pass (bounds the activation arena)
   int last_chunks = 0; long last_cols = 0, last_real_cols = 0;  // trace: ragged chunking of the last run()
-  double min_fill = 0.85;    // a ragged chunk is cut where its real columns / (rows x widest row) would drop below this
+  double min_fill = 0.92;    // a ragged chunk is cut where its real columns / (rows x widest row) would drop below this
   long launches = 0;
  private:
   Net net_;

@@ -72,7 +72,7 @@ VARIANTS = [
     ({"B200OCR_TMA_STORE": "1"}, True),           # same accumulators, stored through shared memory + TMA
     ({"B200OCR_CONV_PERSIST_MIN": "1000000"}, True),  # never the persistent convolution kernel
     ({"B200OCR_NO_PWCONV": "1"}, False),          # narrow 1x1 convolutions on tcgen05 instead of the mma.sync stream
-    ({"B200OCR_NO_SE_APPLY_FUSE": "1"}, True),    # SE gate applied by scale_kernel instead of the pool + gate kernel
+    ({"B200OCR_SE_APPLY_FUSE": "1"}, True),       # SE gate applied by the pool + gate kernel instead of scale_kernel
     ({"B200OCR_PDL": "0"}, True),                 # no programmatic dependent launch
     # every non-persistent 1x1 convolution as 2-CTA clusters with filter multicast
     ({"B200OCR_CONV_MULTICAST": "1", "B200OCR_CONV_MULTICAST_MIN": "1"}, True),
