@@ -144,8 +144,7 @@ struct b200ocr_pool {
   // One uploader thread per device owns the H2D clones: submitting threads hand it a job and sleep until the pixels
   // have landed.  (Issuing the copy from the submitting threads themselves -- 8 to 16 extra threads calling into the
   // CUDA runtime next to the workers -- serialised on the driver at ~115 us per image and slowed the workers' own
-  // launches three-fold: profiles/r02_notes.md section 8.)  The uploader takes every job that is waiting, queues their
-  // copies back to back on its stream and synchronises once.
+  // launches three-fold: profiles/r02_notes.md section 8.)  See upload_loop.
   struct CopyJob {
     std::shared_ptr<Request> r;
     const uint8_t* src = nullptr;
