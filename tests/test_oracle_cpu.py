@@ -366,3 +366,19 @@ def test_jpeg_oracle_equals_cv2_imdecode_bitwise(golden_dir):
     assert n == 36
     with pytest.raises(ValueError):
         jpeg_decode.decode(b"\x89PNG\r\n")
+
+
+def test_native_pool_client_builds_and_fails_loudly_without_a_gpu(models_dir, tmp_path):
+    """tools/pool_feeder (what `bench.py --pool` drives) links against the C ABI only; without a CUDA device it must
+    report the pool's error and exit non-zero -- never fall back to anything."""
+    import b200ocr
+    tools = os.path.join(ROOT, "tools")
+    subprocess.check_call(["make", "-C", tools, "all"], stdout=subprocess.DEVNULL)
+    frames = tmp_path / "frames.bin"
+    frames.write_bytes(bytes(32 * 32 * 3))
+    r = subprocess.run([os.path.join(tools, "pool_feeder"), models_dir, "rawp", str(frames), "-", "32", "32", "2", "1", "1", "4",
+                        "2", "2", "1", "1"], capture_output=True, text=True, timeout=120)
+    if b200ocr.device_count() == 0:
+        assert r.returncode != 0 and "pool_feeder" in r.stderr, (r.returncode, r.stderr)
+    else:
+        assert r.returncode == 0, r.stderr
