@@ -92,7 +92,7 @@ class Classifier {
     c.cpu_math_library_num_threads = cpu_math_library_num_threads; c.use_mkldnn = use_mkldnn;
     c.cls_thresh = cls_thresh; c.use_tensorrt = use_tensorrt; c.precision = precision.c_str();
     c.cls_batch_num = cls_batch_num;
-    cls_thresh_ = cls_thresh;
+    this->cls_thresh = cls_thresh;
     if (b200ocr_cls_create(&c, &h_) != B200OCR_OK) b200ocr_detail::fail("Classifier");
   }
   ~Classifier() { b200ocr_cls_destroy(h_); }
@@ -109,7 +109,7 @@ class Classifier {
     times.insert(times.end(), t, t + 3);
   }
 
-  double cls_thresh_ = 0.9;  // stored and, like the reference's (ocr_cls.h:76), never consulted
+  double cls_thresh = 0.9;  // public like the reference's member (ocr_cls.h:76); stored and, like there, never consulted
 
  private:
   b200ocr_cls_t h_ = nullptr;
