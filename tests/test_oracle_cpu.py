@@ -382,3 +382,30 @@ def test_native_pool_client_builds_and_fails_loudly_without_a_gpu(models_dir, tm
         assert r.returncode != 0 and "pool_feeder" in r.stderr, (r.returncode, r.stderr)
     else:
         assert r.returncode == 0, r.stderr
+
+
+def test_nn_oracle_with_the_shipped_cls_weights_reads_text_orientation(models_dir):
+    """A behavioural pin of the NN oracle (oracle/interp.py) that does not come from this repository: the cls weights
+    are the ones the reference ships (trained and exported by Paddle), and the reference uses the network to tell
+    upright text lines from lines rotated by 180 degrees (src/ocr_cls.cpp:23-106, src/ocr_worker.cpp:262-283).  Through
+    the restated operators -- conv2d + folded batch_norm, hard_swish, SE blocks, depthwise conv, adaptive pool2d, fc,
+    softmax, and the ClsResizeImg / Normalize / PermuteBatch input pipeline -- the 65-layer graph must make that decision
+    correctly and with saturated confidence on text it has never seen; a wrong operator semantic anywhere does not
+    survive that.  (Not a numerical pin: Paddle itself cannot run here, so the oracle stays "parity unpinned".)"""
+    from oracle.pipeline import OracleClassifier
+    cls = OracleClassifier(os.path.join(models_dir, "cls"), 8)
+    words = ["Invoice number 20481", "The quick brown fox", "TOTAL AMOUNT DUE", "date of birth 1987", "hello world again",
+             "Address line two", "PASSPORT No X1234567", "serial 0099-8812-AB", "customer signature", "Payment received",
+             "Nationality: Utopia", "expires 12/2031"]
+    imgs = []
+    for i, w in enumerate(words):
+        scale = 0.9 + 0.1 * (i % 4)
+        (tw, th), bl = cv2.getTextSize(w, cv2.FONT_HERSHEY_SIMPLEX, scale, 2)
+        im = np.full((th + bl + 14, tw + 20, 3), 255, np.uint8)
+        cv2.putText(im, w, (10, th + 6), cv2.FONT_HERSHEY_SIMPLEX, scale, (0, 0, 0), 2, cv2.LINE_AA)
+        imgs.append(im)
+    up_labels, up_scores = cls.run(imgs)
+    dn_labels, dn_scores = cls.run([cv2.rotate(im, cv2.ROTATE_180) for im in imgs])
+    assert up_labels == [0] * len(imgs), up_labels
+    assert dn_labels == [1] * len(imgs), dn_labels
+    assert min(up_scores) > 0.98 and min(dn_scores) > 0.98, (up_scores, dn_scores)   # the worker's cls_thresh (ocr_worker.cpp:44)
