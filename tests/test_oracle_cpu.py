@@ -409,3 +409,25 @@ def test_nn_oracle_with_the_shipped_cls_weights_reads_text_orientation(models_di
     assert up_labels == [0] * len(imgs), up_labels
     assert dn_labels == [1] * len(imgs), dn_labels
     assert min(up_scores) > 0.98 and min(dn_scores) > 0.98, (up_scores, dn_scores)   # the worker's cls_thresh (ocr_worker.cpp:44)
+
+
+def test_oracle_reproduces_the_committed_golden_vectors(models_dir, golden_dir):
+    """tests/golden/expected_stages.json (tools/make_golden.py: the oracle on the reference's own fixtures, stage by
+    stage) guards the checker itself against drift: recomputed here, boxes / labels / strings must be identical and the
+    probabilities equal to 1e-5."""
+    import golden_check
+    import make_golden
+    doc = golden_check.load(golden_dir)
+    now = make_golden.oracle_stages(models_dir, golden_dir)
+    assert [g["name"] for g in doc["images"]] == [n["name"] for n in now]
+    n_lines = 0
+    for g, n in zip(doc["images"], now):
+        golden_check.check_det(n["boxes"], g, box_tol_px=0)
+        assert n["rois"] == g["rois"] and n["cls_labels"] == g["cls_labels"] and n["rec_texts"] == g["rec_texts"]
+        assert np.allclose(n["cls_scores"], g["cls_scores"], rtol=0, atol=1e-5)
+        assert np.allclose(n["rec_scores"], g["rec_scores"], rtol=0, atol=1e-5)
+        golden_check.check_cls(n["cls_labels"], n["cls_scores"], g)
+        n_lines += golden_check.check_rec(n["rec_texts"], n["rec_scores"], g)
+    assert sum(len(g["boxes"]) for g in doc["images"]) >= 10 and n_lines >= 5   # lines decided by a margin >= 2e-2
+    ref = [g for g in doc["images"] if g["name"] == "reference_test_image"][0]
+    assert {"123456789", "Test", "PaddleOCR"} <= set(ref["rec_texts"])   # what createTestImage draws (tests/test_ocr_worker.cpp)

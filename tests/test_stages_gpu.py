@@ -193,3 +193,29 @@ def test_recognised_strings_identical_on_the_test_set(models_dir, images, oracle
             n += 1
     assert n >= 200, n
     assert conf_checked >= 0.8 * n, (conf_checked, n)
+
+
+def test_stages_match_the_committed_golden_vectors(models_dir, golden_dir):
+    """The three stages against tests/golden/expected_stages.json (tools/make_golden.py: the oracle's outputs on the
+    reference's own fixtures, committed): each stage is given the golden upstream data -- the detector the image, the
+    classifier and the recognizer the golden ROI crops, one CRNNRecognizer::Run call per image like the worker's."""
+    import b200ocr
+    import golden_check
+    import make_golden
+    doc = golden_check.load(golden_dir)
+    imgs = dict(make_golden.golden_images(golden_dir))
+    det = b200ocr.Detector(f"{models_dir}/det", limit_type="max", limit_side_len=512, det_db_thresh=0.2,
+                           det_db_box_thresh=0.4, det_db_unclip_ratio=1.8, det_db_score_mode="fast")
+    cls = b200ocr.Classifier(f"{models_dir}/cls", cls_thresh=0.98, cls_batch_num=8)
+    label_path = f"{models_dir}/rec/ppocr_keys_v1.txt"
+    rec = b200ocr.Recognizer(f"{models_dir}/rec", label_path, rec_batch_num=16, rec_img_h=28, rec_img_w=192)
+    checked = 0
+    for g in doc["images"]:
+        img = imgs[g["name"]]
+        golden_check.check_det(det.run(img), g)
+        crops = golden_check.crops_of(img, g)
+        labels, scores = cls.run(crops)
+        golden_check.check_cls(labels, scores, g)
+        texts, rscores = rec.run(crops)
+        checked += golden_check.check_rec(texts, rscores, g)
+    assert checked >= 5
