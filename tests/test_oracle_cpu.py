@@ -428,6 +428,6 @@ def test_oracle_reproduces_the_committed_golden_vectors(models_dir, golden_dir):
         assert np.allclose(n["rec_scores"], g["rec_scores"], rtol=0, atol=1e-5)
         golden_check.check_cls(n["cls_labels"], n["cls_scores"], g)
         n_lines += golden_check.check_rec(n["rec_texts"], n["rec_scores"], g)
-    assert sum(len(g["boxes"]) for g in doc["images"]) >= 10 and n_lines >= 5   # lines decided by a margin >= 2e-2
+    assert sum(len(g["boxes"]) for g in doc["images"]) >= 10 and n_lines >= 5   # lines decided by a margin >= 5e-2
     ref = [g for g in doc["images"] if g["name"] == "reference_test_image"][0]
     assert {"123456789", "Test", "PaddleOCR"} <= set(ref["rec_texts"])   # what createTestImage draws (tests/test_ocr_worker.cpp)
